@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the intermediate-frame synthesis path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 16 synthetic 1088x1920 (1080p padded to /32) frame pairs per
+GPU, 7 intermediate timesteps, fp32.  One step = one pass of the hot path over the batch:
+compute_inputs for all 7 timesteps (one fused launch) + extract_outputs/compute_output_image for all
+7 timesteps (one fused launch) = 112 interpolated frames per GPU.  The two flow U-Nets are out of
+scope (they stay on PyTorch/cuDNN); the stage-2 output is a seeded surrogate.
+
+  value      frames/s, inputs resident in HBM, device-timed with CUDA events, max over ranks
+  e2e        same metric through ssm_synthesize_host: pinned HOST buffers in, fused frames out,
+             host<->device copies inside the timed region
+  roofline   dominant kernel (flow_pack_fwd) algorithmic bytes / event-timed duration vs measured HBM peak
+  cpu_baseline  the reference's torch-op path (oracle/torch_oracle.py, kind "port") on the host cores,
+             rank 0, bounded sample
+--impl reference times that CPU path as an arm of its own.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, PAIRS, NT = 1088, 1920, 16, 7
+NPX = H * W
+WORKLOAD = "ssm_original_1080p_b16_n7"
+METRIC = "interpolated_1080p_frames_per_sec"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("flow_pack_fwd_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(sample):
+    """One bounded sample of the reference CPU path: compute_inputs + compute_output_image once per
+    timestep, as the reference's loops do (evaluate_interpolation_results.py:234-242)."""
+    from oracle import torch_oracle
+    img6, flow4, out5, t = sample
+    outs = []
+    with torch.no_grad():
+        for n in range(t.shape[1]):
+            tn = t[:, n].view(-1, 1, 1, 1)
+            in16 = torch_oracle.compute_inputs(img6, flow4, tn)
+            outs.append(torch_oracle.compute_output_image(img6, in16, out5[:, n], tn))
+    return outs
+
+
+def cpu_sample(pairs=1):
+    from ssm_b200 import synthetic
+    img6 = synthetic.frames(pairs, H, W, seed=42)
+    flow4 = synthetic.flows(pairs, H, W, 4, flow_px=20.0, seed=43)
+    out5 = synthetic.unet_out5(pairs, NT, H, W, seed=44)
+    t = synthetic.timesteps(pairs, NT)
+    return img6, flow4, out5, t
+
+
+def time_cpu_reference(steps, warmup, pairs=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = cpu_sample(pairs)
+    for _ in range(warmup):
+        cpu_reference_step(sample)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(sample)
+        times.append(time.perf_counter() - t0)
+    frames = pairs * NT
+    return frames, times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    frames, times, cores = time_cpu_reference(args.steps, args.warmup)
+    total = sum(times)
+    value = frames * len(times) / total
+    sample = "%d pair x %d timesteps at %dx%d per step (of the %d-pair workload), torch CPU ops, %d threads" % (
+        1, NT, H, W, PAIRS, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
+                   "frames_per_step": frames, "l2": "inputs_exceed_l2"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    import ssm_b200
+    from ssm_b200 import sharding, synthetic
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the synthesis path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # weak scaling: 16 pairs per GPU; the partition function gives each rank whole pairs
+    work = sharding.shard_work(PAIRS * world, NT, rank, world)
+    B = len(work)
+    assert B == PAIRS and all(t0 == 0 and t1 == NT for _, t0, t1 in work)
+    seed0 = 42 + 1000 * rank
+    img6 = synthetic.frames(B, H, W, seed=seed0, device=dev)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=seed0 + 1, device=dev)
+    out5 = synthetic.unet_out5(B, NT, H, W, seed=seed0 + 2, device=dev)
+    t = synthetic.timesteps(B, NT, device=dev)
+
+    def step():
+        with torch.no_grad():
+            in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT)
+            return ssm_b200.fuse(img6, in16, out5, t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    with torch.no_grad():
+        for k in range(K):
+            ev[k][0].record()
+            in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT)
+            ev[k][1].record()
+            frames = ssm_b200.fuse(img6, in16, out5, t)
+            ev[k][2].record()
+    end.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = start.elapsed_time(end)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = tt.item()
+    pack_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    fuse_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+    frames_per_step = B * NT * world
+    value = frames_per_step * K / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel: algorithmic bytes = (10 + 16 N) * 4 B/px per pair
+    peak, peak_src = _peaks()
+    pack_bytes = (10 + 16 * NT) * 4 * NPX * B
+    fuse_bytes = (6 + 12 * NT) * 4 * NPX * B
+    pack_gbs = pack_bytes / (pack_ms * 1e-3) / 1e9
+    fuse_gbs = fuse_bytes / (fuse_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "flow_pack_fwd_kernel<float>", "achieved": pack_gbs, "peak": peak,
+                "unit": "GB/s", "frac": pack_gbs / peak, "traffic": _traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": pack_bytes, "launch_ms": pack_ms,
+                "frac_of_nominal_8tbs": pack_gbs / 8000.0}
+    kernels = {
+        "flow_pack_fwd": {"ms": pack_ms, "algorithmic_gbs": pack_gbs, "frac_of_peak": pack_gbs / peak},
+        "fuse_fwd": {"ms": fuse_ms, "algorithmic_gbs": fuse_gbs, "frac_of_peak": fuse_gbs / peak},
+        "path": {"ms": pack_ms + fuse_ms, "algorithmic_gbs": (pack_bytes + fuse_bytes) / ((pack_ms + fuse_ms) * 1e-3) / 1e9,
+                 "frac_of_peak": (pack_bytes + fuse_bytes) / ((pack_ms + fuse_ms) * 1e-3) / 1e9 / peak},
+    }
+    del in16, frames
+
+    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_img, h_flow, h_out5 = img6.cpu().pin_memory(), flow4.cpu().pin_memory(), out5.cpu().pin_memory()
+        h_t = t.cpu()
+        ssm_b200.synthesize_host(h_img, h_flow, h_out5, h_t)          # warm-up (also pins the output once)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = ssm_b200.synthesize_host(h_img, h_flow, h_out5, h_t)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = tt.item()
+        h2d = (h_img.numel() + h_flow.numel() + h_out5.numel() + h_t.numel()) * 4
+        d2h = res.numel() * 4
+        e2e = {"value": frames_per_step * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "ssm_synthesize_host (pinned host buffers, 3-slot copy/compute pipeline)"}
+        del h_img, h_flow, h_out5, res
+
+    # ---- CPU baseline: the reference's torch-op path on the host cores, rank 0, N=1 only ------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        frames_c, times, cores = time_cpu_reference(steps=3, warmup=1)
+        best = min(times)
+        cpu_baseline = {"value": frames_c / best, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": "1 pair x %d timesteps at %dx%d, best of 3 after 1 warm-up; torch CPU ops "
+                                  "(oracle/torch_oracle.py == the reference's op sequence)" % (NT, H, W),
+                        "ms_per_frame": 1e3 * best / frames_c}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
+                       "frames_per_step": frames_per_step, "l2": "inputs_exceed_l2 (6.1 GB read, 18 GB written per step)",
+                       "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
+                       "parallelism": "pairs sharded over %d rank(s), no collective" % world},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": 2 * K, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

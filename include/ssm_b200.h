@@ -1,0 +1,145 @@
+/*
+ * ssm_b200.h -- C ABI of libssm_b200.so: the B200 (sm_100a) implementation of Super SloMo's
+ * per-pixel intermediate-frame synthesis path.
+ *
+ * The reference (SreenivasVRao/SuperSloMo-VideoInterpolation-PyTorch) has no FFI or operator
+ * registry; its boundary for this path is the Python call surface of scripts/models.  Each
+ * entry point below names the reference function it replaces.  The Python mirror of that call
+ * surface (same names, arguments and error behaviour) lives in
+ * superslomo-videointerpolation-pytorch_b200/ and reaches this ABI through ctypes; see
+ * INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer on the current CUDA device unless the entry point's name
+ *    ends in _host.  The library never allocates, frees or retains caller memory; outputs are
+ *    caller-allocated; inputs are read-only.
+ *  - Calls are asynchronous: work is enqueued on `stream` (a cudaStream_t passed as void*, NULL =
+ *    legacy default stream) and the call returns without synchronising.
+ *  - Re-entrant, no global mutable state apart from the thread-local error string.
+ *  - Return value: 0 = ok; < 0 = argument error (SSM_ERR_*); > 0 = cudaError_t of a failed
+ *    launch.  ssm_last_error() returns a message for the calling thread's last failure.  No C++
+ *    exception crosses the ABI.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Tensors are described by ssm_tensor: planes are dense (element (y, x) of a plane is at
+ * y*W + x) while pair, timestep and channel strides are free, so channel-sliced views such as
+ * input_tensor[:, 6:10] (flow_interpolation.py:402-403) are passed without a copy.
+ * Strides are in ELEMENTS of the storage dtype.
+ */
+#ifndef SSM_B200_H
+#define SSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSM_ABI_VERSION 1
+
+/* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
+#define SSM_DTYPE_F32  0
+#define SSM_DTYPE_BF16 1
+
+/* How the division by max(W-1,1) of layers.py:112-113 is rounded (SURVEY.md finding 3b):
+ * DIV = IEEE division, bit-matches the reference on CPU; RCP = multiply by fp32 1/(W-1),
+ * bit-matches the reference on CUDA (torch's div-by-Python-scalar kernel). */
+#define SSM_COORD_DIV 0
+#define SSM_COORD_RCP 1
+
+#define SSM_OK                 0
+#define SSM_ERR_NULL          -1   /* a required pointer is NULL */
+#define SSM_ERR_SHAPE         -2   /* B, N, C, H or W out of range */
+#define SSM_ERR_DTYPE         -3   /* unknown dtype / coord_mode */
+#define SSM_ERR_ALIGN         -4   /* pointer or stride not aligned for the dtype */
+#define SSM_ERR_WORKSPACE     -5   /* workspace missing or too small */
+#define SSM_ERR_UNSUPPORTED   -6
+
+typedef struct ssm_tensor {
+    void*   data;      /* first element of (pair 0, timestep 0, channel 0) */
+    int64_t stride_b;  /* elements between consecutive frame pairs / samples */
+    int64_t stride_n;  /* elements between consecutive timesteps (ignored where there is no timestep axis) */
+    int64_t stride_c;  /* elements between consecutive channels */
+} ssm_tensor;
+
+int         ssm_version(void);
+const char* ssm_last_error(void);
+
+/* ---- a1: layers.warp(x, flo)  [reference scripts/models/layers.py:73-120] --------------------
+ * out[b,c,y,x] = bilinear(img[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside,
+ * align_corners=True.  img/out: B x C x H x W, flow: B x 2 x H x W. */
+int ssm_warp_fwd(const ssm_tensor* img, const ssm_tensor* flow, const ssm_tensor* out,
+                 int B, int C, int H, int W, int dtype, int coord_mode, void* stream);
+
+/* Backward of warp (what autograd derives for layers.py:73-120).  grad_img and/or grad_flow may
+ * be NULL (not wanted).  grad_img needs a workspace of ssm_warp_bwd_workspace_bytes(B, C, H, W)
+ * (16-byte aligned); it is accumulated deterministically (bit-identical run to run). */
+int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_tensor* flow,
+                 const ssm_tensor* grad_img, const ssm_tensor* grad_flow,
+                 int B, int C, int H, int W, int dtype, int coord_mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2: FlowInterpolationModel.compute_inputs(img_tensor, flow_pred_tensor, t)
+ *      [reference scripts/models/flow_interpolation.py:338-372], batched over N timesteps so
+ *      that the loop of superslomo_r.py:167-179 and its torch.stack become one launch.
+ * img6:  B x 6 x H x W        (channels 0-2 = I0, 3-5 = I1)
+ * flow4: B x 4 x H x W        (0-1 = F01, 2-3 = F10)
+ * t:     B*N fp32 values, t[b*N + n] in (0,1)
+ * out16: B x N x 16 x H x W   [I1, g(I1,F_t1), F_t1, F_t0, g(I0,F_t0), I0] */
+int ssm_flow_pack_fwd(const ssm_tensor* img6, const ssm_tensor* flow4, const float* t,
+                      const ssm_tensor* out16, int B, int N, int H, int W,
+                      int dtype, int coord_mode, void* stream);
+
+/* Backward of a2.  grad16: B x N x 16 x H x W.  grad_flow4 (B x 4 x H x W, summed over the N
+ * timesteps) and grad_img6 (B x 6 x H x W) may be NULL.  grad_img6 needs a workspace of
+ * ssm_flow_pack_bwd_workspace_bytes(B, N, H, W). */
+int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ssm_tensor* flow4,
+                      const float* t, const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
+                      int B, int N, int H, int W, int dtype, int coord_mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3 + a4: extract_outputs + compute_output_image(img_tensor, input_tensor, output_tensor, t)
+ *      [reference scripts/models/flow_interpolation.py:374-429], batched over N timesteps
+ *      (replaces the loop of superslomo_r.py:215-238).
+ * img6:   B x 6 x H x W
+ * flows4: B x N x 4 x H x W   = input_tensor[:, 6:10] (F_t1 then F_t0), usually a strided view
+ * out5:   B x N x 5 x H x W   stage-2 U-Net output (visibility logit, dF_t1, dF_t0)
+ * out3:   B x N x 3 x H x W   fused frame */
+int ssm_fuse_fwd(const ssm_tensor* img6, const ssm_tensor* flows4, const ssm_tensor* out5,
+                 const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                 int dtype, int coord_mode, void* stream);
+
+/* Backward of a3 + a4.  grad3: B x N x 3 x H x W.  grad_out5 (B x N x 5), grad_flows4
+ * (B x N x 4: the gradient of input_tensor[:, 6:10]; the other 12 channels of that gradient are
+ * zero and are the caller's to fill) and grad_img6 (B x 6) may each be NULL.  grad_img6 needs a
+ * workspace of ssm_fuse_bwd_workspace_bytes(B, N, H, W). */
+int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const ssm_tensor* flows4,
+                 const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                 const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
+                 int B, int N, int H, int W, int dtype, int coord_mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
+ * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */
+size_t ssm_warp_bwd_workspace_bytes(int B, int C, int H, int W);
+size_t ssm_flow_pack_bwd_workspace_bytes(int B, int N, int H, int W);
+size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W);
+
+/* ---- host-buffer entry point: the whole path for one batch of frame pairs ---------------------
+ * Takes HOST pointers (pinned memory recommended), copies inputs to the device in pair-sized
+ * chunks on internal streams, runs a2 then a3+a4 for all N timesteps and copies the fused
+ * frames back, overlapping copies with kernels.  Synchronous: returns when out3_host is
+ * complete.  Dense NCHW fp32 layouts:
+ *   img6_host  B x 6 x H x W, flow4_host B x 4 x H x W, out5_host B x N x 5 x H x W,
+ *   t_host B*N floats, out3_host B x N x 3 x H x W, in16_host (optional, may be NULL)
+ *   B x N x 16 x H x W receives the packed stage-2 input.
+ * Device scratch is allocated per call with cudaMallocAsync and released before returning. */
+int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const float* out5_host,
+                        const float* t_host, float* out3_host, float* in16_host,
+                        int B, int N, int H, int W, int coord_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSM_B200_H */

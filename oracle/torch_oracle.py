@@ -1,0 +1,72 @@
+"""Torch restatement of the reference's per-pixel synthesis path (ORACLE -- test infrastructure).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package never does.
+
+The reference path is nothing but torch calls, so this restatement issues the same torch
+operations in the same order and therefore produces the same bits as the reference on the same
+device: on CPU it is the CPU-ATen reference, on a CUDA device with cuDNN disabled it is the
+CUDA-ATen reference, with cuDNN enabled the cuDNN spatial-transformer reference (SURVEY.md
+findings 3/3b).  It is also what bench.py times as the "reference CPU path" on the GPU box,
+where /root/reference does not exist.
+
+Follows:  scripts/models/layers.py:90-120 (warp)
+          scripts/models/flow_interpolation.py:349-367 (compute_inputs)
+          scripts/models/flow_interpolation.py:382-392, 402-427 (extract_outputs, compute_output_image)
+Checked against the imported reference by tests/golden/make_golden.py (bit-equal on CPU).
+"""
+import torch
+import torch.nn.functional as F
+
+
+def warp(x, flo):
+    """layers.py:73-120.  x: B x C x H x W, flo: B x 2 x H x W (channel 0 horizontal)."""
+    B, _, H, W = x.shape
+    cols = torch.arange(0, W).view(1, 1, 1, W).expand(B, 1, H, W)
+    rows = torch.arange(0, H).view(1, 1, H, 1).expand(B, 1, H, W)
+    base = torch.cat((cols, rows), 1).float().to(x.device)          # :92-99 (built on the CPU, then moved)
+    pos = base + flo                                                # :100
+    u = pos[:, 0, :, :].clone()                                     # :109-110
+    v = pos[:, 1, :, :].clone()
+    u = 2.0 * u / max(W - 1, 1) - 1.0                               # :112
+    v = 2.0 * v / max(H - 1, 1) - 1.0                               # :113
+    pos[:, 0, :, :] = u                                             # :115-116
+    pos[:, 1, :, :] = v
+    return F.grid_sample(x, pos.permute(0, 2, 3, 1), align_corners=True)   # :118-119
+
+
+def compute_inputs(img_tensor, flow_pred_tensor, t):
+    """flow_interpolation.py:338-372.  t: B x 1 x 1 x 1."""
+    f01 = flow_pred_tensor[:, 0:2]
+    f10 = flow_pred_tensor[:, 2:4]
+    ft0 = -(1 - t) * t * f01 + (t ** 2) * f10                       # :353
+    ft1 = ((1 - t) ** 2) * f01 - t * (1 - t) * f10                  # :356
+    i0 = img_tensor[:, 0:3]
+    i1 = img_tensor[:, 3:6]
+    g1 = warp(i1, ft1)                                              # :361
+    g0 = warp(i0, ft0)                                              # :362
+    return torch.cat([i1, g1, ft1, ft0, g0, i0], dim=1)             # :364-367
+
+
+def extract_outputs(output_tensor):
+    """flow_interpolation.py:374-392."""
+    v1 = torch.sigmoid(output_tensor[:, 0:1])
+    return v1, output_tensor[:, 1:3], output_tensor[:, 3:5], 1 - v1
+
+
+def compute_output_image(img_tensor, input_tensor, output_tensor, t):
+    """flow_interpolation.py:394-429."""
+    ft1 = input_tensor[:, 6:8]
+    ft0 = input_tensor[:, 8:10]
+    i0 = img_tensor[:, 0:3]
+    i1 = img_tensor[:, 3:6]
+    v1, d1, d0, v0 = extract_outputs(output_tensor)
+    r1 = ft1 + d1                                                   # :412
+    r0 = ft0 + d0                                                   # :413
+    p0 = warp(i0, r0)                                               # :416
+    p1 = warp(i1, r1)                                               # :418
+    p0 = v0 * p0                                                    # :420
+    p1 = v1 * p1                                                    # :421
+    num = (1 - t) * p0 + t * p1                                     # :423
+    den = (1 - t) * v0 + t * v1                                     # :425
+    return num / den                                                # :427

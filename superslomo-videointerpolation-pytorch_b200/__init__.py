@@ -1,0 +1,15 @@
+"""ssm_b200 -- B200 (sm_100a) implementation of Super SloMo's per-pixel intermediate-frame
+synthesis path behind the reference's own call surface (scripts/models/layers.py,
+scripts/models/flow_interpolation.py:338-429).  CUDA only; the kernels live in libssm_b200.so
+(C ABI: include/ssm_b200.h)."""
+from . import _abi
+from .functional import (flow_pack, fuse, get_coord_mode, set_coord_mode, synthesize_host, warp as warp_fn)
+from .layers import avg_pool, conv, warp
+from .flow_interpolation import SynthesisMixin, patch_reference
+
+__all__ = ["warp", "conv", "avg_pool", "flow_pack", "fuse", "synthesize_host", "SynthesisMixin",
+           "patch_reference", "set_coord_mode", "get_coord_mode", "abi_version"]
+
+
+def abi_version():
+    return int(_abi.lib().ssm_version())

@@ -1,0 +1,111 @@
+"""ctypes binding of libssm_b200.so (the C ABI declared in include/ssm_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or a call fails, a
+RuntimeError is raised.  PyTorch supplies device memory and streams only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssm_b200.so")
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+COORD_DIV, COORD_RCP = 0, 1
+
+# every symbol include/ssm_b200.h declares
+EXPORTS = (
+    "ssm_version", "ssm_last_error",
+    "ssm_warp_fwd", "ssm_warp_bwd",
+    "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
+    "ssm_fuse_fwd", "ssm_fuse_bwd",
+    "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
+    "ssm_synthesize_host",
+)
+
+
+class SsmTensor(ctypes.Structure):
+    """struct ssm_tensor of include/ssm_b200.h"""
+    _fields_ = [("data", ctypes.c_void_p), ("stride_b", ctypes.c_int64),
+                ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libssm_b200.so (once).  Raises if it has not been built -- no CPU fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libssm_b200.so is missing at %s. Build it with `python __graft_entry__.py` or "
+            "`python superslomo-videointerpolation-pytorch_b200/build.py`; this package has no "
+            "CPU or eager fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    P, I, V, Z = ctypes.POINTER(SsmTensor), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+    L.ssm_version.restype = I
+    L.ssm_last_error.restype = ctypes.c_char_p
+    L.ssm_warp_fwd.argtypes = [P, P, P, I, I, I, I, I, I, V]
+    L.ssm_warp_bwd.argtypes = [P, P, P, P, P, I, I, I, I, I, I, V, Z, V]
+    L.ssm_flow_pack_fwd.argtypes = [P, P, V, P, I, I, I, I, I, I, V]
+    L.ssm_flow_pack_bwd.argtypes = [P, P, P, V, P, P, I, I, I, I, I, I, V, Z, V]
+    L.ssm_fuse_fwd.argtypes = [P, P, P, V, P, I, I, I, I, I, I, V]
+    L.ssm_fuse_bwd.argtypes = [P, P, P, P, V, P, P, P, I, I, I, I, I, I, V, Z, V]
+    for n in ("ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes"):
+        getattr(L, n).argtypes = [I, I, I, I]
+        getattr(L, n).restype = Z
+    L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I]
+    for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd", "ssm_fuse_fwd",
+              "ssm_fuse_bwd", "ssm_synthesize_host"):
+        getattr(L, n).restype = I
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ssm_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise TypeError("ssm_b200 supports float32 and bfloat16 storage, got %s" % t.dtype)
+
+
+def desc(t, has_n):
+    """ssm_tensor for a (B, C, H, W) [has_n=False] or (B, N, C, H, W) [has_n=True] CUDA tensor whose
+    H x W planes are dense.  Returns None for t is None (an unwanted gradient)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("ssm_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+    st = t.stride()
+    W = t.shape[-1]
+    if st[-1] != 1 or st[-2] != W:
+        raise RuntimeError("ssm_b200 needs dense H x W planes (strides %s for shape %s)" % (st, tuple(t.shape)))
+    if has_n:
+        return SsmTensor(t.data_ptr(), st[0], st[1], st[2])
+    return SsmTensor(t.data_ptr(), st[0], 0, st[1])
+
+
+def ref(d):
+    return ctypes.byref(d) if d is not None else None
+
+
+def dense_planes(t):
+    """Return t itself if its planes are dense, else a contiguous copy."""
+    st = t.stride()
+    if st[-1] == 1 and st[-2] == t.shape[-1]:
+        return t
+    return t.contiguous()
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

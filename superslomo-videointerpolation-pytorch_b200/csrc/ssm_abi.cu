@@ -1,0 +1,424 @@
+// ssm_abi.cu -- the C ABI of libssm_b200.so (declared in include/ssm_b200.h): argument checks,
+// dtype / coordinate-mode dispatch and kernel launches.  CUDA only: there is no CPU path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ssm_scatter.cuh"
+
+namespace {
+
+using namespace ssm;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e > 0 ? (int)e : 1;
+}
+
+#define SSM_LAUNCH_CHECK(what)                                   \
+    do {                                                         \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);     \
+    } while (0)
+
+constexpr size_t HDR_BYTES = 256;
+constexpr long long MAX_PLANE = (1ll << 31) - (1 << 16);   // plane offsets are 32-bit
+
+Geom make_geom(int H, int W) {
+    Geom g;
+    g.H = H; g.W = W;
+    g.xnorm = (float)(W - 1 > 1 ? W - 1 : 1);
+    g.ynorm = (float)(H - 1 > 1 ? H - 1 : 1);
+    g.xinv = 1.0f / g.xnorm;
+    g.yinv = 1.0f / g.ynorm;
+    g.xm1 = (float)(W - 1);
+    g.ym1 = (float)(H - 1);
+    g.xgrad = g.xm1 / 2.0f;
+    g.ygrad = g.ym1 / 2.0f;
+    return g;
+}
+
+int check_common(int B, int N, int C, int H, int W, int dtype, int coord_mode) {
+    if (B <= 0 || N <= 0 || C <= 0 || H <= 0 || W <= 0)
+        return fail(SSM_ERR_SHAPE, "B, N, C, H, W must be positive (got B=%d N=%d C=%d H=%d W=%d)", B, N, C, H, W);
+    if ((long long)H * W > MAX_PLANE) return fail(SSM_ERR_SHAPE, "H*W too large (%d x %d)", H, W);
+    long long tiles = (long long)B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+    if (tiles > 2147483647ll) return fail(SSM_ERR_SHAPE, "too many tiles for one launch (%lld)", tiles);
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
+    if (coord_mode != SSM_COORD_DIV && coord_mode != SSM_COORD_RCP)
+        return fail(SSM_ERR_DTYPE, "unknown coord_mode %d", coord_mode);
+    return SSM_OK;
+}
+
+int check_tensor(const ssm_tensor* t, const char* name, int dtype, bool required) {
+    if (t == nullptr || t->data == nullptr) {
+        if (required) return fail(SSM_ERR_NULL, "%s is NULL", name);
+        return SSM_OK;
+    }
+    size_t esz = dtype == SSM_DTYPE_F32 ? 4 : 2;
+    if (((uintptr_t)t->data) % esz != 0) return fail(SSM_ERR_ALIGN, "%s is not aligned to its element size", name);
+    return SSM_OK;
+}
+
+template <typename T> View<const T> cview(const ssm_tensor* t) {
+    View<const T> v;
+    if (t && t->data) { v.p = (const T*)t->data; v.sb = t->stride_b; v.sn = t->stride_n; v.sc = t->stride_c; }
+    else { v.p = nullptr; v.sb = v.sn = v.sc = 0; }
+    return v;
+}
+template <typename T> View<T> mview(const ssm_tensor* t) {
+    View<T> v;
+    if (t && t->data) { v.p = (T*)t->data; v.sb = t->stride_b; v.sn = t->stride_n; v.sc = t->stride_c; }
+    else { v.p = nullptr; v.sb = v.sn = v.sc = 0; }
+    return v;
+}
+
+unsigned tile_grid(int B, int H, int W) {
+    return (unsigned)((long long)B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W));
+}
+
+int count_bits_for(long long addends) {   // bits needed to hold `addends` unit contributions
+    int b = 1;
+    while ((1ll << b) <= addends) ++b;
+    return b;
+}
+
+// dispatch helper: calls f.template run<T, MODE>() for the runtime dtype / coord_mode
+template <typename F> int dispatch(int dtype, int mode, F&& f) {
+    if (dtype == SSM_DTYPE_F32)
+        return mode == SSM_COORD_DIV ? f.template run<float, SSM_COORD_DIV>() : f.template run<float, SSM_COORD_RCP>();
+    return mode == SSM_COORD_DIV ? f.template run<__nv_bfloat16, SSM_COORD_DIV>()
+                                 : f.template run<__nv_bfloat16, SSM_COORD_RCP>();
+}
+
+unsigned finalize_grid(long long total) {
+    long long blocks = (total + 255) / 256;
+    long long cap = 148ll * 16;
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct WarpFwd {
+    const ssm_tensor *img, *flow, *out; int B, C, H, W; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        warp_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img), cview<T>(flow), mview<T>(out), C, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_warp_fwd");
+        return SSM_OK;
+    }
+};
+
+struct WarpBwd {
+    const ssm_tensor *gout, *img, *flow, *gimg, *gflow; int B, C, H, W; void* ws; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        const Geom g = make_geom(H, W);
+        const bool want_img = gimg && gimg->data, want_flow = gflow && gflow->data;
+        ScatterHdr* hdr = want_img ? (ScatterHdr*)ws : nullptr;
+        const long long npx = (long long)H * W;
+        long long* acc = want_img ? (long long*)((char*)ws + HDR_BYTES) : nullptr;
+        if (want_img) {
+            cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * C * npx, s);
+            if (e != cudaSuccess) return cuda_fail(e, "ssm_warp_bwd memset");
+        }
+        if (want_flow) {
+            warp_bwd_flow_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(gout), cview<T>(img), cview<T>(flow), mview<T>(gflow), C, g, hdr);
+            SSM_LAUNCH_CHECK("ssm_warp_bwd (flow)");
+        } else if (want_img) {
+            absmax_kernel<T><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(cview<T>(gout), C, g, hdr);
+            SSM_LAUNCH_CHECK("ssm_warp_bwd (absmax)");
+        }
+        if (want_img) {
+            const int cb = count_bits_for(npx);
+            warp_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(gout), cview<T>(flow), acc, C, g, hdr, cb);
+            SSM_LAUNCH_CHECK("ssm_warp_bwd (scatter)");
+            const long long total = (long long)B * C * npx;
+            scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg), C, npx, total, hdr, cb);
+            SSM_LAUNCH_CHECK("ssm_warp_bwd (finalize)");
+        }
+        return SSM_OK;
+    }
+};
+
+struct PackFwd {
+    const ssm_tensor *img6, *flow4; const float* t; const ssm_tensor* out16; int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        flow_pack_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img6), cview<T>(flow4), t, mview<T>(out16), N, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_flow_pack_fwd");
+        return SSM_OK;
+    }
+};
+
+struct PackBwd {
+    const ssm_tensor *g16, *img6, *flow4; const float* t; const ssm_tensor *gflow4, *gimg6;
+    int B, N, H, W; void* ws; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        const Geom g = make_geom(H, W);
+        const bool want_img = gimg6 && gimg6->data;
+        const long long npx = (long long)H * W;
+        if (!want_img) {
+            flow_pack_bwd_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(g16), cview<T>(img6), cview<T>(flow4), t, mview<T>(gflow4), nullptr, nullptr, N, g);
+            SSM_LAUNCH_CHECK("ssm_flow_pack_bwd");
+            return SSM_OK;
+        }
+        ScatterHdr* hdr = (ScatterHdr*)ws;
+        long long* acc = (long long*)((char*)ws + HDR_BYTES);
+        float* direct = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
+        cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
+        if (e != cudaSuccess) return cuda_fail(e, "ssm_flow_pack_bwd memset");
+        flow_pack_bwd_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g16), cview<T>(img6), cview<T>(flow4), t, mview<T>(gflow4), direct, hdr, N, g);
+        SSM_LAUNCH_CHECK("ssm_flow_pack_bwd");
+        const int cb = count_bits_for((long long)N * npx);
+        flow_pack_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g16), cview<T>(flow4), t, acc, N, g, hdr, cb);
+        SSM_LAUNCH_CHECK("ssm_flow_pack_bwd (scatter)");
+        const long long total = (long long)B * 6 * npx;
+        scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, direct, mview<T>(gimg6), 6, npx, total, hdr, cb);
+        SSM_LAUNCH_CHECK("ssm_flow_pack_bwd (finalize)");
+        return SSM_OK;
+    }
+};
+
+struct FuseFwd {
+    const ssm_tensor *img6, *flows4, *out5; const float* t; const ssm_tensor* out3; int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        fuse_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(out3), N, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_fuse_fwd");
+        return SSM_OK;
+    }
+};
+
+struct FuseBwd {
+    const ssm_tensor *g3, *img6, *flows4, *out5; const float* t; const ssm_tensor *gout5, *gflows4, *gimg6;
+    int B, N, H, W; void* ws; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        const Geom g = make_geom(H, W);
+        const bool want_img = gimg6 && gimg6->data;
+        const long long npx = (long long)H * W;
+        if (!want_img) {
+            fuse_bwd_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(g3), cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
+                mview<T>(gflows4), nullptr, nullptr, N, g);
+            SSM_LAUNCH_CHECK("ssm_fuse_bwd");
+            return SSM_OK;
+        }
+        ScatterHdr* hdr = (ScatterHdr*)ws;
+        long long* acc = (long long*)((char*)ws + HDR_BYTES);
+        float* stage = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
+        cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
+        if (e != cudaSuccess) return cuda_fail(e, "ssm_fuse_bwd memset");
+        fuse_bwd_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g3), cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
+            mview<T>(gflows4), stage, hdr, N, g);
+        SSM_LAUNCH_CHECK("ssm_fuse_bwd");
+        const int cb = count_bits_for((long long)N * npx);
+        fuse_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            stage, cview<T>(flows4), cview<T>(out5), acc, N, g, hdr, cb);
+        SSM_LAUNCH_CHECK("ssm_fuse_bwd (scatter)");
+        const long long total = (long long)B * 6 * npx;
+        scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg6), 6, npx, total, hdr, cb);
+        SSM_LAUNCH_CHECK("ssm_fuse_bwd (finalize)");
+        return SSM_OK;
+    }
+};
+
+#define SSM_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != SSM_OK) return rc__; \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int ssm_version(void) { return SSM_ABI_VERSION; }
+
+const char* ssm_last_error(void) { return g_err; }
+
+size_t ssm_warp_bwd_workspace_bytes(int B, int C, int H, int W) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return HDR_BYTES + sizeof(long long) * (size_t)B * C * H * W;
+}
+size_t ssm_flow_pack_bwd_workspace_bytes(int B, int N, int H, int W) {
+    if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
+    return HDR_BYTES + (sizeof(long long) + sizeof(float)) * (size_t)B * 6 * H * W;
+}
+size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W) {
+    if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
+    return HDR_BYTES + sizeof(long long) * (size_t)B * 6 * H * W + sizeof(float) * (size_t)B * N * 6 * H * W;
+}
+
+int ssm_warp_fwd(const ssm_tensor* img, const ssm_tensor* flow, const ssm_tensor* out,
+                 int B, int C, int H, int W, int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_common(B, 1, C, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(img, "img", dtype, true));
+    SSM_TRY(check_tensor(flow, "flow", dtype, true));
+    SSM_TRY(check_tensor(out, "out", dtype, true));
+    return dispatch(dtype, coord_mode, WarpFwd{img, flow, out, B, C, H, W, (cudaStream_t)stream});
+}
+
+int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_tensor* flow,
+                 const ssm_tensor* grad_img, const ssm_tensor* grad_flow,
+                 int B, int C, int H, int W, int dtype, int coord_mode,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_common(B, 1, C, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(grad_out, "grad_out", dtype, true));
+    SSM_TRY(check_tensor(img, "img", dtype, true));
+    SSM_TRY(check_tensor(flow, "flow", dtype, true));
+    SSM_TRY(check_tensor(grad_img, "grad_img", dtype, false));
+    SSM_TRY(check_tensor(grad_flow, "grad_flow", dtype, false));
+    if (grad_img && grad_img->data) {
+        if (!workspace || workspace_bytes < ssm_warp_bwd_workspace_bytes(B, C, H, W))
+            return fail(SSM_ERR_WORKSPACE, "ssm_warp_bwd: grad_img needs %zu workspace bytes, got %zu",
+                        ssm_warp_bwd_workspace_bytes(B, C, H, W), workspace ? workspace_bytes : (size_t)0);
+        if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
+    }
+    return dispatch(dtype, coord_mode,
+                    WarpBwd{grad_out, img, flow, grad_img, grad_flow, B, C, H, W, workspace, (cudaStream_t)stream});
+}
+
+int ssm_flow_pack_fwd(const ssm_tensor* img6, const ssm_tensor* flow4, const float* t,
+                      const ssm_tensor* out16, int B, int N, int H, int W,
+                      int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_common(B, N, 16, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_tensor(out16, "out16", dtype, true));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    return dispatch(dtype, coord_mode, PackFwd{img6, flow4, t, out16, B, N, H, W, (cudaStream_t)stream});
+}
+
+int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ssm_tensor* flow4,
+                      const float* t, const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
+                      int B, int N, int H, int W, int dtype, int coord_mode,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_common(B, N, 16, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(grad16, "grad16", dtype, true));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_tensor(grad_flow4, "grad_flow4", dtype, false));
+    SSM_TRY(check_tensor(grad_img6, "grad_img6", dtype, false));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    if (grad_img6 && grad_img6->data) {
+        if (!workspace || workspace_bytes < ssm_flow_pack_bwd_workspace_bytes(B, N, H, W))
+            return fail(SSM_ERR_WORKSPACE, "ssm_flow_pack_bwd: grad_img6 needs %zu workspace bytes, got %zu",
+                        ssm_flow_pack_bwd_workspace_bytes(B, N, H, W), workspace ? workspace_bytes : (size_t)0);
+        if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
+    }
+    return dispatch(dtype, coord_mode, PackBwd{grad16, img6, flow4, t, grad_flow4, grad_img6, B, N, H, W,
+                                               workspace, (cudaStream_t)stream});
+}
+
+int ssm_fuse_fwd(const ssm_tensor* img6, const ssm_tensor* flows4, const ssm_tensor* out5,
+                 const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                 int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flows4, "flows4", dtype, true));
+    SSM_TRY(check_tensor(out5, "out5", dtype, true));
+    SSM_TRY(check_tensor(out3, "out3", dtype, true));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    return dispatch(dtype, coord_mode, FuseFwd{img6, flows4, out5, t, out3, B, N, H, W, (cudaStream_t)stream});
+}
+
+int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const ssm_tensor* flows4,
+                 const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                 const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
+                 int B, int N, int H, int W, int dtype, int coord_mode,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(grad3, "grad3", dtype, true));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flows4, "flows4", dtype, true));
+    SSM_TRY(check_tensor(out5, "out5", dtype, true));
+    SSM_TRY(check_tensor(grad_out5, "grad_out5", dtype, false));
+    SSM_TRY(check_tensor(grad_flows4, "grad_flows4", dtype, false));
+    SSM_TRY(check_tensor(grad_img6, "grad_img6", dtype, false));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    if (grad_img6 && grad_img6->data) {
+        if (!workspace || workspace_bytes < ssm_fuse_bwd_workspace_bytes(B, N, H, W))
+            return fail(SSM_ERR_WORKSPACE, "ssm_fuse_bwd: grad_img6 needs %zu workspace bytes, got %zu",
+                        ssm_fuse_bwd_workspace_bytes(B, N, H, W), workspace ? workspace_bytes : (size_t)0);
+        if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
+    }
+    return dispatch(dtype, coord_mode, FuseBwd{grad3, img6, flows4, out5, t, grad_out5, grad_flows4, grad_img6,
+                                               B, N, H, W, workspace, (cudaStream_t)stream});
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry point: pair-sized chunks, three slots of device scratch on three streams, so
+// the H2D copy of pair b+1, the kernels of pair b and the D2H copy of pair b-1 overlap.
+int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const float* out5_host,
+                        const float* t_host, float* out3_host, float* in16_host,
+                        int B, int N, int H, int W, int coord_mode) {
+    SSM_TRY(check_common(B, N, 16, H, W, SSM_DTYPE_F32, coord_mode));
+    if (!img6_host || !flow4_host || !out5_host || !t_host || !out3_host)
+        return fail(SSM_ERR_NULL, "ssm_synthesize_host: a required host pointer is NULL");
+    if (N > 64) return fail(SSM_ERR_SHAPE, "ssm_synthesize_host: N must be <= 64 (got %d)", N);
+    const size_t npx = (size_t)H * W;
+    const size_t per_pair = (size_t)(6 + 4 + 5 * N + 16 * N + 3 * N) * npx * sizeof(float) + 256;
+    const int slots = B < 3 ? B : 3;
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    char* scratch = nullptr;
+    int rc = SSM_OK;
+    cudaError_t e = cudaMalloc((void**)&scratch, per_pair * slots);
+    if (e != cudaSuccess) return cuda_fail(e, "ssm_synthesize_host cudaMalloc");
+    for (int i = 0; i < slots && rc == SSM_OK; ++i) {
+        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host cudaStreamCreate");
+    }
+    for (int b = 0; b < B && rc == SSM_OK; ++b) {
+        const int k = b % slots;
+        cudaStream_t s = st[k];
+        float* d_img = (float*)(scratch + per_pair * k);
+        float* d_flow = d_img + 6 * npx;
+        float* d_out5 = d_flow + 4 * npx;
+        float* d_in16 = d_out5 + (size_t)5 * N * npx;
+        float* d_out3 = d_in16 + (size_t)16 * N * npx;
+        float* d_t = d_out3 + (size_t)3 * N * npx;
+#define SSM_H(expr) if (rc == SSM_OK && (e = (expr)) != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host " #expr)
+        SSM_H(cudaMemcpyAsync(d_img, img6_host + (size_t)b * 6 * npx, 6 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_flow, flow4_host + (size_t)b * 4 * npx, 4 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_out5, out5_host + (size_t)b * N * 5 * npx, (size_t)N * 5 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_t, t_host + (size_t)b * N, N * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (rc != SSM_OK) break;
+        ssm_tensor T_img{d_img, (int64_t)(6 * npx), 0, (int64_t)npx};
+        ssm_tensor T_flow{d_flow, (int64_t)(4 * npx), 0, (int64_t)npx};
+        ssm_tensor T_out5{d_out5, (int64_t)(5 * N * npx), (int64_t)(5 * npx), (int64_t)npx};
+        ssm_tensor T_in16{d_in16, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
+        ssm_tensor T_fl4{d_in16 + 6 * npx, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
+        ssm_tensor T_out3{d_out3, (int64_t)(3 * N * npx), (int64_t)(3 * npx), (int64_t)npx};
+        rc = ssm_flow_pack_fwd(&T_img, &T_flow, d_t, &T_in16, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
+        if (rc == SSM_OK) rc = ssm_fuse_fwd(&T_img, &T_fl4, &T_out5, d_t, &T_out3, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
+        SSM_H(cudaMemcpyAsync(out3_host + (size_t)b * N * 3 * npx, d_out3, (size_t)N * 3 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (in16_host)
+            SSM_H(cudaMemcpyAsync(in16_host + (size_t)b * N * 16 * npx, d_in16, (size_t)N * 16 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));
+#undef SSM_H
+    }
+    for (int i = 0; i < slots; ++i)
+        if (st[i]) {
+            e = cudaStreamSynchronize(st[i]);
+            if (e != cudaSuccess && rc == SSM_OK) rc = cuda_fail(e, "ssm_synthesize_host sync");
+            cudaStreamDestroy(st[i]);
+        }
+    cudaFree(scratch);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""Drop-in for the per-pixel methods of the reference's FlowInterpolationModel
+(scripts/models/flow_interpolation.py:338-429).
+
+`SynthesisMixin` carries `compute_inputs`, `extract_outputs` and `compute_output_image` with the
+reference's names, argument order and shapes; mixing it into (or patching it onto) the reference's
+FlowInterpolationModel replaces ~110 ATen launches per call by one fused sm_100a kernel each.  The
+`*_batched` methods are the timestep-batched forms used by the new forward loop: they take all N
+intermediate times of a pair in one launch.
+"""
+import torch
+
+from . import functional as F_ssm
+
+
+class SynthesisMixin:
+    """Per-pixel synthesis methods; no parameters, no state."""
+
+    def compute_inputs(self, img_tensor, flow_pred_tensor, t):
+        """flow_interpolation.py:338.  img_tensor B x 6 x H x W, flow_pred_tensor B x 4 x H x W,
+        t B x 1 x 1 x 1 (per-sample time in (0,1)) -> B x 16 x H x W."""
+        out = F_ssm.flow_pack(img_tensor, flow_pred_tensor, t, n_timesteps=1)
+        return out[:, 0]
+
+    def compute_inputs_batched(self, img_tensor, flow_pred_tensor, t):
+        """All N timesteps of every pair at once.  t: B x N -> B x N x 16 x H x W."""
+        t = torch.as_tensor(t)
+        n = t.numel() // img_tensor.shape[0]
+        return F_ssm.flow_pack(img_tensor, flow_pred_tensor, t, n_timesteps=n)
+
+    def extract_outputs(self, output_tensor):
+        """flow_interpolation.py:374.  Returns (v_1t, dflow_t1, dflow_t0, v_0t).  Kept for callers that
+        want the pieces (losses.py:80-101, superslomo_r.py:129-140); compute_output_image does not
+        call it -- the sigmoid is fused into the kernel."""
+        v_1t = torch.sigmoid(output_tensor[:, 0:1])
+        return v_1t, output_tensor[:, 1:3], output_tensor[:, 3:5], 1 - v_1t
+
+    def compute_output_image(self, img_tensor, input_tensor, output_tensor, t):
+        """flow_interpolation.py:394.  img_tensor B x 6, input_tensor B x 16, output_tensor B x 5
+        (x H x W), t B x 1 x 1 x 1 -> fused frame B x 3 x H x W."""
+        out = F_ssm.fuse(img_tensor, input_tensor.unsqueeze(1), output_tensor.unsqueeze(1), t)
+        return out[:, 0]
+
+    def compute_output_image_batched(self, img_tensor, input_tensor, output_tensor, t):
+        """input_tensor B x N x 16, output_tensor B x N x 5, t B x N -> B x N x 3 x H x W."""
+        return F_ssm.fuse(img_tensor, input_tensor, output_tensor, t)
+
+
+def patch_reference(flow_interpolation_module, layers_module=None, losses_module=None):
+    """Install the B200 path into an imported copy of the reference's scripts/models package:
+
+        from models import flow_interpolation, layers, losses
+        ssm_b200.patch_reference(flow_interpolation, layers, losses)
+
+    Replaces FlowInterpolationModel.{compute_inputs, extract_outputs, compute_output_image} and the
+    module-level `warp` names the reference calls (flow_interpolation.py:9, losses.py:8)."""
+    from .layers import warp
+    cls = flow_interpolation_module.FlowInterpolationModel
+    for name in ("compute_inputs", "extract_outputs", "compute_output_image",
+                 "compute_inputs_batched", "compute_output_image_batched"):
+        setattr(cls, name, getattr(SynthesisMixin, name))
+    flow_interpolation_module.warp = warp
+    for mod in (layers_module, losses_module):
+        if mod is not None:
+            mod.warp = warp

@@ -1,0 +1,270 @@
+"""Differentiable torch entry points over the C ABI (include/ssm_b200.h).
+
+The reference has no hand-written backward: its path is differentiable because it is made of
+torch ops (scripts/models/layers.py:73-120, scripts/models/flow_interpolation.py:338-429).  Here
+each fused kernel pair is a torch.autograd.Function with gradients for every floating input
+except t, which is what autograd derives for the reference.
+
+All functions require CUDA tensors; nothing here computes on the CPU.
+"""
+import ctypes
+
+import torch
+
+from . import _abi
+
+_COORD_MODES = {"cpu": _abi.COORD_DIV, "div": _abi.COORD_DIV, "cuda": _abi.COORD_RCP, "rcp": _abi.COORD_RCP}
+_default_coord_mode = _abi.COORD_DIV
+
+
+def set_coord_mode(mode):
+    """Select which reference bit-pattern the sampling coordinates follow (SURVEY.md finding 3b).
+
+    "cpu" / "div": IEEE division by max(W-1,1)  -- bit-matches the reference run on CPU (default)
+    "cuda" / "rcp": multiply by fp32 1/(W-1)     -- bit-matches the reference run on CUDA (ATen)
+    """
+    global _default_coord_mode
+    _default_coord_mode = _resolve_mode(mode)
+
+
+def get_coord_mode():
+    return _default_coord_mode
+
+
+def _resolve_mode(mode):
+    if mode is None:
+        return _default_coord_mode
+    if isinstance(mode, str):
+        return _COORD_MODES[mode.lower()]
+    if mode in (_abi.COORD_DIV, _abi.COORD_RCP):
+        return int(mode)
+    raise ValueError("unknown coord mode %r" % (mode,))
+
+
+def _same(*ts):
+    t0 = ts[0]
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("ssm_b200 runs on CUDA tensors only -- there is no CPU fallback "
+                               "(got a tensor on %s)" % t.device)
+    for t in ts[1:]:
+        if t.dtype != t0.dtype or t.device != t0.device:
+            raise RuntimeError("ssm_b200: all tensors of a call must share dtype and device "
+                               "(got %s/%s and %s/%s)" % (t0.dtype, t0.device, t.dtype, t.device))
+
+
+def _workspace(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def _t_vector(t, count, device):
+    """t as `count` contiguous fp32 values on `device` (t is never differentiated)."""
+    t = torch.as_tensor(t).detach()
+    t = t.to(device=device, dtype=torch.float32).reshape(-1)
+    if t.numel() == 1 and count > 1:
+        t = t.expand(count)
+    if t.numel() != count:
+        raise RuntimeError("ssm_b200: t has %d values, expected %d (one per pair and timestep)" % (t.numel(), count))
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+class _Warp(torch.autograd.Function):
+    """layers.warp(x, flo) -- reference scripts/models/layers.py:73-120"""
+
+    @staticmethod
+    def forward(ctx, x, flo, mode):
+        _same(x, flo)
+        x, flo = _abi.dense_planes(x), _abi.dense_planes(flo)
+        B, C, H, W = x.shape
+        if flo.shape != (B, 2, H, W):
+            raise RuntimeError("warp: flo must be B x 2 x H x W, got %s for x %s" % (tuple(flo.shape), tuple(x.shape)))
+        out = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _abi.lib().ssm_warp_fwd(_abi.ref(_abi.desc(x, False)), _abi.ref(_abi.desc(flo, False)),
+                                         _abi.ref(_abi.desc(out, False)), B, C, H, W, _abi.dtype_code(x), mode,
+                                         _abi.stream_ptr(x.device))
+        _abi.check(rc, "ssm_warp_fwd")
+        ctx.save_for_backward(x, flo)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, flo = ctx.saved_tensors
+        B, C, H, W = x.shape
+        need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_x or need_f):
+            return None, None, None
+        gout = _abi.dense_planes(gout.to(x.dtype))
+        gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need_x else None
+        gf = torch.empty_like(flo, memory_format=torch.contiguous_format) if need_f else None
+        L = _abi.lib()
+        ws, ws_ptr, ws_bytes = None, None, 0
+        if need_x:
+            ws_bytes = L.ssm_warp_bwd_workspace_bytes(B, C, H, W)
+            ws = _workspace(ws_bytes, x.device)
+            ws_ptr = ctypes.c_void_p(ws.data_ptr())
+        with torch.cuda.device(x.device):
+            rc = L.ssm_warp_bwd(_abi.ref(_abi.desc(gout, False)), _abi.ref(_abi.desc(x, False)),
+                                _abi.ref(_abi.desc(flo, False)), _abi.ref(_abi.desc(gx, False)),
+                                _abi.ref(_abi.desc(gf, False)), B, C, H, W, _abi.dtype_code(x), ctx.mode,
+                                ws_ptr, ws_bytes, _abi.stream_ptr(x.device))
+        _abi.check(rc, "ssm_warp_bwd")
+        return gx, gf, None
+
+
+def warp(x, flo, coord_mode=None):
+    """Backward-warp image x (B x C x H x W) by flow flo (B x 2 x H x W; channel 0 horizontal)."""
+    return _Warp.apply(x, flo, _resolve_mode(coord_mode))
+
+
+# ---------------------------------------------------------------------------------------------
+class _FlowPack(torch.autograd.Function):
+    """compute_inputs for N timesteps -- reference scripts/models/flow_interpolation.py:338-372"""
+
+    @staticmethod
+    def forward(ctx, img6, flow4, tvec, N, mode):
+        _same(img6, flow4)
+        img6, flow4 = _abi.dense_planes(img6), _abi.dense_planes(flow4)
+        B, C6, H, W = img6.shape
+        if C6 != 6 or flow4.shape != (B, 4, H, W):
+            raise RuntimeError("compute_inputs: expected img B x 6 x H x W and flow B x 4 x H x W, got %s and %s"
+                               % (tuple(img6.shape), tuple(flow4.shape)))
+        out = torch.empty((B, N, 16, H, W), dtype=img6.dtype, device=img6.device)
+        with torch.cuda.device(img6.device):
+            rc = _abi.lib().ssm_flow_pack_fwd(_abi.ref(_abi.desc(img6, False)), _abi.ref(_abi.desc(flow4, False)),
+                                              ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(out, True)),
+                                              B, N, H, W, _abi.dtype_code(img6), mode, _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_flow_pack_fwd")
+        ctx.save_for_backward(img6, flow4, tvec)
+        ctx.N, ctx.mode = N, mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g16):
+        img6, flow4, tvec = ctx.saved_tensors
+        B, _, H, W = img6.shape
+        N = ctx.N
+        need_i, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_i or need_f):
+            return None, None, None, None, None
+        g16 = _abi.dense_planes(g16.to(img6.dtype))
+        gi = torch.empty_like(img6, memory_format=torch.contiguous_format) if need_i else None
+        gf = torch.empty_like(flow4, memory_format=torch.contiguous_format) if need_f else None
+        L = _abi.lib()
+        ws, ws_ptr, ws_bytes = None, None, 0
+        if need_i:
+            ws_bytes = L.ssm_flow_pack_bwd_workspace_bytes(B, N, H, W)
+            ws = _workspace(ws_bytes, img6.device)
+            ws_ptr = ctypes.c_void_p(ws.data_ptr())
+        with torch.cuda.device(img6.device):
+            rc = L.ssm_flow_pack_bwd(_abi.ref(_abi.desc(g16, True)), _abi.ref(_abi.desc(img6, False)),
+                                     _abi.ref(_abi.desc(flow4, False)), ctypes.c_void_p(tvec.data_ptr()),
+                                     _abi.ref(_abi.desc(gf, False)), _abi.ref(_abi.desc(gi, False)),
+                                     B, N, H, W, _abi.dtype_code(img6), ctx.mode, ws_ptr, ws_bytes,
+                                     _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_flow_pack_bwd")
+        return gi, gf, None, None, None
+
+
+def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None):
+    """Stage-2 input for n_timesteps intermediate times of every pair: B x N x 16 x H x W.
+
+    t holds B*N values (t[b, n]); a single value is broadcast."""
+    B = img6.shape[0]
+    tvec = _t_vector(t, B * n_timesteps, img6.device)
+    return _FlowPack.apply(img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode))
+
+
+# ---------------------------------------------------------------------------------------------
+class _Fuse(torch.autograd.Function):
+    """extract_outputs + compute_output_image for N timesteps -- flow_interpolation.py:374-429"""
+
+    @staticmethod
+    def forward(ctx, img6, in16, out5, tvec, mode):
+        _same(img6, in16, out5)
+        img6, in16, out5 = _abi.dense_planes(img6), _abi.dense_planes(in16), _abi.dense_planes(out5)
+        B, C6, H, W = img6.shape
+        N = in16.shape[1]
+        if C6 != 6 or in16.shape != (B, N, 16, H, W) or out5.shape != (B, N, 5, H, W):
+            raise RuntimeError("compute_output_image: expected img B x 6, input B x N x 16, output B x N x 5 "
+                               "(x H x W), got %s, %s, %s" % (tuple(img6.shape), tuple(in16.shape), tuple(out5.shape)))
+        out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
+        flows4 = in16[:, :, 6:10]
+        with torch.cuda.device(img6.device):
+            rc = _abi.lib().ssm_fuse_fwd(_abi.ref(_abi.desc(img6, False)), _abi.ref(_abi.desc(flows4, True)),
+                                         _abi.ref(_abi.desc(out5, True)), ctypes.c_void_p(tvec.data_ptr()),
+                                         _abi.ref(_abi.desc(out, True)), B, N, H, W, _abi.dtype_code(img6), mode,
+                                         _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_fwd")
+        ctx.save_for_backward(img6, in16, out5, tvec)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g3):
+        img6, in16, out5, tvec = ctx.saved_tensors
+        B, _, H, W = img6.shape
+        N = in16.shape[1]
+        need_i, need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_i or need_x or need_y):
+            return None, None, None, None, None
+        g3 = _abi.dense_planes(g3.to(img6.dtype))
+        gi = torch.empty_like(img6, memory_format=torch.contiguous_format) if need_i else None
+        gy = torch.empty_like(out5, memory_format=torch.contiguous_format) if need_y else None
+        gx = None
+        gx_flows = None
+        if need_x:
+            # the gradient of the 16-channel tensor is zero outside channels 6:10
+            gx = torch.zeros_like(in16, memory_format=torch.contiguous_format)
+            gx_flows = gx[:, :, 6:10]
+        L = _abi.lib()
+        ws, ws_ptr, ws_bytes = None, None, 0
+        if need_i:
+            ws_bytes = L.ssm_fuse_bwd_workspace_bytes(B, N, H, W)
+            ws = _workspace(ws_bytes, img6.device)
+            ws_ptr = ctypes.c_void_p(ws.data_ptr())
+        with torch.cuda.device(img6.device):
+            rc = L.ssm_fuse_bwd(_abi.ref(_abi.desc(g3, True)), _abi.ref(_abi.desc(img6, False)),
+                                _abi.ref(_abi.desc(in16[:, :, 6:10], True)), _abi.ref(_abi.desc(out5, True)),
+                                ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(gy, True)),
+                                _abi.ref(_abi.desc(gx_flows, True)), _abi.ref(_abi.desc(gi, False)),
+                                B, N, H, W, _abi.dtype_code(img6), ctx.mode, ws_ptr, ws_bytes,
+                                _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_bwd")
+        return gi, gx, gy, None, None
+
+
+def fuse(img6, in16, out5, t, coord_mode=None):
+    """Fused frames for every (pair, timestep): img6 B x 6, in16 B x N x 16, out5 B x N x 5 -> B x N x 3."""
+    B, N = in16.shape[0], in16.shape[1]
+    tvec = _t_vector(t, B * N, img6.device)
+    return _Fuse.apply(img6, in16, out5, tvec, _resolve_mode(coord_mode))
+
+
+# ---------------------------------------------------------------------------------------------
+def synthesize_host(img6, flow4, out5, t, coord_mode=None, return_inputs=False):
+    """Whole path on HOST tensors (pinned memory recommended) through ssm_synthesize_host: copies
+    in, runs both fused kernels for all N timesteps of every pair, copies the frames out.
+
+    img6 B x 6 x H x W, flow4 B x 4 x H x W, out5 B x N x 5 x H x W, t B*N values; fp32 CPU tensors.
+    Returns out3 B x N x 3 x H x W (and in16 B x N x 16 x H x W if return_inputs) as pinned CPU tensors.
+    """
+    for name, x in (("img6", img6), ("flow4", flow4), ("out5", out5)):
+        if x.device.type != "cpu" or x.dtype != torch.float32 or not x.is_contiguous():
+            raise RuntimeError("synthesize_host: %s must be a contiguous fp32 CPU tensor" % name)
+    B, _, H, W = img6.shape
+    N = out5.shape[1]
+    tv = torch.as_tensor(t, dtype=torch.float32).reshape(-1).contiguous()
+    if tv.numel() != B * N:
+        raise RuntimeError("synthesize_host: t needs B*N values")
+    pin = torch.cuda.is_available()
+    out3 = torch.empty((B, N, 3, H, W), dtype=torch.float32, pin_memory=pin)
+    in16 = torch.empty((B, N, 16, H, W), dtype=torch.float32, pin_memory=pin) if return_inputs else None
+    rc = _abi.lib().ssm_synthesize_host(
+        ctypes.c_void_p(img6.data_ptr()), ctypes.c_void_p(flow4.data_ptr()), ctypes.c_void_p(out5.data_ptr()),
+        ctypes.c_void_p(tv.data_ptr()), ctypes.c_void_p(out3.data_ptr()),
+        ctypes.c_void_p(in16.data_ptr()) if in16 is not None else None, B, N, H, W, _resolve_mode(coord_mode))
+    _abi.check(rc, "ssm_synthesize_host")
+    return (out3, in16) if return_inputs else out3

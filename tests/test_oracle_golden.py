@@ -1,0 +1,89 @@
+"""CPU suite: the oracle against the golden vectors produced by the reference itself
+(tests/golden/make_golden.py imported /root/reference/scripts and ran it on CPU)."""
+import pytest
+import torch
+
+from oracle import c_oracle, torch_oracle
+from util import assert_close_fp32, golden_cases, load_golden
+
+CASES = golden_cases()
+
+
+def test_golden_fixtures_present():
+    assert len(CASES) >= 7
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_c_oracle_matches_reference(name):
+    d = load_golden(name)
+    img3, flow2 = d["img6"][:, 0:3].contiguous(), d["flow4"][:, 0:2].contiguous()
+    assert_close_fp32(c_oracle.warp(img3, flow2), d["warp_out"], "warp fwd")
+    gi, gf = c_oracle.warp_backward(d["warp_gout"], img3, flow2)
+    assert_close_fp32(gi, d["warp_gimg"], "warp grad img")
+    assert_close_fp32(gf, d["warp_gflow"], "warp grad flow")
+
+    in16 = c_oracle.compute_inputs(d["img6"], d["flow4"], d["t"])
+    # the estimated flows fix the sampling coordinates downstream: they must be bit-identical
+    assert torch.equal(in16[:, 6:10], d["in16"][:, 6:10]), "estimated flows are not bit-identical"
+    assert torch.equal(in16[:, 0:3], d["in16"][:, 0:3]) and torch.equal(in16[:, 13:16], d["in16"][:, 13:16])
+    assert_close_fp32(in16, d["in16"], "compute_inputs fwd")
+    gi, gf = c_oracle.compute_inputs_backward(d["pack_g16"], d["img6"], d["flow4"], d["t"])
+    assert_close_fp32(gi, d["pack_gimg"], "compute_inputs grad img")
+    assert_close_fp32(gf, d["pack_gflow"], "compute_inputs grad flow")
+
+    frame = c_oracle.compute_output_image(d["img6"], d["in16"], d["out5"], d["t"])
+    assert_close_fp32(frame, d["frame"], "compute_output_image fwd")
+    gi, gx, gy = c_oracle.compute_output_image_backward(d["fuse_g3"], d["img6"], d["in16"], d["out5"], d["t"])
+    assert_close_fp32(gi, d["fuse_gimg"], "compute_output_image grad img")
+    assert_close_fp32(gx[:, 6:10], d["fuse_gflows"], "compute_output_image grad in16[6:10]")
+    assert gx[:, :6].abs().max() == 0 and gx[:, 10:].abs().max() == 0
+    assert_close_fp32(gy, d["fuse_gout5"], "compute_output_image grad out5")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_oracle_matches_reference(name):
+    """The torch restatement issues the reference's torch ops: same bits on the same torch build."""
+    d = load_golden(name)
+    t = d["t"].view(-1, 1, 1, 1)
+    assert_close_fp32(torch_oracle.warp(d["img6"][:, 0:3], d["flow4"][:, 0:2]), d["warp_out"], "warp", tol=1e-6)
+    assert_close_fp32(torch_oracle.compute_inputs(d["img6"], d["flow4"], t), d["in16"], "compute_inputs", tol=1e-6)
+    assert_close_fp32(torch_oracle.compute_output_image(d["img6"], d["in16"], d["out5"], t), d["frame"],
+                      "compute_output_image", tol=1e-6)
+
+
+def test_coord_modes_differ_only_slightly():
+    """RCP (CUDA-style reciprocal multiply) and DIV (CPU-style division) are two reference
+    bit-patterns: close in the forward, not identical (SURVEY.md finding 3b)."""
+    d = load_golden("wide_1920")
+    img3, flow2 = d["img6"][:, 0:3].contiguous(), d["flow4"][:, 0:2].contiguous()
+    a = c_oracle.warp(img3, flow2, coord_mode=c_oracle.COORD_DIV)
+    b = c_oracle.warp(img3, flow2, coord_mode=c_oracle.COORD_RCP)
+    assert (a - b).abs().max() < 5e-3
+    assert not torch.equal(a, b)
+
+
+def test_oracle_properties():
+    """Analytic properties the reference satisfies (SURVEY.md section 8(c) iii)."""
+    from ssm_b200 import synthetic
+    B, H, W = 2, 32, 48
+    img6 = synthetic.frames(B, H, W, seed=3)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=4.0, seed=4)
+    out5 = synthetic.unet_out5(B, 1, H, W, seed=5)[:, 0].contiguous()
+    t = torch.tensor([0.25, 0.625])
+    in16 = c_oracle.compute_inputs(img6, flow4, t)
+    # 16-channel layout (flow_interpolation.py:364-367)
+    assert torch.equal(in16[:, 0:3], img6[:, 3:6]) and torch.equal(in16[:, 13:16], img6[:, 0:3])
+    assert torch.equal(in16[:, 3:6], c_oracle.warp(img6[:, 3:6].contiguous(), in16[:, 6:8].contiguous()))
+    assert torch.equal(in16[:, 10:13], c_oracle.warp(img6[:, 0:3].contiguous(), in16[:, 8:10].contiguous()))
+    # time-reversal symmetry of the fusion
+    frame = c_oracle.compute_output_image(img6, in16, out5, t)
+    img_sw = torch.cat([img6[:, 3:6], img6[:, 0:3]], 1)
+    in_sw = in16.clone()
+    in_sw[:, 6:8], in_sw[:, 8:10] = in16[:, 8:10], in16[:, 6:8]
+    out_sw = torch.cat([-out5[:, 0:1], out5[:, 3:5], out5[:, 1:3]], 1)
+    frame_sw = c_oracle.compute_output_image(img_sw, in_sw, out_sw, 1.0 - t)
+    assert (frame - frame_sw).abs().max() < 2e-6
+    # saturated visibility stays finite
+    sat = out5.clone()
+    sat[:, 0] = 40.0
+    assert torch.isfinite(c_oracle.compute_output_image(img6, in16, sat, t)).all()

@@ -1,0 +1,290 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against
+  * the golden vectors produced by the reference itself (tests/golden),
+  * the C oracle (oracle/ssm_oracle.c) on seeded inputs, in both coordinate modes,
+  * the reference's own torch ops run on the CUDA device (oracle/torch_oracle.py with cuDNN off =
+    CUDA-ATen bit-pattern; with cuDNN on = cuDNN bit-pattern, reported, not asserted at 1e-5),
+and through size-independent properties at BASELINE.json's full size (16 pairs 1088x1920, N=7).
+Tolerances: fp32 max abs error <= 1e-5; bf16 storage <= 2e-2 (+ 2^-7 relative above magnitude 1).
+"""
+import pytest
+import torch
+
+import ssm_b200
+from oracle import c_oracle, torch_oracle
+from ssm_b200 import synthetic
+from util import assert_close_bf16, assert_close_fp32, golden_cases, load_golden, max_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MODES = [("cpu", c_oracle.COORD_DIV), ("cuda", c_oracle.COORD_RCP)]
+
+
+def _dev(x, grad=False):
+    return x.to(DEV).requires_grad_(grad)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_vectors(name):
+    """Reference outputs (CPU run of the unmodified reference) vs the CUDA path, mode "cpu"."""
+    d = load_golden(name)
+    B = d["img6"].shape[0]
+    t = d["t"].view(B, 1, 1, 1)
+    # warp fwd + bwd
+    x, f = _dev(d["img6"][:, 0:3], True), _dev(d["flow4"][:, 0:2], True)
+    y = ssm_b200.warp(x, f)
+    y.backward(_dev(d["warp_gout"]))
+    assert_close_fp32(y, d["warp_out"], "warp fwd")
+    assert_close_fp32(x.grad, d["warp_gimg"], "warp grad img")
+    assert_close_fp32(f.grad, d["warp_gflow"], "warp grad flow")
+    # compute_inputs fwd + bwd through the reference-shaped method
+    ops = ssm_b200.SynthesisMixin()
+    a, b = _dev(d["img6"], True), _dev(d["flow4"], True)
+    in16 = ops.compute_inputs(a, b, _dev(t))
+    in16.backward(_dev(d["pack_g16"]))
+    assert torch.equal(in16[:, 6:10].detach().cpu(), d["in16"][:, 6:10]), "estimated flows not bit-identical"
+    assert_close_fp32(in16, d["in16"], "compute_inputs fwd")
+    assert_close_fp32(a.grad, d["pack_gimg"], "compute_inputs grad img")
+    assert_close_fp32(b.grad, d["pack_gflow"], "compute_inputs grad flow")
+    # compute_output_image fwd + bwd
+    a, xin, yo = _dev(d["img6"], True), _dev(d["in16"], True), _dev(d["out5"], True)
+    frame = ops.compute_output_image(a, xin, yo, _dev(t))
+    frame.backward(_dev(d["fuse_g3"]))
+    assert_close_fp32(frame, d["frame"], "compute_output_image fwd")
+    assert_close_fp32(a.grad, d["fuse_gimg"], "compute_output_image grad img")
+    assert_close_fp32(xin.grad[:, 6:10], d["fuse_gflows"], "compute_output_image grad in16[6:10]")
+    assert xin.grad[:, :6].abs().max() == 0 and xin.grad[:, 10:].abs().max() == 0
+    assert_close_fp32(yo.grad, d["fuse_gout5"], "compute_output_image grad out5")
+
+
+# ---------------------------------------------------------------------------------------------
+def _inputs(B, N, H, W, seed, kind="smooth", smooth=True, flow_px=8.0):
+    img6 = synthetic.frames(B, H, W, seed=seed, smooth=smooth)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=flow_px, seed=seed + 1, kind=kind)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=seed + 2)
+    t = synthetic.timesteps(B, N) if N > 1 else synthetic.random_timesteps(B, 1, seed=seed + 3)
+    return img6, flow4, out5, t
+
+
+@pytest.mark.parametrize("mode_name,mode", MODES)
+@pytest.mark.parametrize("B,N,H,W,kind,smooth", [
+    (2, 3, 64, 96, "smooth", True),
+    (1, 7, 45, 77, "noise", False),      # ragged: not a multiple of the 32x8 tile
+    (2, 1, 33, 31, "border", True),      # narrower than one tile, samples cross every border
+    (1, 2, 8, 1920, "integer", False),
+    (1, 1, 1, 1, "zero", False),         # degenerate 1x1 frame: max(W-1,1) path
+    (3, 2, 352, 352, "smooth", True),    # training crop size
+])
+def test_batched_kernels_vs_c_oracle(mode_name, mode, B, N, H, W, kind, smooth):
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=100 + H + W, kind=kind, smooth=smooth)
+    gen = torch.Generator().manual_seed(5)
+    g16 = torch.randn(B, N, 16, H, W, generator=gen)
+    g3 = torch.randn(B, N, 3, H, W, generator=gen)
+    a, b = _dev(img6, True), _dev(flow4, True)
+    in16 = ssm_b200.flow_pack(a, b, _dev(t), n_timesteps=N, coord_mode=mode_name)
+    in16.backward(_dev(g16))
+    a2, xin, yo = _dev(img6, True), _dev(in16.detach().cpu(), True), _dev(out5, True)
+    frames = ssm_b200.fuse(a2, xin, yo, _dev(t), coord_mode=mode_name)
+    frames.backward(_dev(g3))
+    ref_gimg = torch.zeros_like(img6)
+    ref_gflow = torch.zeros_like(flow4)
+    ref_gimg2 = torch.zeros_like(img6)
+    for n in range(N):
+        tn = t[:, n]
+        r16 = c_oracle.compute_inputs(img6, flow4, tn, coord_mode=mode)
+        assert torch.equal(in16[:, n, 6:10].detach().cpu(), r16[:, 6:10]), "estimated flows not bit-identical"
+        assert_close_fp32(in16[:, n], r16, "flow_pack fwd n=%d" % n)
+        gi, gf = c_oracle.compute_inputs_backward(g16[:, n].contiguous(), img6, flow4, tn, coord_mode=mode)
+        ref_gimg += gi
+        ref_gflow += gf
+        y5 = out5[:, n].contiguous()
+        r3 = c_oracle.compute_output_image(img6, r16, y5, tn, coord_mode=mode)
+        assert_close_fp32(frames[:, n], r3, "fuse fwd n=%d" % n)
+        gi2, gx, gy = c_oracle.compute_output_image_backward(g3[:, n].contiguous(), img6, r16, y5, tn, coord_mode=mode)
+        ref_gimg2 += gi2
+        assert_close_fp32(xin.grad[:, n], gx, "fuse grad in16 n=%d" % n)
+        assert_close_fp32(yo.grad[:, n], gy, "fuse grad out5 n=%d" % n)
+    # sums over N timesteps: allow N roundings
+    assert_close_fp32(b.grad, ref_gflow, "flow_pack grad flow", tol=1e-5 * max(1, N // 2))
+    assert_close_fp32(a.grad, ref_gimg, "flow_pack grad img", tol=1e-5 * max(1, N // 2))
+    assert_close_fp32(a2.grad, ref_gimg2, "fuse grad img", tol=1e-5 * max(1, N // 2))
+
+
+@pytest.mark.parametrize("C", [1, 3, 5])
+def test_warp_channels_and_partial_grads(C):
+    B, H, W = 2, 40, 72
+    gen = torch.Generator().manual_seed(C)
+    x = torch.randn(B, C, H, W, generator=gen)
+    f = synthetic.flows(B, H, W, 2, flow_px=5.0, seed=9)
+    g = torch.randn(B, C, H, W, generator=gen)
+    want_out = c_oracle.warp(x, f)
+    want_gx, want_gf = c_oracle.warp_backward(g, x, f)
+    for need_x, need_f in [(True, True), (True, False), (False, True)]:
+        xd, fd = _dev(x, need_x), _dev(f, need_f)
+        y = ssm_b200.warp(xd, fd)
+        y.backward(_dev(g))
+        assert_close_fp32(y, want_out, "warp fwd")
+        if need_x:
+            assert_close_fp32(xd.grad, want_gx, "warp grad img")
+        if need_f:
+            assert_close_fp32(fd.grad, want_gf, "warp grad flow")
+
+
+def test_strided_views_are_accepted():
+    """compute_output_image receives channel-sliced views (flow_interpolation.py:402-403)."""
+    B, H, W = 2, 32, 64
+    img6, flow4, out5, t = _inputs(B, 1, H, W, seed=77)
+    big = torch.randn(B, 9, H, W)
+    big[:, 2:8] = img6
+    view = _dev(big)[:, 2:8]                       # non-contiguous batch stride
+    in16 = ssm_b200.flow_pack(view, _dev(flow4), _dev(t), n_timesteps=1)
+    ref16 = c_oracle.compute_inputs(img6, flow4, t[:, 0])
+    assert_close_fp32(in16[:, 0], ref16, "flow_pack on a channel-sliced view")
+    y = ssm_b200.warp(view[:, 0:3], _dev(flow4)[:, 2:4])
+    assert_close_fp32(y, c_oracle.warp(img6[:, 0:3].contiguous(), flow4[:, 2:4].contiguous()), "warp on views")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_against_reference_ops_on_cuda():
+    """The reference's own torch ops on the CUDA device.  cuDNN off = ATen's CUDA kernels, matched
+    by coord mode "cuda" at 1e-5 (fwd and grads); the CPU-vs-CUDA and cuDNN deltas of the REFERENCE
+    are printed for context (they exceed 1e-5 on their own, SURVEY.md findings 3/3b)."""
+    B, H, W = 2, 352, 352
+    img6, flow4, out5, t = _inputs(B, 1, H, W, seed=300, flow_px=10.0)
+    t4 = t.view(B, 1, 1, 1)
+    g16 = torch.randn(B, 16, H, W, generator=torch.Generator().manual_seed(1))
+    g3 = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(2))
+
+    def run_ref(cudnn):
+        prev = torch.backends.cudnn.enabled
+        torch.backends.cudnn.enabled = cudnn
+        try:
+            a, b = _dev(img6, True), _dev(flow4, True)
+            in16 = torch_oracle.compute_inputs(a, b, _dev(t4))
+            in16.backward(_dev(g16))
+            a2, xin, yo = _dev(img6, True), in16.detach().clone().requires_grad_(True), _dev(out5[:, 0], True)
+            fr = torch_oracle.compute_output_image(a2, xin, yo, _dev(t4))
+            fr.backward(_dev(g3))
+            return dict(in16=in16.detach(), gflow=b.grad, gimg=a.grad, frame=fr.detach(), gin=xin.grad, gout=yo.grad,
+                        gimg2=a2.grad)
+        finally:
+            torch.backends.cudnn.enabled = prev
+
+    def run_new(mode):
+        a, b = _dev(img6, True), _dev(flow4, True)
+        in16 = ssm_b200.flow_pack(a, b, _dev(t), n_timesteps=1, coord_mode=mode)
+        in16.backward(_dev(g16).unsqueeze(1))
+        a2, xin, yo = _dev(img6, True), in16.detach().clone().requires_grad_(True), _dev(out5, True)
+        fr = ssm_b200.fuse(a2, xin, yo, _dev(t), coord_mode=mode)
+        fr.backward(_dev(g3).unsqueeze(1))
+        return dict(in16=in16.detach()[:, 0], gflow=b.grad, gimg=a.grad, frame=fr.detach()[:, 0], gin=xin.grad[:, 0],
+                    gout=yo.grad[:, 0], gimg2=a2.grad)
+
+    aten = run_ref(cudnn=False)
+    cudnn = run_ref(cudnn=True)
+    new_cuda = run_new("cuda")
+    new_cpu = run_new("cpu")
+    report = {k: (max_err(new_cuda[k], aten[k]), max_err(new_cpu[k], aten[k]), max_err(cudnn[k], aten[k])) for k in aten}
+    print("\nmax abs diff vs reference-on-CUDA (ATen): key: new[mode=cuda]  new[mode=cpu]  reference-cuDNN")
+    for k, v in report.items():
+        print("  %-6s %.2e  %.2e  %.2e" % ((k,) + v))
+    for k in aten:
+        assert_close_fp32(new_cuda[k], aten[k], "mode=cuda vs reference ATen-CUDA: " + k)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_image_gradient_is_deterministic():
+    """Bit-identical run to run (the reference's atomicAdd scatter is not)."""
+    B, N, H, W = 2, 7, 96, 128
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=500, kind="noise", smooth=False)
+    flow4 = flow4 * 0.0 + flow4.mean(dim=(2, 3), keepdim=True)   # constant flow: many sources per destination
+    g3 = torch.randn(B, N, 3, H, W, generator=torch.Generator().manual_seed(3))
+    outs = []
+    for _ in range(3):
+        a, b = _dev(img6, True), _dev(flow4, True)
+        in16 = ssm_b200.flow_pack(a, b, _dev(t), n_timesteps=N)
+        fr = ssm_b200.fuse(a, in16, _dev(out5), _dev(t))
+        fr.backward(_dev(g3))
+        outs.append((a.grad.clone(), b.grad.clone()))
+    for gi, gf in outs[1:]:
+        assert torch.equal(gi, outs[0][0]) and torch.equal(gf, outs[0][1])
+
+
+@pytest.mark.parametrize("mode_name,mode", MODES)
+def test_bf16_storage(mode_name, mode):
+    """bf16 storage, fp32 math: against the fp32 oracle on the same bf16-rounded inputs."""
+    B, N, H, W = 2, 2, 64, 96
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=700, flow_px=3.0)
+    img6, flow4, out5 = (x.bfloat16() for x in (img6, flow4, out5))
+    g3 = (torch.randn(B, N, 3, H, W, generator=torch.Generator().manual_seed(4)) * 0.25).bfloat16()
+    a, b = _dev(img6), _dev(flow4, True)
+    in16 = ssm_b200.flow_pack(a, b, _dev(t), n_timesteps=N, coord_mode=mode_name)
+    assert in16.dtype == torch.bfloat16
+    xin, yo = in16.detach().clone().requires_grad_(True), _dev(out5, True)
+    fr = ssm_b200.fuse(a, xin, yo, _dev(t), coord_mode=mode_name)
+    fr.backward(_dev(g3))
+    for n in range(N):
+        tn = t[:, n]
+        r16 = c_oracle.compute_inputs(img6.float(), flow4.float(), tn, coord_mode=mode)
+        assert_close_bf16(in16[:, n], r16, "bf16 flow_pack fwd")
+        x16 = in16[:, n].detach().float().cpu()
+        r3 = c_oracle.compute_output_image(img6.float(), x16, out5[:, n].float().contiguous(), tn, coord_mode=mode)
+        assert_close_bf16(fr[:, n], r3, "bf16 fuse fwd")
+        _, gx, gy = c_oracle.compute_output_image_backward(g3[:, n].float().contiguous(), img6.float(), x16,
+                                                           out5[:, n].float().contiguous(), tn, coord_mode=mode,
+                                                           need_img=False)
+        assert_close_bf16(yo.grad[:, n], gy, "bf16 fuse grad out5")
+        assert_close_bf16(xin.grad[:, n], gx, "bf16 fuse grad in16")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    """BASELINE.json configs[1]: 16 pairs 1088x1920, 7 timesteps, on one B200.  Size-independent
+    properties on the whole batch + the C oracle on two (pair, timestep) slices."""
+    B, N, H, W = 16, 7, 1088, 1920
+    img6 = synthetic.frames(B, H, W, seed=42, device=DEV)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=43, device=DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=44, device=DEV)
+    t = synthetic.timesteps(B, N, device=DEV)
+    in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=N)
+    frames = ssm_b200.fuse(img6, in16, out5, t)
+    assert torch.isfinite(frames).all()
+    # layout identities (flow_interpolation.py:364-367), exact
+    for n in (0, N - 1):
+        assert torch.equal(in16[:, n, 0:3], img6[:, 3:6]) and torch.equal(in16[:, n, 13:16], img6[:, 0:3])
+    # warped channels == stand-alone warp with the packed flows
+    w1 = ssm_b200.warp(img6[:, 3:6], in16[:, 3, 6:8])
+    assert max_err(w1, in16[:, 3, 3:6]) <= 1e-6
+    # idempotence / determinism of the forward
+    assert torch.equal(ssm_b200.fuse(img6, in16, out5, t), frames)
+    # time-reversal symmetry: swap frames, flows, residuals, negate the logit, t -> 1 - t
+    b = 5
+    img_sw = torch.cat([img6[b:b + 1, 3:6], img6[b:b + 1, 0:3]], 1)
+    in_sw = in16[b:b + 1].clone()
+    in_sw[:, :, 6:8], in_sw[:, :, 8:10] = in16[b:b + 1, :, 8:10], in16[b:b + 1, :, 6:8]
+    out_sw = torch.cat([-out5[b:b + 1, :, 0:1], out5[b:b + 1, :, 3:5], out5[b:b + 1, :, 1:3]], 2)
+    fr_sw = ssm_b200.fuse(img_sw, in_sw, out_sw, 1.0 - t[b:b + 1])
+    assert max_err(fr_sw, frames[b:b + 1]) <= 5e-6
+    # two slices against the C oracle
+    for (b, n) in ((0, 0), (15, 6)):
+        i6, f4 = img6[b:b + 1].cpu(), flow4[b:b + 1].cpu()
+        tn = t[b:b + 1, n].cpu()
+        r16 = c_oracle.compute_inputs(i6, f4, tn)
+        assert_close_fp32(in16[b:b + 1, n], r16, "full-size flow_pack (%d,%d)" % (b, n))
+        r3 = c_oracle.compute_output_image(i6, r16, out5[b:b + 1, n].cpu().contiguous(), tn)
+        assert_close_fp32(frames[b:b + 1, n], r3, "full-size fuse (%d,%d)" % (b, n))
+
+
+def test_host_entry_point_matches_device_path():
+    """ssm_synthesize_host (host buffers, copies inside) == device path."""
+    B, N, H, W = 4, 3, 64, 96
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=900)
+    out3, in16 = ssm_b200.synthesize_host(img6.pin_memory(), flow4.pin_memory(), out5.pin_memory(), t,
+                                          return_inputs=True)
+    d16 = ssm_b200.flow_pack(_dev(img6), _dev(flow4), _dev(t), n_timesteps=N)
+    d3 = ssm_b200.fuse(_dev(img6), d16, _dev(out5), _dev(t))
+    assert torch.equal(in16, d16.cpu()) and torch.equal(out3, d3.cpu())
+    for n in range(N):
+        r16 = c_oracle.compute_inputs(img6, flow4, t[:, n])
+        assert_close_fp32(out3[:, n], c_oracle.compute_output_image(img6, r16, out5[:, n].contiguous(), t[:, n]),
+                          "host entry point vs oracle")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 1
+#define SSM_ABI_VERSION 2
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -80,6 +80,16 @@ int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_te
                  int B, int C, int H, int W, int dtype, int coord_mode,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- frame re-layout (no reference counterpart; an internal staging step of a2/a4) -----------
+ * The gathers of a2 and a3+a4 are bound by L1 request throughput when the three colour planes of
+ * a frame are fetched separately.  ssm_pack_frames copies img6 (B x 6 x H x W planar) into a
+ * pixel-interleaved RGBx buffer `packed` (B x 2 x H x W x 4 elements of the storage dtype,
+ * ssm_packed_frames_bytes(B, H, W, dtype) bytes, 16-byte aligned) so each bilinear tap is one
+ * request.  It is optional: every entry point below takes `packed` and gathers from the planar
+ * frames when it is NULL.  It pays for itself from N >= 2 timesteps per pair. */
+size_t ssm_packed_frames_bytes(int B, int H, int W, int dtype);
+int ssm_pack_frames(const ssm_tensor* img6, void* packed, int B, int H, int W, int dtype, void* stream);
+
 /* ---- a2: FlowInterpolationModel.compute_inputs(img_tensor, flow_pred_tensor, t)
  *      [reference scripts/models/flow_interpolation.py:338-372], batched over N timesteps so
  *      that the loop of superslomo_r.py:167-179 and its torch.stack become one launch.
@@ -87,15 +97,15 @@ int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_te
  * flow4: B x 4 x H x W        (0-1 = F01, 2-3 = F10)
  * t:     B*N fp32 values, t[b*N + n] in (0,1)
  * out16: B x N x 16 x H x W   [I1, g(I1,F_t1), F_t1, F_t0, g(I0,F_t0), I0] */
-int ssm_flow_pack_fwd(const ssm_tensor* img6, const ssm_tensor* flow4, const float* t,
+int ssm_flow_pack_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const float* t,
                       const ssm_tensor* out16, int B, int N, int H, int W,
                       int dtype, int coord_mode, void* stream);
 
 /* Backward of a2.  grad16: B x N x 16 x H x W.  grad_flow4 (B x 4 x H x W, summed over the N
  * timesteps) and grad_img6 (B x 6 x H x W) may be NULL.  grad_img6 needs a workspace of
  * ssm_flow_pack_bwd_workspace_bytes(B, N, H, W). */
-int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ssm_tensor* flow4,
-                      const float* t, const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
+int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const float* t, const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
                       int B, int N, int H, int W, int dtype, int coord_mode,
                       void* workspace, size_t workspace_bytes, void* stream);
 
@@ -106,7 +116,7 @@ int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ss
  * flows4: B x N x 4 x H x W   = input_tensor[:, 6:10] (F_t1 then F_t0), usually a strided view
  * out5:   B x N x 5 x H x W   stage-2 U-Net output (visibility logit, dF_t1, dF_t0)
  * out3:   B x N x 3 x H x W   fused frame */
-int ssm_fuse_fwd(const ssm_tensor* img6, const ssm_tensor* flows4, const ssm_tensor* out5,
+int ssm_fuse_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flows4, const ssm_tensor* out5,
                  const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
                  int dtype, int coord_mode, void* stream);
 
@@ -114,8 +124,8 @@ int ssm_fuse_fwd(const ssm_tensor* img6, const ssm_tensor* flows4, const ssm_ten
  * (B x N x 4: the gradient of input_tensor[:, 6:10]; the other 12 channels of that gradient are
  * zero and are the caller's to fill) and grad_img6 (B x 6) may each be NULL.  grad_img6 needs a
  * workspace of ssm_fuse_bwd_workspace_bytes(B, N, H, W). */
-int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const ssm_tensor* flows4,
-                 const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                 const ssm_tensor* flows4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
                  const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
                  int B, int N, int H, int W, int dtype, int coord_mode,
                  void* workspace, size_t workspace_bytes, void* stream);
@@ -134,10 +144,12 @@ size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W);
  *   img6_host  B x 6 x H x W, flow4_host B x 4 x H x W, out5_host B x N x 5 x H x W,
  *   t_host B*N floats, out3_host B x N x 3 x H x W, in16_host (optional, may be NULL)
  *   B x N x 16 x H x W receives the packed stage-2 input.
- * Device scratch is allocated per call with cudaMallocAsync and released before returning. */
+ * `scratch` is caller-owned DEVICE memory of at least ssm_synthesize_host_scratch_bytes(B, N, H, W)
+ * bytes (three pair-sized slots), 256-byte aligned. */
+size_t ssm_synthesize_host_scratch_bytes(int B, int N, int H, int W);
 int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const float* out5_host,
                         const float* t_host, float* out3_host, float* in16_host,
-                        int B, int N, int H, int W, int coord_mode);
+                        int B, int N, int H, int W, int coord_mode, void* scratch, size_t scratch_bytes);
 
 #ifdef __cplusplus
 }

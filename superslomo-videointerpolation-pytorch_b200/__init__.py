@@ -3,11 +3,12 @@ synthesis path behind the reference's own call surface (scripts/models/layers.py
 scripts/models/flow_interpolation.py:338-429).  CUDA only; the kernels live in libssm_b200.so
 (C ABI: include/ssm_b200.h)."""
 from . import _abi
-from .functional import (flow_pack, fuse, get_coord_mode, set_coord_mode, synthesize_host, warp as warp_fn)
+from .functional import (flow_pack, fuse, get_coord_mode, pack_frames, set_coord_mode, synthesize_host,
+                         synthesize_host_scratch_bytes)
 from .layers import avg_pool, conv, warp
 from .flow_interpolation import SynthesisMixin, patch_reference
 
-__all__ = ["warp", "conv", "avg_pool", "flow_pack", "fuse", "synthesize_host", "SynthesisMixin",
+__all__ = ["warp", "conv", "avg_pool", "flow_pack", "fuse", "pack_frames", "synthesize_host", "synthesize_host_scratch_bytes", "SynthesisMixin",
            "patch_reference", "set_coord_mode", "get_coord_mode", "abi_version"]
 
 

@@ -21,7 +21,8 @@ EXPORTS = (
     "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
     "ssm_fuse_fwd", "ssm_fuse_bwd",
     "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
-    "ssm_synthesize_host",
+    "ssm_packed_frames_bytes", "ssm_pack_frames",
+    "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes",
 )
 
 
@@ -50,16 +51,18 @@ def lib():
     L.ssm_last_error.restype = ctypes.c_char_p
     L.ssm_warp_fwd.argtypes = [P, P, P, I, I, I, I, I, I, V]
     L.ssm_warp_bwd.argtypes = [P, P, P, P, P, I, I, I, I, I, I, V, Z, V]
-    L.ssm_flow_pack_fwd.argtypes = [P, P, V, P, I, I, I, I, I, I, V]
-    L.ssm_flow_pack_bwd.argtypes = [P, P, P, V, P, P, I, I, I, I, I, I, V, Z, V]
-    L.ssm_fuse_fwd.argtypes = [P, P, P, V, P, I, I, I, I, I, I, V]
-    L.ssm_fuse_bwd.argtypes = [P, P, P, P, V, P, P, P, I, I, I, I, I, I, V, Z, V]
-    for n in ("ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes"):
+    L.ssm_pack_frames.argtypes = [P, V, I, I, I, I, V]
+    L.ssm_flow_pack_fwd.argtypes = [P, V, P, V, P, I, I, I, I, I, I, V]
+    L.ssm_flow_pack_bwd.argtypes = [P, P, V, P, V, P, P, I, I, I, I, I, I, V, Z, V]
+    L.ssm_fuse_fwd.argtypes = [P, V, P, P, V, P, I, I, I, I, I, I, V]
+    L.ssm_fuse_bwd.argtypes = [P, P, V, P, P, V, P, P, P, I, I, I, I, I, I, V, Z, V]
+    for n in ("ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
+              "ssm_packed_frames_bytes", "ssm_synthesize_host_scratch_bytes"):
         getattr(L, n).argtypes = [I, I, I, I]
         getattr(L, n).restype = Z
-    L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I]
-    for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd", "ssm_fuse_fwd",
-              "ssm_fuse_bwd", "ssm_synthesize_host"):
+    L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I, V, Z]
+    for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
+              "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_synthesize_host"):
         getattr(L, n).restype = I
     _lib = L
     return L

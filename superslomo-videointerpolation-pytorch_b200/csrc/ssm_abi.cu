@@ -70,6 +70,11 @@ int check_tensor(const ssm_tensor* t, const char* name, int dtype, bool required
     return SSM_OK;
 }
 
+int check_packed(const void* packed) {
+    if (packed && ((uintptr_t)packed) % 16 != 0) return fail(SSM_ERR_ALIGN, "packed must be 16-byte aligned");
+    return SSM_OK;
+}
+
 template <typename T> View<const T> cview(const ssm_tensor* t) {
     View<const T> v;
     if (t && t->data) { v.p = (const T*)t->data; v.sb = t->stride_b; v.sn = t->stride_n; v.sc = t->stride_c; }
@@ -91,6 +96,16 @@ int count_bits_for(long long addends) {   // bits needed to hold `addends` unit 
     int b = 1;
     while ((1ll << b) <= addends) ++b;
     return b;
+}
+
+template <typename F> int dispatch3(int dtype, int mode, bool packed, F&& f) {
+    if (dtype == SSM_DTYPE_F32) {
+        if (mode == SSM_COORD_DIV) return packed ? f.template run<float, SSM_COORD_DIV, true>() : f.template run<float, SSM_COORD_DIV, false>();
+        return packed ? f.template run<float, SSM_COORD_RCP, true>() : f.template run<float, SSM_COORD_RCP, false>();
+    }
+    if (mode == SSM_COORD_DIV)
+        return packed ? f.template run<__nv_bfloat16, SSM_COORD_DIV, true>() : f.template run<__nv_bfloat16, SSM_COORD_DIV, false>();
+    return packed ? f.template run<__nv_bfloat16, SSM_COORD_RCP, true>() : f.template run<__nv_bfloat16, SSM_COORD_RCP, false>();
 }
 
 // dispatch helper: calls f.template run<T, MODE>() for the runtime dtype / coord_mode
@@ -151,26 +166,36 @@ struct WarpBwd {
     }
 };
 
-struct PackFwd {
-    const ssm_tensor *img6, *flow4; const float* t; const ssm_tensor* out16; int B, N, H, W; cudaStream_t s;
+struct PackFrames {
+    const ssm_tensor* img6; void* packed; int B, H, W; cudaStream_t s;
     template <typename T, int MODE> int run() {
-        flow_pack_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            cview<T>(img6), cview<T>(flow4), t, mview<T>(out16), N, make_geom(H, W));
+        pack_frames_kernel<T><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(cview<T>(img6), (T*)packed, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_pack_frames");
+        return SSM_OK;
+    }
+};
+
+struct PackFwd {
+    const ssm_tensor* img6; const void* packed; const ssm_tensor* flow4; const float* t; const ssm_tensor* out16;
+    int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        flow_pack_fwd_kernel<T, MODE, PACKED><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img6), (const T*)packed, cview<T>(flow4), t, mview<T>(out16), N, make_geom(H, W));
         SSM_LAUNCH_CHECK("ssm_flow_pack_fwd");
         return SSM_OK;
     }
 };
 
 struct PackBwd {
-    const ssm_tensor *g16, *img6, *flow4; const float* t; const ssm_tensor *gflow4, *gimg6;
-    int B, N, H, W; void* ws; cudaStream_t s;
-    template <typename T, int MODE> int run() {
+    const ssm_tensor *g16, *img6; const void* packed; const ssm_tensor* flow4; const float* t;
+    const ssm_tensor *gflow4, *gimg6; int B, N, H, W; void* ws; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
         const Geom g = make_geom(H, W);
         const bool want_img = gimg6 && gimg6->data;
         const long long npx = (long long)H * W;
         if (!want_img) {
-            flow_pack_bwd_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-                cview<T>(g16), cview<T>(img6), cview<T>(flow4), t, mview<T>(gflow4), nullptr, nullptr, N, g);
+            flow_pack_bwd_kernel<T, MODE, PACKED, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(g16), cview<T>(img6), (const T*)packed, cview<T>(flow4), t, mview<T>(gflow4), nullptr, nullptr, N, g);
             SSM_LAUNCH_CHECK("ssm_flow_pack_bwd");
             return SSM_OK;
         }
@@ -179,8 +204,8 @@ struct PackBwd {
         float* direct = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
         cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
         if (e != cudaSuccess) return cuda_fail(e, "ssm_flow_pack_bwd memset");
-        flow_pack_bwd_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            cview<T>(g16), cview<T>(img6), cview<T>(flow4), t, mview<T>(gflow4), direct, hdr, N, g);
+        flow_pack_bwd_kernel<T, MODE, PACKED, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g16), cview<T>(img6), (const T*)packed, cview<T>(flow4), t, mview<T>(gflow4), direct, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_flow_pack_bwd");
         const int cb = count_bits_for((long long)N * npx);
         flow_pack_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
@@ -194,25 +219,26 @@ struct PackBwd {
 };
 
 struct FuseFwd {
-    const ssm_tensor *img6, *flows4, *out5; const float* t; const ssm_tensor* out3; int B, N, H, W; cudaStream_t s;
-    template <typename T, int MODE> int run() {
-        fuse_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(out3), N, make_geom(H, W));
+    const ssm_tensor* img6; const void* packed; const ssm_tensor *flows4, *out5; const float* t;
+    const ssm_tensor* out3; int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        fuse_fwd_kernel<T, MODE, PACKED><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(out3), N, make_geom(H, W));
         SSM_LAUNCH_CHECK("ssm_fuse_fwd");
         return SSM_OK;
     }
 };
 
 struct FuseBwd {
-    const ssm_tensor *g3, *img6, *flows4, *out5; const float* t; const ssm_tensor *gout5, *gflows4, *gimg6;
-    int B, N, H, W; void* ws; cudaStream_t s;
-    template <typename T, int MODE> int run() {
+    const ssm_tensor *g3, *img6; const void* packed; const ssm_tensor *flows4, *out5; const float* t;
+    const ssm_tensor *gout5, *gflows4, *gimg6; int B, N, H, W; void* ws; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
         const Geom g = make_geom(H, W);
         const bool want_img = gimg6 && gimg6->data;
         const long long npx = (long long)H * W;
         if (!want_img) {
-            fuse_bwd_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-                cview<T>(g3), cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
+            fuse_bwd_kernel<T, MODE, PACKED, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(g3), cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
                 mview<T>(gflows4), nullptr, nullptr, N, g);
             SSM_LAUNCH_CHECK("ssm_fuse_bwd");
             return SSM_OK;
@@ -222,8 +248,8 @@ struct FuseBwd {
         float* stage = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
         cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
         if (e != cudaSuccess) return cuda_fail(e, "ssm_fuse_bwd memset");
-        fuse_bwd_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            cview<T>(g3), cview<T>(img6), cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
+        fuse_bwd_kernel<T, MODE, PACKED, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g3), cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
             mview<T>(gflows4), stage, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd");
         const int cb = count_bits_for((long long)N * npx);
@@ -293,21 +319,36 @@ int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_te
                     WarpBwd{grad_out, img, flow, grad_img, grad_flow, B, C, H, W, workspace, (cudaStream_t)stream});
 }
 
-int ssm_flow_pack_fwd(const ssm_tensor* img6, const ssm_tensor* flow4, const float* t,
+size_t ssm_packed_frames_bytes(int B, int H, int W, int dtype) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)B * 2 * H * W * 4 * (dtype == SSM_DTYPE_F32 ? 4 : 2);
+}
+
+int ssm_pack_frames(const ssm_tensor* img6, void* packed, int B, int H, int W, int dtype, void* stream) {
+    SSM_TRY(check_common(B, 1, 6, H, W, dtype, SSM_COORD_DIV));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    if (!packed) return fail(SSM_ERR_NULL, "packed is NULL");
+    if (((uintptr_t)packed) % 16 != 0) return fail(SSM_ERR_ALIGN, "packed must be 16-byte aligned");
+    return dispatch(dtype, SSM_COORD_DIV, PackFrames{img6, packed, B, H, W, (cudaStream_t)stream});
+}
+
+int ssm_flow_pack_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const float* t,
                       const ssm_tensor* out16, int B, int N, int H, int W,
                       int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 16, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
     SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
     SSM_TRY(check_tensor(out16, "out16", dtype, true));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
-    return dispatch(dtype, coord_mode, PackFwd{img6, flow4, t, out16, B, N, H, W, (cudaStream_t)stream});
+    return dispatch3(dtype, coord_mode, packed != nullptr, PackFwd{img6, packed, flow4, t, out16, B, N, H, W, (cudaStream_t)stream});
 }
 
-int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ssm_tensor* flow4,
-                      const float* t, const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
-                      int B, int N, int H, int W, int dtype, int coord_mode,
+int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const float* t, const ssm_tensor* grad_flow4,
+                      const ssm_tensor* grad_img6, int B, int N, int H, int W, int dtype, int coord_mode,
                       void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 16, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(grad16, "grad16", dtype, true));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
@@ -321,27 +362,29 @@ int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const ss
                         ssm_flow_pack_bwd_workspace_bytes(B, N, H, W), workspace ? workspace_bytes : (size_t)0);
         if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
     }
-    return dispatch(dtype, coord_mode, PackBwd{grad16, img6, flow4, t, grad_flow4, grad_img6, B, N, H, W,
-                                               workspace, (cudaStream_t)stream});
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     PackBwd{grad16, img6, packed, flow4, t, grad_flow4, grad_img6, B, N, H, W, workspace, (cudaStream_t)stream});
 }
 
-int ssm_fuse_fwd(const ssm_tensor* img6, const ssm_tensor* flows4, const ssm_tensor* out5,
+int ssm_fuse_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flows4, const ssm_tensor* out5,
                  const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
                  int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
     SSM_TRY(check_tensor(flows4, "flows4", dtype, true));
     SSM_TRY(check_tensor(out5, "out5", dtype, true));
     SSM_TRY(check_tensor(out3, "out3", dtype, true));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
-    return dispatch(dtype, coord_mode, FuseFwd{img6, flows4, out5, t, out3, B, N, H, W, (cudaStream_t)stream});
+    return dispatch3(dtype, coord_mode, packed != nullptr, FuseFwd{img6, packed, flows4, out5, t, out3, B, N, H, W, (cudaStream_t)stream});
 }
 
-int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const ssm_tensor* flows4,
-                 const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                 const ssm_tensor* flows4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
                  const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
                  int B, int N, int H, int W, int dtype, int coord_mode,
                  void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(grad3, "grad3", dtype, true));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
@@ -357,28 +400,43 @@ int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const ssm_tens
                         ssm_fuse_bwd_workspace_bytes(B, N, H, W), workspace ? workspace_bytes : (size_t)0);
         if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
     }
-    return dispatch(dtype, coord_mode, FuseBwd{grad3, img6, flows4, out5, t, grad_out5, grad_flows4, grad_img6,
-                                               B, N, H, W, workspace, (cudaStream_t)stream});
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     FuseBwd{grad3, img6, packed, flows4, out5, t, grad_out5, grad_flows4, grad_img6, B, N, H, W,
+                             workspace, (cudaStream_t)stream});
 }
 
 // ---------------------------------------------------------------------------------------------
-// Host-buffer entry point: pair-sized chunks, three slots of device scratch on three streams, so
-// the H2D copy of pair b+1, the kernels of pair b and the D2H copy of pair b-1 overlap.
+// Host-buffer entry point: pair-sized chunks, three slots of caller-owned device scratch on three
+// streams, so the H2D copy of pair b+1, the kernels of pair b and the D2H copy of pair b-1 overlap.
+static size_t host_slot_bytes(int N, int H, int W) {
+    const size_t npx = (size_t)H * W;
+    size_t floats = (size_t)(6 + 4 + 8 + 5 * N + 16 * N + 3 * N) * npx;   // img, flow, RGBx, out5, in16, out3
+    return (floats * sizeof(float) + 64 * sizeof(float) + 255) / 256 * 256;
+}
+
+size_t ssm_synthesize_host_scratch_bytes(int B, int N, int H, int W) {
+    if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
+    return host_slot_bytes(N, H, W) * (B < 3 ? B : 3);
+}
+
 int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const float* out5_host,
                         const float* t_host, float* out3_host, float* in16_host,
-                        int B, int N, int H, int W, int coord_mode) {
+                        int B, int N, int H, int W, int coord_mode, void* scratch_v, size_t scratch_bytes) {
     SSM_TRY(check_common(B, N, 16, H, W, SSM_DTYPE_F32, coord_mode));
     if (!img6_host || !flow4_host || !out5_host || !t_host || !out3_host)
         return fail(SSM_ERR_NULL, "ssm_synthesize_host: a required host pointer is NULL");
     if (N > 64) return fail(SSM_ERR_SHAPE, "ssm_synthesize_host: N must be <= 64 (got %d)", N);
+    if (!scratch_v || scratch_bytes < ssm_synthesize_host_scratch_bytes(B, N, H, W))
+        return fail(SSM_ERR_WORKSPACE, "ssm_synthesize_host: needs %zu bytes of device scratch, got %zu",
+                    ssm_synthesize_host_scratch_bytes(B, N, H, W), scratch_v ? scratch_bytes : (size_t)0);
+    if (((uintptr_t)scratch_v) % 256 != 0) return fail(SSM_ERR_ALIGN, "scratch must be 256-byte aligned");
     const size_t npx = (size_t)H * W;
-    const size_t per_pair = (size_t)(6 + 4 + 5 * N + 16 * N + 3 * N) * npx * sizeof(float) + 256;
+    const size_t per_pair = host_slot_bytes(N, H, W);
     const int slots = B < 3 ? B : 3;
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-    char* scratch = nullptr;
+    char* scratch = (char*)scratch_v;
     int rc = SSM_OK;
-    cudaError_t e = cudaMalloc((void**)&scratch, per_pair * slots);
-    if (e != cudaSuccess) return cuda_fail(e, "ssm_synthesize_host cudaMalloc");
+    cudaError_t e;
     for (int i = 0; i < slots && rc == SSM_OK; ++i) {
         e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host cudaStreamCreate");
@@ -388,15 +446,16 @@ int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const f
         cudaStream_t s = st[k];
         float* d_img = (float*)(scratch + per_pair * k);
         float* d_flow = d_img + 6 * npx;
-        float* d_out5 = d_flow + 4 * npx;
+        float* d_rgbx = d_flow + 4 * npx;
+        float* d_out5 = d_rgbx + 8 * npx;
         float* d_in16 = d_out5 + (size_t)5 * N * npx;
         float* d_out3 = d_in16 + (size_t)16 * N * npx;
         float* d_t = d_out3 + (size_t)3 * N * npx;
 #define SSM_H(expr) if (rc == SSM_OK && (e = (expr)) != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host " #expr)
         SSM_H(cudaMemcpyAsync(d_img, img6_host + (size_t)b * 6 * npx, 6 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
         SSM_H(cudaMemcpyAsync(d_flow, flow4_host + (size_t)b * 4 * npx, 4 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
-        SSM_H(cudaMemcpyAsync(d_out5, out5_host + (size_t)b * N * 5 * npx, (size_t)N * 5 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
         SSM_H(cudaMemcpyAsync(d_t, t_host + (size_t)b * N, N * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_out5, out5_host + (size_t)b * N * 5 * npx, (size_t)N * 5 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
         if (rc != SSM_OK) break;
         ssm_tensor T_img{d_img, (int64_t)(6 * npx), 0, (int64_t)npx};
         ssm_tensor T_flow{d_flow, (int64_t)(4 * npx), 0, (int64_t)npx};
@@ -404,8 +463,10 @@ int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const f
         ssm_tensor T_in16{d_in16, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
         ssm_tensor T_fl4{d_in16 + 6 * npx, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
         ssm_tensor T_out3{d_out3, (int64_t)(3 * N * npx), (int64_t)(3 * npx), (int64_t)npx};
-        rc = ssm_flow_pack_fwd(&T_img, &T_flow, d_t, &T_in16, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
-        if (rc == SSM_OK) rc = ssm_fuse_fwd(&T_img, &T_fl4, &T_out5, d_t, &T_out3, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
+        const void* rgbx = N >= 2 ? d_rgbx : nullptr;
+        if (rgbx) rc = ssm_pack_frames(&T_img, d_rgbx, 1, H, W, SSM_DTYPE_F32, s);
+        if (rc == SSM_OK) rc = ssm_flow_pack_fwd(&T_img, rgbx, &T_flow, d_t, &T_in16, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
+        if (rc == SSM_OK) rc = ssm_fuse_fwd(&T_img, rgbx, &T_fl4, &T_out5, d_t, &T_out3, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
         SSM_H(cudaMemcpyAsync(out3_host + (size_t)b * N * 3 * npx, d_out3, (size_t)N * 3 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (in16_host)
             SSM_H(cudaMemcpyAsync(in16_host + (size_t)b * N * 16 * npx, d_in16, (size_t)N * 16 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -417,7 +478,6 @@ int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const f
             if (e != cudaSuccess && rc == SSM_OK) rc = cuda_fail(e, "ssm_synthesize_host sync");
             cudaStreamDestroy(st[i]);
         }
-    cudaFree(scratch);
     return rc;
 }
 

@@ -130,6 +130,43 @@ __device__ __forceinline__ float bilerp(const Quad& v, const Taps& t) {
     return acc;
 }
 
+// ---- packed frames -----------------------------------------------------------------------------
+// The gathers are the L1-bound part of every kernel (ncu, profiles/r01a: 79 % L1tex throughput at
+// 48 % DRAM): with the flows of the bench workload the 32 lanes of a warp hit ~17 different
+// sectors per tap, and a planar NCHW frame needs one such request per tap AND channel.  A
+// pre-pass (pack_frames_kernel) therefore re-lays each frame as pixel-interleaved RGBx (4 elements
+// per pixel: 16 B in fp32, 8 B in bf16), so one request per tap brings all three channels.
+template <typename T> __device__ __forceinline__ void load_px(const T* p, float (&v)[3]);
+template <> __device__ __forceinline__ void load_px<float>(const float* p, float (&v)[3]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z;
+}
+template <> __device__ __forceinline__ void load_px<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[3]) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(q.x << 16);
+    v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16);
+}
+
+// corner values of the three colour planes of one frame.  PACKED: `frame` points at the RGBx copy
+// (H*W*4 elements); otherwise at plane 0 of the planar frame with channel stride sc.
+template <typename T, bool PACKED>
+__device__ __forceinline__ void gather3(const T* __restrict__ frame, long long sc, const Taps& t, int W, Quad (&q)[3]) {
+    if (PACKED) {
+        const T* p = frame + (long long)t.off * 4;
+        float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f}, c[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+        if (t.nw) load_px(p, a);
+        if (t.ne) load_px(p + 4, b);
+        if (t.sw) load_px(p + 4 * W, c);
+        if (t.se) load_px(p + 4 * W + 4, d);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { q[k].nw = a[k]; q[k].ne = b[k]; q[k].sw = c[k]; q[k].se = d[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[k] = gather_quad(frame + k * sc, t, W);
+    }
+}
+
 // accumulate d(bilerp)/d(ix), d(bilerp)/d(iy) times upstream gradient g
 __device__ __forceinline__ void bilerp_grad(const Quad& v, const Taps& t, float g, float& gix, float& giy) {
     float xe = t.fx + 1.0f, ys = t.fy + 1.0f;

@@ -5,8 +5,13 @@
 // in L1.  A CTA is a 32 x 8 pixel tile: a warp is 32 consecutive pixels of one row, so every
 // streaming load/store is one full 128-byte line per warp and the 32 gather addresses of a tap fall
 // into one or two lines when the flow is smooth; the 8 rows share the north/south tap lines in L1.
-// CTAs are numbered pair-major so that the two frames of a pair (50 MB at 1088x1920 fp32) stay
-// resident in the 126 MB L2 while all tiles and timesteps of that pair are processed.
+// CTAs are numbered pair-major so that the two frames of a pair (50 MB planar / 67 MB packed at
+// 1088x1920 fp32) stay resident in the 126 MB L2 while all tiles and timesteps of that pair are
+// processed.
+//
+// Every kernel that gathers from the frames is templated on PACKED: gather from the RGBx copy made
+// by pack_frames_kernel (one 16-byte request per tap) or from the planar frames (three 4-byte
+// requests per tap).  See ssm_device.cuh for why.
 //
 // All of it is HBM-bound element-wise + gather work: no tensor cores.
 #pragma once
@@ -36,8 +41,52 @@ __device__ __forceinline__ TileIdx tile_index(int H, int W) {
     return t;
 }
 
+// the two frames of pair b, as the gather source of the PACKED / planar variants
+template <typename T, bool PACKED> struct Frames {
+    const T* f0;
+    const T* f1;
+    long long sc;
+    __device__ __forceinline__ Frames(const View<const T>& img6, const T* __restrict__ packed, int b, long long npx) {
+        if (PACKED) {
+            f0 = packed + (long long)b * 8 * npx;
+            f1 = f0 + 4 * npx;
+            sc = 0;
+        } else {
+            f0 = img6.p + b * img6.sb;
+            f1 = f0 + 3 * img6.sc;
+            sc = img6.sc;
+        }
+    }
+};
+
 // =============================================================================================
-// a1: warp forward          reference scripts/models/layers.py:73-120
+// frame re-layout: B x 6 x H x W planar  ->  B x 2 x H x W x 4 (RGBx), once per batch of pairs
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS)
+pack_frames_kernel(View<const T> img6, T* __restrict__ packed, Geom g) {
+    TileIdx ti = tile_index(g.H, g.W);
+    if (!ti.valid) return;
+    const int p = ti.y * g.W + ti.x;
+    const long long npx = (long long)g.H * g.W;
+    const T* I = img6.p + ti.b * img6.sb + p;
+    T* o = packed + ((long long)ti.b * 8 * npx) + (long long)p * 4;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const float r = lds_(I + (3 * f + 0) * img6.sc), gg = lds_(I + (3 * f + 1) * img6.sc), bb = lds_(I + (3 * f + 2) * img6.sc);
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(o + f * 4 * npx) = make_float4(r, gg, bb, 0.0f);
+        } else {
+            const unsigned lo = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(r)) |
+                                ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(gg)) << 16);
+            const unsigned hi = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(bb));
+            *reinterpret_cast<uint2*>(o + f * 4 * npx) = make_uint2(lo, hi);
+        }
+    }
+}
+
+// =============================================================================================
+// a1: warp forward          reference scripts/models/layers.py:73-120   (any channel count: planar)
 // =============================================================================================
 template <typename T, int MODE>
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -91,37 +140,40 @@ warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, 
 //     batched over N timesteps (absorbs the loop + torch.stack of superslomo_r.py:167-179 and the
 //     three torch.cat of :364-367): reads 10 channels once, writes 16 channels per timestep.
 // =============================================================================================
-template <typename T, int MODE>
+template <typename T, int MODE, bool PACKED>
 __global__ void __launch_bounds__(TILE_THREADS)
-flow_pack_fwd_kernel(View<const T> img6, View<const T> flow4, const float* __restrict__ tv,
-                     View<T> out16, int N, Geom g) {
+flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flow4,
+                     const float* __restrict__ tv, View<T> out16, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
-    const T* I0 = img6.p + ti.b * img6.sb;
-    const T* I1 = I0 + 3 * img6.sc;
+    const long long npx = (long long)g.H * g.W;
+    const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
     const T* F = flow4.p + ti.b * flow4.sb + p;
     const float f01x = lds_(F), f01y = lds_(F + flow4.sc);
     const float f10x = lds_(F + 2 * flow4.sc), f10y = lds_(F + 3 * flow4.sc);
     float c0[3], c1[3];
+    if (PACKED) {
+        load_px(fr.f0 + (long long)p * 4, c0);
+        load_px(fr.f1 + (long long)p * 4, c1);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        c0[c] = ldg_(I0 + c * img6.sc + p);
-        c1[c] = ldg_(I1 + c * img6.sc + p);
+        for (int c = 0; c < 3; ++c) {
+            c0[c] = ldg_(fr.f0 + c * fr.sc + p);
+            c1[c] = ldg_(fr.f1 + c * fr.sc + p);
+        }
     }
-    for (int n = 0; n < N; ++n) {
-        const Coef k = make_coef(__ldg(tv + ti.b * N + n));
+    const float* tp = tv + ti.b * N;
+    T* O = out16.p + ti.b * out16.sb + p;
+    for (int n = 0; n < N; ++n, O += out16.sn) {
+        const Coef k = make_coef(__ldg(tp + n));
         const float e0x = est_t0(k, f01x, f10x), e0y = est_t0(k, f01y, f10y);   // F_t0  :353
         const float e1x = est_t1(k, f01x, f10x), e1y = est_t1(k, f01y, f10y);   // F_t1  :356
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);               // warp(img_1, F_t1) :361
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, e0x, e0y, g);               // warp(img_0, F_t0) :362
         Quad q1[3], q0[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            q1[c] = gather_quad(I1 + c * img6.sc, t1, g.W);
-            q0[c] = gather_quad(I0 + c * img6.sc, t0, g.W);
-        }
-        T* O = out16.p + ti.b * out16.sb + n * out16.sn + p;
+        gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
+        gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {                                           // :364-367
             sts_(O + (0 + c) * out16.sc, c1[c]);
@@ -138,9 +190,9 @@ flow_pack_fwd_kernel(View<const T> img6, View<const T> flow4, const float* __res
 // registers (deterministic).  With IMG_GRAD the direct image gradients (channels 0:3 and 13:16 of
 // grad16, summed over timesteps) go to an fp32 staging buffer and max |grad16[:, 3:6|10:13]| is
 // recorded; the warped-image part is added by the scatter pass (ssm_scatter.cuh).
-template <typename T, int MODE, bool IMG_GRAD>
+template <typename T, int MODE, bool PACKED, bool IMG_GRAD>
 __global__ void __launch_bounds__(TILE_THREADS)
-flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, View<const T> flow4,
+flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict__ packed, View<const T> flow4,
                      const float* __restrict__ tv, View<T> gflow4, float* __restrict__ gimg_direct,
                      ScatterHdr* hdr, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
@@ -149,16 +201,16 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, View<const T> flow4,
         const bool want_flow = gflow4.p != nullptr;
         const int p = ti.y * g.W + ti.x;
         const long long npx = (long long)g.H * g.W;
-        const T* I0 = img6.p + ti.b * img6.sb;
-        const T* I1 = I0 + 3 * img6.sc;
+        const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
         const T* F = flow4.p + ti.b * flow4.sb + p;
         const float f01x = lds_(F), f01y = lds_(F + flow4.sc);
         const float f10x = lds_(F + 2 * flow4.sc), f10y = lds_(F + 3 * flow4.sc);
         float d01x = 0, d01y = 0, d10x = 0, d10y = 0;
         float di0[3] = {0, 0, 0}, di1[3] = {0, 0, 0};
-        for (int n = 0; n < N; ++n) {
-            const Coef k = make_coef(__ldg(tv + ti.b * N + n));
-            const T* G = g16.p + ti.b * g16.sb + n * g16.sn + p;
+        const float* tp = tv + ti.b * N;
+        const T* G = g16.p + ti.b * g16.sb + p;
+        for (int n = 0; n < N; ++n, G += g16.sn) {
+            const Coef k = make_coef(__ldg(tp + n));
             float gw1[3], gw0[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -175,13 +227,14 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, View<const T> flow4,
             const float e1x = est_t1(k, f01x, f10x), e1y = est_t1(k, f01y, f10y);
             const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);
             const Taps t0 = make_taps<MODE>(ti.x, ti.y, e0x, e0y, g);
+            Quad q1[3], q0[3];
+            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
+            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
             float g1x = 0, g1y = 0, g0x = 0, g0y = 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                Quad q1 = gather_quad(I1 + c * img6.sc, t1, g.W);
-                Quad q0 = gather_quad(I0 + c * img6.sc, t0, g.W);
-                bilerp_grad(q1, t1, gw1[c], g1x, g1y);
-                bilerp_grad(q0, t0, gw0[c], g0x, g0y);
+                bilerp_grad(q1[c], t1, gw1[c], g1x, g1y);
+                bilerp_grad(q0[c], t0, gw0[c], g0x, g0y);
             }
             const float de1x = lds_(G + 6 * g16.sc) + coord_grad_to_flow<MODE>(g1x, g.xgrad, g.xnorm, g.xinv);
             const float de1y = lds_(G + 7 * g16.sc) + coord_grad_to_flow<MODE>(g1y, g.ygrad, g.ynorm, g.yinv);
@@ -214,20 +267,22 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, View<const T> flow4,
 // a3 + a4: extract_outputs + compute_output_image   flow_interpolation.py:374-429
 //     batched over N timesteps (the loop of superslomo_r.py:215-238)
 // =============================================================================================
-template <typename T, int MODE>
+template <typename T, int MODE, bool PACKED>
 __global__ void __launch_bounds__(TILE_THREADS)
-fuse_fwd_kernel(View<const T> img6, View<const T> flows4, View<const T> out5,
+fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const T> out5,
                 const float* __restrict__ tv, View<T> out3, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
-    const T* I0 = img6.p + ti.b * img6.sb;
-    const T* I1 = I0 + 3 * img6.sc;
-    for (int n = 0; n < N; ++n) {
-        const float tt = __ldg(tv + ti.b * N + n);
+    const long long npx = (long long)g.H * g.W;
+    const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
+    const float* tp = tv + ti.b * N;
+    const T* X = flows4.p + ti.b * flows4.sb + p;
+    const T* Y = out5.p + ti.b * out5.sb + p;
+    T* O = out3.p + ti.b * out3.sb + p;
+    for (int n = 0; n < N; ++n, X += flows4.sn, Y += out5.sn, O += out3.sn) {
+        const float tt = __ldg(tp + n);
         const float omt = __fsub_rn(1.0f, tt);
-        const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
-        const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
         const float v1 = sigmoid_(lds_(Y));                                          // :386-388
         const float v0 = 1.0f - v1;                                                  // :390
         const float f1x = __fadd_rn(lds_(X), lds_(Y + out5.sc));                     // :412
@@ -237,13 +292,9 @@ fuse_fwd_kernel(View<const T> img6, View<const T> flows4, View<const T> out5,
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);                    // :416
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);                    // :418
         Quad q0[3], q1[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            q0[c] = gather_quad(I0 + c * img6.sc, t0, g.W);
-            q1[c] = gather_quad(I1 + c * img6.sc, t1, g.W);
-        }
+        gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
+        gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
         const float z = omt * v0 + tt * v1;                                          // :425
-        T* O = out3.p + ti.b * out3.sb + n * out3.sn + p;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float w0 = v0 * bilerp(q0[c], t0);                                 // :420
@@ -258,20 +309,20 @@ fuse_fwd_kernel(View<const T> img6, View<const T> flows4, View<const T> out5,
 // (input_tensor[:, 6:10]).  With STAGE, d/d(warped I0), d/d(warped I1) are written to an fp32
 // staging buffer (B x N x 6 x H x W) and their max magnitude is recorded for the deterministic
 // image-gradient pass (ssm_scatter.cuh).
-template <typename T, int MODE, bool STAGE>
+template <typename T, int MODE, bool PACKED, bool STAGE>
 __global__ void __launch_bounds__(TILE_THREADS)
-fuse_bwd_kernel(View<const T> g3, View<const T> img6, View<const T> flows4, View<const T> out5,
-                const float* __restrict__ tv, View<T> gout5, View<T> gflows4,
+fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ packed, View<const T> flows4,
+                View<const T> out5, const float* __restrict__ tv, View<T> gout5, View<T> gflows4,
                 float* __restrict__ stage, ScatterHdr* hdr, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
     float amax = 0.0f;
     if (ti.valid) {
         const int p = ti.y * g.W + ti.x;
         const long long npx = (long long)g.H * g.W;
-        const T* I0 = img6.p + ti.b * img6.sb;
-        const T* I1 = I0 + 3 * img6.sc;
+        const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
+        const float* tp = tv + ti.b * N;
         for (int n = 0; n < N; ++n) {
-            const float tt = __ldg(tv + ti.b * N + n);
+            const float tt = __ldg(tp + n);
             const float omt = __fsub_rn(1.0f, tt);
             const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
             const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
@@ -285,11 +336,8 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, View<const T> flows4, View
             const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
             const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
             Quad q0[3], q1[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                q0[c] = gather_quad(I0 + c * img6.sc, t0, g.W);
-                q1[c] = gather_quad(I1 + c * img6.sc, t1, g.W);
-            }
+            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
+            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
             const float z = omt * v0 + tt * v1;
             const float rz = __fdiv_rn(1.0f, z);
             float dz = 0, dv0 = 0, dv1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;

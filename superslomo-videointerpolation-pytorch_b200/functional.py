@@ -120,35 +120,70 @@ def warp(x, flo, coord_mode=None):
 
 
 # ---------------------------------------------------------------------------------------------
+def pack_frames(img6):
+    """RGBx re-layout of a batch of frame pairs (ssm_pack_frames): B x 6 x H x W planar ->
+    B x 2 x H x W x 4 pixel-interleaved, so each bilinear tap of the gathers is one memory request.
+    Optional: flow_pack / fuse build it themselves when they are given N >= 2 timesteps; build it
+    once here and pass it to both to share it.  Not differentiable (it is a staging copy)."""
+    _same(img6)
+    img6 = _abi.dense_planes(img6.detach())
+    B, C6, H, W = img6.shape
+    if C6 != 6:
+        raise RuntimeError("pack_frames: expected B x 6 x H x W, got %s" % (tuple(img6.shape),))
+    packed = torch.empty((B, 2, H, W, 4), dtype=img6.dtype, device=img6.device)
+    with torch.cuda.device(img6.device):
+        rc = _abi.lib().ssm_pack_frames(_abi.ref(_abi.desc(img6, False)), ctypes.c_void_p(packed.data_ptr()),
+                                        B, H, W, _abi.dtype_code(img6), _abi.stream_ptr(img6.device))
+    _abi.check(rc, "ssm_pack_frames")
+    return packed
+
+
+def _packed_ptr(packed, img6):
+    if packed is None:
+        return None
+    B, _, H, W = img6.shape
+    if packed.shape != (B, 2, H, W, 4) or packed.dtype != img6.dtype or packed.device != img6.device \
+            or not packed.is_contiguous():
+        raise RuntimeError("packed frames do not match img_tensor (expected contiguous %s %s)"
+                           % ((B, 2, H, W, 4), img6.dtype))
+    return ctypes.c_void_p(packed.data_ptr())
+
+
+_AUTO_PACK_MIN_TIMESTEPS = 2
+
+
 class _FlowPack(torch.autograd.Function):
     """compute_inputs for N timesteps -- reference scripts/models/flow_interpolation.py:338-372"""
 
     @staticmethod
-    def forward(ctx, img6, flow4, tvec, N, mode):
+    def forward(ctx, img6, flow4, tvec, N, mode, packed):
         _same(img6, flow4)
         img6, flow4 = _abi.dense_planes(img6), _abi.dense_planes(flow4)
         B, C6, H, W = img6.shape
         if C6 != 6 or flow4.shape != (B, 4, H, W):
             raise RuntimeError("compute_inputs: expected img B x 6 x H x W and flow B x 4 x H x W, got %s and %s"
                                % (tuple(img6.shape), tuple(flow4.shape)))
+        if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+            packed = pack_frames(img6)
         out = torch.empty((B, N, 16, H, W), dtype=img6.dtype, device=img6.device)
         with torch.cuda.device(img6.device):
-            rc = _abi.lib().ssm_flow_pack_fwd(_abi.ref(_abi.desc(img6, False)), _abi.ref(_abi.desc(flow4, False)),
+            rc = _abi.lib().ssm_flow_pack_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
+                                              _abi.ref(_abi.desc(flow4, False)),
                                               ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(out, True)),
                                               B, N, H, W, _abi.dtype_code(img6), mode, _abi.stream_ptr(img6.device))
         _abi.check(rc, "ssm_flow_pack_fwd")
-        ctx.save_for_backward(img6, flow4, tvec)
+        ctx.save_for_backward(img6, flow4, tvec, packed)
         ctx.N, ctx.mode = N, mode
         return out
 
     @staticmethod
     def backward(ctx, g16):
-        img6, flow4, tvec = ctx.saved_tensors
+        img6, flow4, tvec, packed = ctx.saved_tensors
         B, _, H, W = img6.shape
         N = ctx.N
         need_i, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_i or need_f):
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         g16 = _abi.dense_planes(g16.to(img6.dtype))
         gi = torch.empty_like(img6, memory_format=torch.contiguous_format) if need_i else None
         gf = torch.empty_like(flow4, memory_format=torch.contiguous_format) if need_f else None
@@ -160,21 +195,23 @@ class _FlowPack(torch.autograd.Function):
             ws_ptr = ctypes.c_void_p(ws.data_ptr())
         with torch.cuda.device(img6.device):
             rc = L.ssm_flow_pack_bwd(_abi.ref(_abi.desc(g16, True)), _abi.ref(_abi.desc(img6, False)),
+                                     _packed_ptr(packed, img6),
                                      _abi.ref(_abi.desc(flow4, False)), ctypes.c_void_p(tvec.data_ptr()),
                                      _abi.ref(_abi.desc(gf, False)), _abi.ref(_abi.desc(gi, False)),
                                      B, N, H, W, _abi.dtype_code(img6), ctx.mode, ws_ptr, ws_bytes,
                                      _abi.stream_ptr(img6.device))
         _abi.check(rc, "ssm_flow_pack_bwd")
-        return gi, gf, None, None, None
+        return gi, gf, None, None, None, None
 
 
-def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None):
+def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None, packed=None):
     """Stage-2 input for n_timesteps intermediate times of every pair: B x N x 16 x H x W.
 
-    t holds B*N values (t[b, n]); a single value is broadcast."""
+    t holds B*N values (t[b, n]); a single value is broadcast.  packed: optional result of
+    pack_frames(img6) to share the RGBx copy between flow_pack and fuse."""
     B = img6.shape[0]
     tvec = _t_vector(t, B * n_timesteps, img6.device)
-    return _FlowPack.apply(img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode))
+    return _FlowPack.apply(img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode), packed)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -182,7 +219,7 @@ class _Fuse(torch.autograd.Function):
     """extract_outputs + compute_output_image for N timesteps -- flow_interpolation.py:374-429"""
 
     @staticmethod
-    def forward(ctx, img6, in16, out5, tvec, mode):
+    def forward(ctx, img6, in16, out5, tvec, mode, packed):
         _same(img6, in16, out5)
         img6, in16, out5 = _abi.dense_planes(img6), _abi.dense_planes(in16), _abi.dense_planes(out5)
         B, C6, H, W = img6.shape
@@ -190,26 +227,29 @@ class _Fuse(torch.autograd.Function):
         if C6 != 6 or in16.shape != (B, N, 16, H, W) or out5.shape != (B, N, 5, H, W):
             raise RuntimeError("compute_output_image: expected img B x 6, input B x N x 16, output B x N x 5 "
                                "(x H x W), got %s, %s, %s" % (tuple(img6.shape), tuple(in16.shape), tuple(out5.shape)))
+        if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+            packed = pack_frames(img6)
         out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
         flows4 = in16[:, :, 6:10]
         with torch.cuda.device(img6.device):
-            rc = _abi.lib().ssm_fuse_fwd(_abi.ref(_abi.desc(img6, False)), _abi.ref(_abi.desc(flows4, True)),
+            rc = _abi.lib().ssm_fuse_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
+                                         _abi.ref(_abi.desc(flows4, True)),
                                          _abi.ref(_abi.desc(out5, True)), ctypes.c_void_p(tvec.data_ptr()),
                                          _abi.ref(_abi.desc(out, True)), B, N, H, W, _abi.dtype_code(img6), mode,
                                          _abi.stream_ptr(img6.device))
         _abi.check(rc, "ssm_fuse_fwd")
-        ctx.save_for_backward(img6, in16, out5, tvec)
+        ctx.save_for_backward(img6, in16, out5, tvec, packed)
         ctx.mode = mode
         return out
 
     @staticmethod
     def backward(ctx, g3):
-        img6, in16, out5, tvec = ctx.saved_tensors
+        img6, in16, out5, tvec, packed = ctx.saved_tensors
         B, _, H, W = img6.shape
         N = in16.shape[1]
         need_i, need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if not (need_i or need_x or need_y):
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         g3 = _abi.dense_planes(g3.to(img6.dtype))
         gi = torch.empty_like(img6, memory_format=torch.contiguous_format) if need_i else None
         gy = torch.empty_like(out5, memory_format=torch.contiguous_format) if need_y else None
@@ -227,44 +267,64 @@ class _Fuse(torch.autograd.Function):
             ws_ptr = ctypes.c_void_p(ws.data_ptr())
         with torch.cuda.device(img6.device):
             rc = L.ssm_fuse_bwd(_abi.ref(_abi.desc(g3, True)), _abi.ref(_abi.desc(img6, False)),
+                                _packed_ptr(packed, img6),
                                 _abi.ref(_abi.desc(in16[:, :, 6:10], True)), _abi.ref(_abi.desc(out5, True)),
                                 ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(gy, True)),
                                 _abi.ref(_abi.desc(gx_flows, True)), _abi.ref(_abi.desc(gi, False)),
                                 B, N, H, W, _abi.dtype_code(img6), ctx.mode, ws_ptr, ws_bytes,
                                 _abi.stream_ptr(img6.device))
         _abi.check(rc, "ssm_fuse_bwd")
-        return gi, gx, gy, None, None
+        return gi, gx, gy, None, None, None
 
 
-def fuse(img6, in16, out5, t, coord_mode=None):
+def fuse(img6, in16, out5, t, coord_mode=None, packed=None):
     """Fused frames for every (pair, timestep): img6 B x 6, in16 B x N x 16, out5 B x N x 5 -> B x N x 3."""
     B, N = in16.shape[0], in16.shape[1]
     tvec = _t_vector(t, B * N, img6.device)
-    return _Fuse.apply(img6, in16, out5, tvec, _resolve_mode(coord_mode))
+    return _Fuse.apply(img6, in16, out5, tvec, _resolve_mode(coord_mode), packed)
 
 
 # ---------------------------------------------------------------------------------------------
-def synthesize_host(img6, flow4, out5, t, coord_mode=None, return_inputs=False):
+def synthesize_host(img6, flow4, out5, t, coord_mode=None, return_inputs=False, out=None, scratch=None):
     """Whole path on HOST tensors (pinned memory recommended) through ssm_synthesize_host: copies
-    in, runs both fused kernels for all N timesteps of every pair, copies the frames out.
+    in, runs the fused kernels for all N timesteps of every pair, copies the frames out.
 
     img6 B x 6 x H x W, flow4 B x 4 x H x W, out5 B x N x 5 x H x W, t B*N values; fp32 CPU tensors.
-    Returns out3 B x N x 3 x H x W (and in16 B x N x 16 x H x W if return_inputs) as pinned CPU tensors.
+    Returns out3 B x N x 3 x H x W (and in16 B x N x 16 x H x W if return_inputs) as CPU tensors.
+    out: optional preallocated (pinned) result tensor; scratch: optional uint8 CUDA tensor of
+    ssm_synthesize_host_scratch_bytes -- pass both to keep allocations out of repeated calls.
     """
     for name, x in (("img6", img6), ("flow4", flow4), ("out5", out5)):
         if x.device.type != "cpu" or x.dtype != torch.float32 or not x.is_contiguous():
             raise RuntimeError("synthesize_host: %s must be a contiguous fp32 CPU tensor" % name)
+    if not torch.cuda.is_available():
+        raise RuntimeError("synthesize_host needs a CUDA device -- there is no CPU fallback")
     B, _, H, W = img6.shape
     N = out5.shape[1]
     tv = torch.as_tensor(t, dtype=torch.float32).reshape(-1).contiguous()
     if tv.numel() != B * N:
         raise RuntimeError("synthesize_host: t needs B*N values")
-    pin = torch.cuda.is_available()
-    out3 = torch.empty((B, N, 3, H, W), dtype=torch.float32, pin_memory=pin)
-    in16 = torch.empty((B, N, 16, H, W), dtype=torch.float32, pin_memory=pin) if return_inputs else None
-    rc = _abi.lib().ssm_synthesize_host(
-        ctypes.c_void_p(img6.data_ptr()), ctypes.c_void_p(flow4.data_ptr()), ctypes.c_void_p(out5.data_ptr()),
-        ctypes.c_void_p(tv.data_ptr()), ctypes.c_void_p(out3.data_ptr()),
-        ctypes.c_void_p(in16.data_ptr()) if in16 is not None else None, B, N, H, W, _resolve_mode(coord_mode))
+    L = _abi.lib()
+    if out is None:
+        out = torch.empty((B, N, 3, H, W), dtype=torch.float32, pin_memory=True)
+    elif out.shape != (B, N, 3, H, W) or out.dtype != torch.float32 or not out.is_contiguous() or out.is_cuda:
+        raise RuntimeError("synthesize_host: out must be a contiguous fp32 CPU tensor of shape B x N x 3 x H x W")
+    in16 = torch.empty((B, N, 16, H, W), dtype=torch.float32, pin_memory=True) if return_inputs else None
+    need = L.ssm_synthesize_host_scratch_bytes(B, N, H, W)
+    if scratch is None:
+        scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    elif not scratch.is_cuda or scratch.numel() * scratch.element_size() < need:
+        raise RuntimeError("synthesize_host: scratch must be a CUDA tensor of at least %d bytes" % need)
+    with torch.cuda.device(scratch.device):
+        torch.cuda.current_stream().synchronize()      # scratch may still be in use by earlier work
+        rc = L.ssm_synthesize_host(
+            ctypes.c_void_p(img6.data_ptr()), ctypes.c_void_p(flow4.data_ptr()), ctypes.c_void_p(out5.data_ptr()),
+            ctypes.c_void_p(tv.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+            ctypes.c_void_p(in16.data_ptr()) if in16 is not None else None, B, N, H, W, _resolve_mode(coord_mode),
+            ctypes.c_void_p(scratch.data_ptr()), scratch.numel() * scratch.element_size())
     _abi.check(rc, "ssm_synthesize_host")
-    return (out3, in16) if return_inputs else out3
+    return (out, in16) if return_inputs else out
+
+
+def synthesize_host_scratch_bytes(B, N, H, W):
+    return int(_abi.lib().ssm_synthesize_host_scratch_bytes(B, N, H, W))

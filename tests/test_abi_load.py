@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_error_string():
-    assert ssm_b200.abi_version() == 1
+    assert ssm_b200.abi_version() == 2
     assert isinstance(_abi.lib().ssm_last_error(), bytes)
 
 
@@ -43,13 +43,16 @@ def test_argument_errors_without_gpu():
     rc = L.ssm_warp_fwd(ctypes.byref(t), ctypes.byref(t), ctypes.byref(t), 0, 3, 8, 8, 0, 0, None)
     assert rc == -2
     # bad dtype / coord mode
-    assert L.ssm_fuse_fwd(None, None, None, None, None, 1, 1, 8, 8, 7, 0, None) == -3
-    assert L.ssm_fuse_fwd(None, None, None, None, None, 1, 1, 8, 8, 0, 5, None) == -3
+    assert L.ssm_fuse_fwd(None, None, None, None, None, None, 1, 1, 8, 8, 7, 0, None) == -3
+    assert L.ssm_fuse_fwd(None, None, None, None, None, None, 1, 1, 8, 8, 0, 5, None) == -3
     # misaligned pointer
     bad = _abi.SsmTensor(3, 64, 0, 64)
     assert L.ssm_warp_fwd(ctypes.byref(bad), ctypes.byref(bad), ctypes.byref(bad), 1, 1, 8, 8, 0, 0, None) == -4
     # host entry point: NULL host pointers
-    assert L.ssm_synthesize_host(None, None, None, None, None, None, 1, 1, 8, 8, 0) == -1
+    assert L.ssm_synthesize_host(None, None, None, None, None, None, 1, 1, 8, 8, 0, None, 0) == -1
+    # packed frames buffer must be 16-byte aligned
+    ok = _abi.SsmTensor(64, 64, 0, 64)
+    assert L.ssm_pack_frames(ctypes.byref(ok), ctypes.c_void_p(8), 1, 8, 8, 0, None) == -4
 
 
 def test_workspace_sizes():
@@ -59,6 +62,9 @@ def test_workspace_sizes():
     assert L.ssm_flow_pack_bwd_workspace_bytes(2, 7, 32, 48) == 256 + 12 * 2 * 6 * npx
     assert L.ssm_fuse_bwd_workspace_bytes(2, 7, 32, 48) == 256 + 8 * 2 * 6 * npx + 4 * 2 * 7 * 6 * npx
     assert L.ssm_warp_bwd_workspace_bytes(0, 3, 32, 48) == 0
+    assert L.ssm_packed_frames_bytes(2, 32, 48, 0) == 2 * 2 * npx * 16
+    assert L.ssm_packed_frames_bytes(2, 32, 48, 1) == 2 * 2 * npx * 8
+    assert L.ssm_synthesize_host_scratch_bytes(5, 7, 32, 48) >= 3 * 4 * npx * (6 + 4 + 8 + 24 * 7)
 
 
 def test_cpu_tensors_are_refused():

@@ -130,6 +130,31 @@ def test_warp_channels_and_partial_grads(C):
             assert_close_fp32(fd.grad, want_gf, "warp grad flow")
 
 
+def test_packed_and_planar_gathers_agree_bitwise():
+    """The RGBx staging copy changes how taps are fetched, not what is computed."""
+    B, N, H, W = 2, 3, 40, 72
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=60, kind="border")
+    a, f, y, td = _dev(img6), _dev(flow4), _dev(out5), _dev(t)
+    rgbx = ssm_b200.pack_frames(a)
+    assert rgbx.shape == (B, 2, H, W, 4)
+    assert torch.equal(rgbx[:, 0, :, :, :3].permute(0, 3, 1, 2), a[:, 0:3])
+    assert torch.equal(rgbx[:, 1, :, :, :3].permute(0, 3, 1, 2), a[:, 3:6])
+    packed16 = ssm_b200.flow_pack(a, f, td, n_timesteps=N, packed=rgbx)
+    for n in range(N):   # N = 1 calls take the planar path
+        planar16 = ssm_b200.flow_pack(a, f, td[:, n], n_timesteps=1)
+        assert torch.equal(packed16[:, n], planar16[:, 0])
+        planar3 = ssm_b200.fuse(a, packed16[:, n:n + 1], y[:, n:n + 1], td[:, n])
+        packed3 = ssm_b200.fuse(a, packed16[:, n:n + 1], y[:, n:n + 1], td[:, n], packed=rgbx)
+        assert torch.equal(planar3, packed3)
+    # bf16 storage
+    ab = a.bfloat16()
+    rb = ssm_b200.pack_frames(ab)
+    assert torch.equal(rb[:, 1, :, :, :3].permute(0, 3, 1, 2), ab[:, 3:6])
+    p16 = ssm_b200.flow_pack(ab, f.bfloat16(), td, n_timesteps=N, packed=rb)
+    q16 = ssm_b200.flow_pack(ab, f.bfloat16(), td[:, 1], n_timesteps=1)
+    assert torch.equal(p16[:, 1], q16[:, 0])
+
+
 def test_strided_views_are_accepted():
     """compute_output_image receives channel-sliced views (flow_interpolation.py:402-403)."""
     B, H, W = 2, 32, 64

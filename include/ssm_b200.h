@@ -66,6 +66,11 @@ typedef struct ssm_tensor {
 int         ssm_version(void);
 const char* ssm_last_error(void);
 
+/* Self-test (known-answer): compares the kernels' 5-instruction constant-divisor division with the
+ * IEEE division for the divisor max(size-1,1) over every finite fp32 dividend; adds the number of
+ * bit mismatches to *mismatches_device (a zero-initialised device counter).  Expected: 0. */
+int ssm_selftest_division(int size, unsigned long long* mismatches_device, void* stream);
+
 /* ---- a1: layers.warp(x, flo)  [reference scripts/models/layers.py:73-120] --------------------
  * out[b,c,y,x] = bilinear(img[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside,
  * align_corners=True.  img/out: B x C x H x W, flow: B x 2 x H x W. */

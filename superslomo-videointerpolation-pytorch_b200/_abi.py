@@ -22,7 +22,7 @@ EXPORTS = (
     "ssm_fuse_fwd", "ssm_fuse_bwd",
     "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
     "ssm_packed_frames_bytes", "ssm_pack_frames",
-    "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes",
+    "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
 )
 
 
@@ -51,6 +51,8 @@ def lib():
     L.ssm_last_error.restype = ctypes.c_char_p
     L.ssm_warp_fwd.argtypes = [P, P, P, I, I, I, I, I, I, V]
     L.ssm_warp_bwd.argtypes = [P, P, P, P, P, I, I, I, I, I, I, V, Z, V]
+    L.ssm_selftest_division.argtypes = [I, V, V]
+    L.ssm_selftest_division.restype = I
     L.ssm_pack_frames.argtypes = [P, V, I, I, I, I, V]
     L.ssm_flow_pack_fwd.argtypes = [P, V, P, V, P, I, I, I, I, I, I, V]
     L.ssm_flow_pack_bwd.argtypes = [P, P, V, P, V, P, P, I, I, I, I, I, I, V, Z, V]

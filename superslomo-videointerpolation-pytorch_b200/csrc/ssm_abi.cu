@@ -67,6 +67,8 @@ int check_tensor(const ssm_tensor* t, const char* name, int dtype, bool required
     }
     size_t esz = dtype == SSM_DTYPE_F32 ? 4 : 2;
     if (((uintptr_t)t->data) % esz != 0) return fail(SSM_ERR_ALIGN, "%s is not aligned to its element size", name);
+    const long long sc = t->stride_c < 0 ? -t->stride_c : t->stride_c;
+    if (sc > ((1ll << 31) - 1) / 16) return fail(SSM_ERR_SHAPE, "%s: channel stride %lld too large (32-bit channel offsets)", name, sc);
     return SSM_OK;
 }
 
@@ -263,6 +265,21 @@ struct FuseBwd {
     }
 };
 
+// exhaustive check of div_rn_const against the IEEE division for one divisor
+__global__ void selftest_division_kernel(float d, float y, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float s = __uint_as_float((unsigned)i);
+        if (!isfinite(s)) continue;
+        const float want = __fdiv_rn(s, d);
+        if (want != 0.0f && fabsf(want) < 1.17549435e-38f) continue;   // denormal quotients: not on the path
+        const float got = div_rn_const(s, d, y);
+        if (__float_as_uint(got) != __float_as_uint(want)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 #define SSM_TRY(expr)            \
     do {                         \
         int rc__ = (expr);       \
@@ -288,6 +305,15 @@ size_t ssm_flow_pack_bwd_workspace_bytes(int B, int N, int H, int W) {
 size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W) {
     if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
     return HDR_BYTES + sizeof(long long) * (size_t)B * 6 * H * W + sizeof(float) * (size_t)B * N * 6 * H * W;
+}
+
+int ssm_selftest_division(int size, unsigned long long* mismatches_device, void* stream) {
+    if (size < 1) return fail(SSM_ERR_SHAPE, "size must be >= 1");
+    if (!mismatches_device) return fail(SSM_ERR_NULL, "mismatches_device is NULL");
+    const float d = (float)(size - 1 > 1 ? size - 1 : 1);
+    selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d, 1.0f / d, mismatches_device);
+    SSM_LAUNCH_CHECK("ssm_selftest_division");
+    return SSM_OK;
 }
 
 int ssm_warp_fwd(const ssm_tensor* img, const ssm_tensor* flow, const ssm_tensor* out,

@@ -56,12 +56,26 @@ struct Geom {
     float xgrad, ygrad;  // float(W-1)/2, float(H-1)/2               ATen backward multiplier
 };
 
+// Correctly rounded s / d for a launch-constant divisor d with y = RN(1/d) precomputed on the host:
+// two Markstein correction steps (q <- q + (s - q*d)*y with the residual exact in an FMA).  After
+// the first step q is a faithful rounding of s/d; with y correctly rounded and the significand of
+// d not all ones (d = W-1 is a small integer) the second step then returns RN(s/d).  5 instructions
+// instead of the ~27 of the generic IEEE division sequence; checked exhaustively against
+// __fdiv_rn over every fp32 s by ssm_selftest_division (tests/test_parity_gpu.py).
+__device__ __forceinline__ float div_rn_const(float s, float d, float y) {
+    float q = __fmul_rn(s, y);
+    float r = __fmaf_rn(-q, d, s);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-q, d, s);
+    return __fmaf_rn(r, y, q);
+}
+
 // layers.py:100 (grid + flo), :112 (2.0*u/max(W-1,1) - 1.0), ATen ((c + 1)/2)*(size - 1)
 template <int MODE>
 __device__ __forceinline__ float sample_coord(float pos, float flow, float norm, float inv, float m1) {
     float g = __fadd_rn(pos, flow);
     float s = __fmul_rn(2.0f, g);
-    float n = (MODE == SSM_COORD_DIV) ? __fdiv_rn(s, norm) : __fmul_rn(s, inv);
+    float n = (MODE == SSM_COORD_DIV) ? div_rn_const(s, norm, inv) : __fmul_rn(s, inv);
     n = __fsub_rn(n, 1.0f);
     float a = __fadd_rn(n, 1.0f);
     a = __fmul_rn(a, 0.5f);
@@ -73,7 +87,7 @@ __device__ __forceinline__ float sample_coord(float pos, float flow, float norm,
 template <int MODE>
 __device__ __forceinline__ float coord_grad_to_flow(float gi, float gmul, float norm, float inv) {
     float g = __fmul_rn(gi, gmul);
-    g = (MODE == SSM_COORD_DIV) ? __fdiv_rn(g, norm) : __fmul_rn(g, inv);
+    g = (MODE == SSM_COORD_DIV) ? div_rn_const(g, norm, inv) : __fmul_rn(g, inv);
     return __fmul_rn(g, 2.0f);
 }
 
@@ -199,7 +213,9 @@ __device__ __forceinline__ float est_t1(const Coef& c, float f01, float f10) {
     return __fsub_rn(__fmul_rn(c.c10, f01), __fmul_rn(c.c11, f10));
 }
 
-__device__ __forceinline__ float sigmoid_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// sigmoid and the final normalisation are not coordinate arithmetic: a correctly rounded reciprocal
+// (1 ulp off an IEEE division at worst) is far inside the 1e-5 bar
+__device__ __forceinline__ float sigmoid_(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
 
 // ---- bookkeeping of the deterministic image-gradient accumulation (see ssm_scatter.cuh) --------
 struct ScatterHdr {          // lives at the start of the workspace, zeroed before every launch

@@ -164,7 +164,8 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
         }
     }
     const float* tp = tv + ti.b * N;
-    T* O = out16.p + ti.b * out16.sb + p;
+    T* __restrict__ O = out16.p + ti.b * out16.sb + p;
+    const int osc = (int)out16.sc;   // fits 32 bits (checked on the host): one IMAD.WIDE per address
     for (int n = 0; n < N; ++n, O += out16.sn) {
         const Coef k = make_coef(__ldg(tp + n));
         const float e0x = est_t0(k, f01x, f10x), e0y = est_t0(k, f01y, f10y);   // F_t0  :353
@@ -176,13 +177,13 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
         gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {                                           // :364-367
-            sts_(O + (0 + c) * out16.sc, c1[c]);
-            sts_(O + (3 + c) * out16.sc, bilerp(q1[c], t1));
-            sts_(O + (10 + c) * out16.sc, bilerp(q0[c], t0));
-            sts_(O + (13 + c) * out16.sc, c0[c]);
+            sts_(O + (0 + c) * osc, c1[c]);
+            sts_(O + (3 + c) * osc, bilerp(q1[c], t1));
+            sts_(O + (10 + c) * osc, bilerp(q0[c], t0));
+            sts_(O + (13 + c) * osc, c0[c]);
         }
-        sts_(O + 6 * out16.sc, e1x); sts_(O + 7 * out16.sc, e1y);
-        sts_(O + 8 * out16.sc, e0x); sts_(O + 9 * out16.sc, e0y);
+        sts_(O + 6 * osc, e1x); sts_(O + 7 * osc, e1y);
+        sts_(O + 8 * osc, e0x); sts_(O + 9 * osc, e0y);
     }
 }
 
@@ -277,30 +278,32 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
     const long long npx = (long long)g.H * g.W;
     const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
     const float* tp = tv + ti.b * N;
-    const T* X = flows4.p + ti.b * flows4.sb + p;
-    const T* Y = out5.p + ti.b * out5.sb + p;
-    T* O = out3.p + ti.b * out3.sb + p;
+    const T* __restrict__ X = flows4.p + ti.b * flows4.sb + p;
+    const T* __restrict__ Y = out5.p + ti.b * out5.sb + p;
+    T* __restrict__ O = out3.p + ti.b * out3.sb + p;
+    // channel strides fit 32 bits (checked on the host): one IMAD.WIDE per address
+    const int xsc = (int)flows4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;
     for (int n = 0; n < N; ++n, X += flows4.sn, Y += out5.sn, O += out3.sn) {
         const float tt = __ldg(tp + n);
         const float omt = __fsub_rn(1.0f, tt);
         const float v1 = sigmoid_(lds_(Y));                                          // :386-388
         const float v0 = 1.0f - v1;                                                  // :390
-        const float f1x = __fadd_rn(lds_(X), lds_(Y + out5.sc));                     // :412
-        const float f1y = __fadd_rn(lds_(X + flows4.sc), lds_(Y + 2 * out5.sc));
-        const float f0x = __fadd_rn(lds_(X + 2 * flows4.sc), lds_(Y + 3 * out5.sc)); // :413
-        const float f0y = __fadd_rn(lds_(X + 3 * flows4.sc), lds_(Y + 4 * out5.sc));
+        const float f1x = __fadd_rn(lds_(X), lds_(Y + ysc));                         // :412
+        const float f1y = __fadd_rn(lds_(X + xsc), lds_(Y + 2 * ysc));
+        const float f0x = __fadd_rn(lds_(X + 2 * xsc), lds_(Y + 3 * ysc));           // :413
+        const float f0y = __fadd_rn(lds_(X + 3 * xsc), lds_(Y + 4 * ysc));
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);                    // :416
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);                    // :418
         Quad q0[3], q1[3];
         gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
         gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
-        const float z = omt * v0 + tt * v1;                                          // :425
+        const float rz = __frcp_rn(omt * v0 + tt * v1);                              // 1/Z  :425
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float w0 = v0 * bilerp(q0[c], t0);                                 // :420
             const float w1 = v1 * bilerp(q1[c], t1);                                 // :421
             const float s = omt * w0 + tt * w1;                                      // :423
-            sts_(O + c * out3.sc, __fdiv_rn(s, z));                                  // :427
+            sts_(O + c * osc, s * rz);                                               // :427
         }
     }
 }
@@ -339,7 +342,7 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ pack
             gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
             gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
             const float z = omt * v0 + tt * v1;
-            const float rz = __fdiv_rn(1.0f, z);
+            const float rz = __frcp_rn(z);
             float dz = 0, dv0 = 0, dv1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
             float* st = STAGE ? stage + ((long long)(ti.b * N + n) * 6) * npx + p : nullptr;
 #pragma unroll

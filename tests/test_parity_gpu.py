@@ -313,3 +313,16 @@ def test_host_entry_point_matches_device_path():
         r16 = c_oracle.compute_inputs(img6, flow4, t[:, n])
         assert_close_fp32(out3[:, n], c_oracle.compute_output_image(img6, r16, out5[:, n].contiguous(), t[:, n]),
                           "host entry point vs oracle")
+
+
+@pytest.mark.parametrize("size", [1920, 1088, 352, 1280, 736, 3840, 2176, 2, 1, 37, 4097])
+def test_constant_divisor_division_is_ieee_exact(size):
+    """Known-answer self-test: the kernels' 5-instruction division by max(size-1,1) equals the IEEE
+    division bit for bit over every finite fp32 dividend (2^32 cases per divisor)."""
+    import ctypes
+    from ssm_b200 import _abi
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    rc = _abi.lib().ssm_selftest_division(size, ctypes.c_void_p(counter.data_ptr()), _abi.stream_ptr(torch.device(DEV)))
+    _abi.check(rc, "ssm_selftest_division")
+    torch.cuda.synchronize()
+    assert counter.item() == 0, "%d mismatches for size %d" % (counter.item(), size)

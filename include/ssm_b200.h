@@ -67,8 +67,11 @@ int         ssm_version(void);
 const char* ssm_last_error(void);
 
 /* Self-test (known-answer): compares the kernels' 5-instruction constant-divisor division with the
- * IEEE division for the divisor max(size-1,1) over every finite fp32 dividend; adds the number of
- * bit mismatches to *mismatches_device (a zero-initialised device counter).  Expected: 0. */
+ * IEEE division for the divisor max(size-1,1) over every finite fp32 dividend s.  mismatches_device
+ * points at three zero-initialised device counters: [0] += dividends for which the normalised
+ * coordinate rn(s/d - 1) -- the value the path consumes (layers.py:112) -- differs (expected 0);
+ * [1] += dividends whose raw quotient differs (only quotients in the denormal range, where the
+ * residual underflows, may); [2] = bits of one such dividend. */
 int ssm_selftest_division(int size, unsigned long long* mismatches_device, void* stream);
 
 /* ---- a1: layers.warp(x, flo)  [reference scripts/models/layers.py:73-120] --------------------

@@ -265,19 +265,22 @@ struct FuseBwd {
     }
 };
 
-// exhaustive check of div_rn_const against the IEEE division for one divisor
-__global__ void selftest_division_kernel(float d, float y, unsigned long long* mismatches) {
-    unsigned long long bad = 0;
+// exhaustive check of div_rn_const against the IEEE division for one divisor.
+// out[0] += dividends whose NORMALISED COORDINATE rn(q - 1) differs (what the path consumes,
+// layers.py:112); out[1] += dividends whose raw quotient differs; out[2] = one such dividend's bits.
+__global__ void selftest_division_kernel(float d, float y, unsigned long long* out) {
+    unsigned long long bad_n = 0, bad_q = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (1ull << 32);
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float s = __uint_as_float((unsigned)i);
         if (!isfinite(s)) continue;
         const float want = __fdiv_rn(s, d);
-        if (want != 0.0f && fabsf(want) < 1.17549435e-38f) continue;   // denormal quotients: not on the path
         const float got = div_rn_const(s, d, y);
-        if (__float_as_uint(got) != __float_as_uint(want)) ++bad;
+        if (__float_as_uint(got) != __float_as_uint(want)) { ++bad_q; out[2] = i; }
+        if (__float_as_uint(__fsub_rn(got, 1.0f)) != __float_as_uint(__fsub_rn(want, 1.0f))) ++bad_n;
     }
-    if (bad) atomicAdd(mismatches, bad);
+    if (bad_n) atomicAdd(out, bad_n);
+    if (bad_q) atomicAdd(out + 1, bad_q);
 }
 
 #define SSM_TRY(expr)            \

@@ -269,7 +269,7 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict_
 //     batched over N timesteps (the loop of superslomo_r.py:215-238)
 // =============================================================================================
 template <typename T, int MODE, bool PACKED>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const T> out5,
                 const float* __restrict__ tv, View<T> out3, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
@@ -283,15 +283,30 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
     T* __restrict__ O = out3.p + ti.b * out3.sb + p;
     // channel strides fit 32 bits (checked on the host): one IMAD.WIDE per address
     const int xsc = (int)flows4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;
-    for (int n = 0; n < N; ++n, X += flows4.sn, Y += out5.sn, O += out3.sn) {
+    // The 9 streaming loads of timestep n+1 are issued before the gathers of timestep n, so that two
+    // dependent long-latency phases (HBM stream, then L2/L1 gather) overlap across iterations.
+    float xs[4], ys[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+    for (int n = 0; n < N; ++n, O += out3.sn) {
         const float tt = __ldg(tp + n);
         const float omt = __fsub_rn(1.0f, tt);
-        const float v1 = sigmoid_(lds_(Y));                                          // :386-388
+        const float logit = ys[0];
+        const float f1x = __fadd_rn(xs[0], ys[1]);                                   // :412
+        const float f1y = __fadd_rn(xs[1], ys[2]);
+        const float f0x = __fadd_rn(xs[2], ys[3]);                                   // :413
+        const float f0y = __fadd_rn(xs[3], ys[4]);
+        if (n + 1 < N) {
+            X += flows4.sn; Y += out5.sn;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+        }
+        const float v1 = sigmoid_(logit);                                            // :386-388
         const float v0 = 1.0f - v1;                                                  // :390
-        const float f1x = __fadd_rn(lds_(X), lds_(Y + ysc));                         // :412
-        const float f1y = __fadd_rn(lds_(X + xsc), lds_(Y + 2 * ysc));
-        const float f0x = __fadd_rn(lds_(X + 2 * xsc), lds_(Y + 3 * ysc));           // :413
-        const float f0y = __fadd_rn(lds_(X + 3 * xsc), lds_(Y + 4 * ysc));
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);                    // :416
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);                    // :418
         Quad q0[3], q1[3];

@@ -70,3 +70,72 @@ def compute_output_image(img_tensor, input_tensor, output_tensor, t):
     num = (1 - t) * p0 + t * p1                                     # :423
     den = (1 - t) * v0 + t * v1                                     # :425
     return num / den                                                # :427
+
+
+# ---- the reference's model loop (scripts/models/superslomo_r.py:90-106, 152-293) ----------------
+def get_image_pairs(img_tensor):
+    """superslomo_r.py:90-106: B x T x 3 x H x W -> B x (T-1) x 6 x H x W."""
+    frames = list(img_tensor.split(dim=1, split_size=1))
+    pairs = [torch.cat([a, b], dim=2)[:, 0] for a, b in zip(frames[:-1], frames[1:])]
+    return torch.stack(pairs, dim=1)
+
+
+def warp_loss_maps(img_pair, flow_c, in16, out5, target, stage1_frozen=False, stage2_frozen=False):
+    """losses.py:113-170 (L1 maps, before weighting)."""
+    i0, i1 = img_pair[:, 0:3], img_pair[:, 3:6]
+    total = 0
+    if not stage1_frozen:
+        total = total + (warp(i1, flow_c[:, 0:2]) - i0).abs() + (warp(i0, flow_c[:, 2:4]) - i1).abs()
+    if not stage2_frozen:
+        r1 = in16[:, 6:8] + out5[:, 1:3]
+        r0 = in16[:, 8:10] + out5[:, 3:5]
+        total = total + (warp(i0, r0) - target).abs() + (warp(i1, r1) - target).abs()
+    return total
+
+
+def losses(img_pair, flow_c, in16, out5, frame, target, lambda_r=60.0, lambda_p=20.0, lambda_w=10.0):
+    """losses.py:196-249 without the VGG term (weights unavailable offline): [B, 4]."""
+    mean = lambda x: x.reshape(x.shape[0], -1).mean(dim=1, keepdim=True)
+    rec = mean(lambda_r * (frame - target).abs())
+    wl = mean(lambda_w * warp_loss_maps(img_pair, flow_c, in16, out5, target))
+    per = torch.zeros_like(rec)
+    return torch.cat([rec + wl + per, rec, wl, per], dim=1)
+
+
+def model_forward(stage1, stage2, image_tensor, t_interp, target_images=None):
+    """superslomo_r.py:250-293 + 152-248, window by window as the reference does.  stage1/stage2 are
+    modules with the reference's interface.  Returns (middle frame, extras) or (middle frame,
+    losses [B, 4]) when targets are given."""
+    pairs = get_image_pairs(image_tensor)
+    T = pairs.shape[1]
+    mid = T // 2
+    c_out = stage1(pairs)
+    in16, encs = [], []
+    for w in range(T):
+        enc, flow = c_out[w]
+        in16.append(compute_inputs(pairs[:, w], flow, t_interp[:, w]))
+        encs.append(enc)
+    in16 = torch.stack(in16, dim=1)
+    i_out = stage2(in16, encs)
+    est, total = None, 0
+    for w in range(T):
+        frame = compute_output_image(pairs[:, w], in16[:, w], i_out[w], t_interp[:, w])
+        if target_images is not None:
+            total = total + losses(pairs[:, w], c_out[w][1], in16[:, w], i_out[w], frame, target_images[:, w])
+        if w == mid:
+            est = frame
+    if target_images is not None:
+        return est, total / T
+    x, y, flow = in16[:, mid], i_out[mid], c_out[mid][1]
+    v0 = 1 - torch.sigmoid(y[:, 0:1])
+    return est, (flow[:, 0:2], flow[:, 2:4], x[:, 6:8], x[:, 8:10], x[:, 6:8] + y[:, 1:3], x[:, 8:10] + y[:, 3:5], v0)
+
+
+def interpolate_frames(stage1, stage2, image_tensor, n_intermediate):
+    """evaluate_interpolation_results.py:213-244: the whole model once per intermediate time."""
+    B, T = image_tensor.shape[0], image_tensor.shape[1]
+    out = []
+    for idx in range(1, n_intermediate + 1):
+        t = torch.full((B, T - 1, 1, 1, 1), float(idx), device=image_tensor.device) / float(n_intermediate + 1)
+        out.append(model_forward(stage1, stage2, image_tensor, t)[0])
+    return torch.stack(out, dim=1)

@@ -1,15 +1,18 @@
 """ssm_b200 -- B200 (sm_100a) implementation of Super SloMo's per-pixel intermediate-frame
 synthesis path behind the reference's own call surface (scripts/models/layers.py,
-scripts/models/flow_interpolation.py:338-429).  CUDA only; the kernels live in libssm_b200.so
-(C ABI: include/ssm_b200.h)."""
+scripts/models/flow_interpolation.py:338-429, scripts/models/superslomo_r.py).  CUDA only; the
+kernels live in libssm_b200.so (C ABI: include/ssm_b200.h)."""
 from . import _abi
 from .functional import (flow_pack, fuse, get_coord_mode, pack_frames, set_coord_mode, synthesize_host,
                          synthesize_host_scratch_bytes)
 from .layers import avg_pool, conv, warp
 from .flow_interpolation import SynthesisMixin, patch_reference
+from . import losses, sharding, superslomo_r, synthetic, unets
+from .superslomo_r import FullModel
 
-__all__ = ["warp", "conv", "avg_pool", "flow_pack", "fuse", "pack_frames", "synthesize_host", "synthesize_host_scratch_bytes", "SynthesisMixin",
-           "patch_reference", "set_coord_mode", "get_coord_mode", "abi_version"]
+__all__ = ["warp", "conv", "avg_pool", "flow_pack", "fuse", "pack_frames", "synthesize_host",
+           "synthesize_host_scratch_bytes", "SynthesisMixin", "FullModel", "patch_reference",
+           "set_coord_mode", "get_coord_mode", "abi_version"]
 
 
 def abi_version():

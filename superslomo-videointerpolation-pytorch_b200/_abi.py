@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssm_b200.so")
+# SSM_B200_LIB points at an alternative build of the same library (kernel-variant experiments)
+LIB_PATH = os.environ.get("SSM_B200_LIB") or os.path.join(_HERE, "libssm_b200.so")
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 COORD_DIV, COORD_RCP = 0, 1

@@ -269,7 +269,13 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict_
 //     batched over N timesteps (the loop of superslomo_r.py:215-238)
 // =============================================================================================
 template <typename T, int MODE, bool PACKED>
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+#ifndef SSM_FUSE_MIN_BLOCKS
+#define SSM_FUSE_MIN_BLOCKS 4
+#endif
+#ifndef SSM_FUSE_PREFETCH
+#define SSM_FUSE_PREFETCH 1
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, SSM_FUSE_MIN_BLOCKS)
 fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const T> out5,
                 const float* __restrict__ tv, View<T> out3, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
@@ -286,19 +292,28 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
     // The 9 streaming loads of timestep n+1 are issued before the gathers of timestep n, so that two
     // dependent long-latency phases (HBM stream, then L2/L1 gather) overlap across iterations.
     float xs[4], ys[5];
+    if (SSM_FUSE_PREFETCH) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+        for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+        for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+    }
     for (int n = 0; n < N; ++n, O += out3.sn) {
         const float tt = __ldg(tp + n);
         const float omt = __fsub_rn(1.0f, tt);
+        if (!SSM_FUSE_PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+            X += flows4.sn; Y += out5.sn;
+        }
         const float logit = ys[0];
         const float f1x = __fadd_rn(xs[0], ys[1]);                                   // :412
         const float f1y = __fadd_rn(xs[1], ys[2]);
         const float f0x = __fadd_rn(xs[2], ys[3]);                                   // :413
         const float f0y = __fadd_rn(xs[3], ys[4]);
-        if (n + 1 < N) {
+        if (SSM_FUSE_PREFETCH && n + 1 < N) {
             X += flows4.sn; Y += out5.sn;
 #pragma unroll
             for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);

@@ -1,0 +1,61 @@
+"""Training losses around the synthesis path, with the reference's call surface
+(scripts/models/losses.py:43-249).
+
+Only the warp-loss front-end is part of the rebuilt path: its four `warp` calls
+(losses.py:152-161) run through the sm_100a kernel and back-propagate through it.  The L1
+reconstruction term is a plain torch expression.  The VGG16 perceptual term needs the pretrained
+torchvision weights the reference downloads (losses.py:23), which are unavailable offline and out of
+scope; a feature extractor can be injected, otherwise that term is zero.
+
+forward() returns the reference's [B, 4] tensor: (total, reconstruction, warp, perceptual), each the
+per-sample mean (kept per sample because the reference gathers it across DataParallel replicas).
+"""
+import torch
+import torch.nn as nn
+
+from .layers import warp
+
+
+def _sample_mean(x):
+    return x.reshape(x.shape[0], -1).mean(dim=1, keepdim=True)
+
+
+class SSMLosses(nn.Module):
+    def __init__(self, cfg=None, lambda_r=60.0, lambda_p=20.0, lambda_w=10.0, stage1_frozen=False,
+                 stage2_frozen=False, perceptual_features=None):
+        super().__init__()
+        if cfg is not None:
+            lambda_r = cfg.getfloat("TRAIN", "LAMBDA_R")      # losses.py:73-78
+            lambda_w = cfg.getfloat("TRAIN", "LAMBDA_W")
+            lambda_p = cfg.getfloat("TRAIN", "LAMBDA_P")
+            stage1_frozen = cfg.getboolean("STAGE1", "FREEZE")
+            stage2_frozen = cfg.getboolean("STAGE2", "FREEZE")
+        self.loss_weights = (lambda_r, lambda_p, lambda_w)
+        self.stage1_frozen, self.stage2_frozen = stage1_frozen, stage2_frozen
+        self.perceptual_features = perceptual_features     # e.g. torchvision vgg16.features[:23]
+
+    def get_warp_loss(self, img_tensor, flowC_output, flowI_input, flowI_output, target_image):
+        """losses.py:113-170: (total, stage-1 part, stage-2 part) as B x 3 x H x W L1 maps."""
+        img_0, img_1 = img_tensor[:, 0:3], img_tensor[:, 3:6]
+        zero = torch.zeros_like(target_image)
+        stage1 = stage2 = zero
+        if not self.stage1_frozen:
+            stage1 = (warp(img_1, flowC_output[:, 0:2]) - img_0).abs() + (warp(img_0, flowC_output[:, 2:4]) - img_1).abs()
+        if not self.stage2_frozen:
+            flow_t1 = flowI_input[:, 6:8] + flowI_output[:, 1:3]
+            flow_t0 = flowI_input[:, 8:10] + flowI_output[:, 3:5]
+            stage2 = (warp(img_0, flow_t0) - target_image).abs() + (warp(img_1, flow_t1) - target_image).abs()
+        return stage1 + stage2, stage1, stage2
+
+    def forward(self, flowC_input, flowC_output, flowI_input, flowI_output, interpolated_image, target_image):
+        lambda_r, lambda_p, lambda_w = self.loss_weights
+        rec = _sample_mean(lambda_r * (interpolated_image - target_image).abs())
+        if self.perceptual_features is not None and lambda_p != 0:
+            fa, fb = self.perceptual_features(interpolated_image), self.perceptual_features(target_image)
+            per = _sample_mean(lambda_p * (fa - fb) ** 2)
+        else:
+            per = torch.zeros_like(rec)
+        wl, _, _ = self.get_warp_loss(flowC_input, flowC_output, flowI_input, flowI_output, target_image)
+        wl = _sample_mean(lambda_w * wl)
+        total = rec + wl + per
+        return torch.cat([total, rec, wl, per], dim=1)     # [B, 4]

@@ -1,0 +1,133 @@
+"""Timestep-batched forward loop of the full model, with the reference's FullModel call surface
+(scripts/models/superslomo_r.py:33-293).
+
+What changes against the reference loop:
+  * windows (and, in `interpolate`, timesteps) are folded into the batch: compute_inputs runs once for
+    all of them (one launch instead of a Python loop + torch.stack, superslomo_r.py:167-179), and so
+    does compute_output_image (:215-238);
+  * in inference only the middle window goes through compute_output_image -- the reference computes
+    every window and keeps the middle one (:237-238);
+  * `interpolate` runs stage 1 ONCE per frame pair for all N intermediate times; the reference's eval
+    and visualise loops call the whole model, stage 1 included, once per timestep
+    (evaluate_interpolation_results.py:234-242, visualize_interpolation.py:139-144);
+  * the inference extras come out of the tensors already at hand instead of being recomputed
+    (get_intermediate_outputs, :108-150).
+The two U-Nets are ordinary torch modules (out of scope); any pair with the reference's interface
+can be passed in, e.g. the reference's own FlowComputationModel / FlowInterpolationModel.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F_ssm
+from . import unets
+from .flow_interpolation import SynthesisMixin
+from .losses import SSMLosses
+
+
+def _cfg_bool(cfg, section, key, default):
+    if cfg is not None and cfg.has_option(section, key):
+        return cfg.getboolean(section, key)
+    return default
+
+
+class FullModel(nn.Module, SynthesisMixin):
+    def __init__(self, cfg=None, writer=None, stage1_model=None, stage2_model=None, loss=None):
+        super().__init__()
+        self.cfg, self.writer = cfg, writer
+        self.cross_skip = _cfg_bool(cfg, "STAGE2", "CROSS_SKIP", True)
+        load_prev = _cfg_bool(cfg, "STAGE1", "LOADPREV", False)      # superslomo_r.py:46-52
+        w1 = cfg.get("STAGE1", "WEIGHTS") if (cfg is not None and load_prev) else None
+        w2 = cfg.get("STAGE2", "WEIGHTS") if (cfg is not None and load_prev) else None
+        self.stage1_model = stage1_model if stage1_model is not None else unets.get_model(
+            w1, 6, 4, self.cross_skip, stage=1, cfg=cfg)
+        self.stage2_model = stage2_model if stage2_model is not None else unets.get_model(
+            w2, 16, 5, self.cross_skip, stage=2, cfg=cfg)
+        self.freeze_weights()
+        self.loss = loss if loss is not None else SSMLosses(cfg)
+
+    def freeze_weights(self):
+        """superslomo_r.py:73-88"""
+        for section, model in (("STAGE1", self.stage1_model), ("STAGE2", self.stage2_model)):
+            if _cfg_bool(self.cfg, section, "FREEZE", False):
+                model.eval()
+                for p in model.parameters():
+                    p.requires_grad = False
+
+    @staticmethod
+    def get_image_pairs(img_tensor):
+        """B x T x 3 x H x W -> B x (T-1) x 6 x H x W, adjacent frames paired (superslomo_r.py:90-106)."""
+        return torch.cat([img_tensor[:, :-1], img_tensor[:, 1:]], dim=2)
+
+    # -----------------------------------------------------------------------------------------
+    def _stage1(self, image_pairs):
+        """-> flows B x W x 4 x H x W, encodings list (or None)."""
+        outs = self.stage1_model(image_pairs)
+        flows = torch.stack([o[1] for o in outs], dim=1)
+        encs = [o[0] for o in outs]
+        return flows, encs
+
+    def forward(self, image_tensor, t_interp, target_images=None, iteration=None, inference_mode=True):
+        """superslomo_r.py:250-293.  image_tensor B x T x 3 x H x W, t_interp B x (T-1) x 1 x 1 x 1.
+        Training: (est_img_t of the middle window, losses [B, 4]); inference: (est_img_t,
+        (flowC_01, flowC_10, est_flow_t1, est_flow_t0, refined_flow_t1, refined_flow_t0, v_0t))."""
+        if not inference_mode:
+            assert target_images is not None, "No target found for loss."
+            assert target_images.shape[1] == image_tensor.shape[1] - 1, "Insufficient number of targets."
+        pairs = self.get_image_pairs(image_tensor)                    # B x W x 6 x H x W
+        B, Wn = pairs.shape[0], pairs.shape[1]
+        mid = Wn // 2
+        flows, encs = self._stage1(pairs)
+        t_bw = t_interp.reshape(B, Wn)
+        flat = lambda x: x.reshape(B * Wn, *x.shape[2:])
+        # compute_inputs for every window in one launch (windows folded into the pair axis)
+        in16 = F_ssm.flow_pack(flat(pairs), flat(flows), t_bw.reshape(-1), n_timesteps=1)   # (B*W) x 1 x 16
+        in16 = in16.view(B, Wn, 16, *in16.shape[-2:])
+        out5 = torch.stack(self.stage2_model(in16, encs), dim=1)      # B x W x 5 x H x W
+        if inference_mode:
+            sel = slice(mid, mid + 1)
+            frame = F_ssm.fuse(pairs[:, mid], in16[:, sel], out5[:, sel], t_bw[:, mid])[:, 0]
+            x, y = in16[:, mid], out5[:, mid]
+            v_0t = 1 - torch.sigmoid(y[:, 0:1])
+            extras = (flows[:, mid, 0:2], flows[:, mid, 2:4], x[:, 6:8], x[:, 8:10],
+                      x[:, 6:8] + y[:, 1:3], x[:, 8:10] + y[:, 3:5], v_0t)
+            return frame, extras
+        frames = F_ssm.fuse(flat(pairs), flat(in16).unsqueeze(1), flat(out5).unsqueeze(1), t_bw.reshape(-1))
+        frames = frames.view(B, Wn, 3, *frames.shape[-2:])
+        losses = 0
+        for w in range(Wn):
+            losses = losses + self.loss(pairs[:, w], flows[:, w], in16[:, w], out5[:, w], frames[:, w],
+                                        target_images[:, w])
+        return frames[:, mid], losses / Wn
+
+    # -----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def interpolate(self, image_tensor, t_values, unet_chunk=None):
+        """All intermediate frames of every sample in one pass: image_tensor B x T x 3 x H x W,
+        t_values N times in (0,1) (e.g. k/8, k = 1..7) -> B x N x 3 x H x W (middle window).
+        Stage 1 runs once; compute_inputs / compute_output_image take all N times per launch;
+        stage 2 runs on the folded (B*N) batch, in chunks of `unet_chunk` timesteps if given."""
+        pairs = self.get_image_pairs(image_tensor)
+        B, Wn = pairs.shape[0], pairs.shape[1]
+        mid = Wn // 2
+        t_values = torch.as_tensor(t_values, dtype=torch.float32, device=image_tensor.device).reshape(-1)
+        N = t_values.numel()
+        flows, encs = self._stage1(pairs)
+        t_bn = t_values.view(1, N).expand(B, N).contiguous()
+        step = N if unet_chunk is None else max(1, int(unet_chunk))
+        rgbx = [F_ssm.pack_frames(pairs[:, w]) for w in range(Wn)]
+        frames = []
+        for n0 in range(0, N, step):
+            tn = t_bn[:, n0:n0 + step].contiguous()
+            n = tn.shape[1]
+            # B x W x n x 16: every window at every time of the chunk
+            in16 = torch.stack([F_ssm.flow_pack(pairs[:, w], flows[:, w], tn, n_timesteps=n, packed=rgbx[w])
+                                for w in range(Wn)], dim=1) if Wn > 1 else \
+                F_ssm.flow_pack(pairs[:, 0], flows[:, 0], tn, n_timesteps=n, packed=rgbx[0]).unsqueeze(1)
+            # stage 2 sees (B*n) samples of W windows each
+            x = in16.permute(0, 2, 1, 3, 4, 5).reshape(B * n, Wn, 16, *in16.shape[-2:])
+            e = None
+            if encs[0] is not None:
+                e = [enc.repeat_interleave(n, dim=0) for enc in encs]
+            out5 = self.stage2_model(x, e)[mid].view(B, n, 5, *in16.shape[-2:])
+            frames.append(F_ssm.fuse(pairs[:, mid], in16[:, mid], out5, tn, packed=rgbx[mid]))
+        return torch.cat(frames, dim=1)

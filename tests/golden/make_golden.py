@@ -122,3 +122,53 @@ if __name__ == "__main__":
         total += sz
         print("%-16s B=%d %4dx%-4d %-8s -> %.1f KB" % (name, B, H, W, kind, sz / 1024))
     print("torch_oracle == reference bit for bit on every case; total %.2f MB" % (total / 2 ** 20))
+
+
+# ---- the model loop (rows a6-a8): the reference's FullModel run on CPU ---------------------------
+def run_loop_case(name, n_frames, seed):
+    """Runs scripts/models/superslomo_r.py::FullModel (CONV bottleneck, random-init U-Nets from a
+    fixed seed, LAMBDA_P = 0 because the VGG weights cannot be downloaded) in inference and training
+    mode on CPU.  The reference hard-codes .cuda() (superslomo_r.py:211); Tensor.cuda is patched to
+    the identity for this run only.  U-Net weights are NOT stored (155 MB): tests rebuild them from
+    the same seed (same construction order, same state_dict keys)."""
+    import configparser
+    import torchvision
+    from models import superslomo_r as ref_model
+
+    cfg = configparser.RawConfigParser()
+    cfg.read("/root/reference/configs/superslomo_original.ini")
+    for sec in ("STAGE1", "STAGE2"):
+        cfg.set(sec, "LOADPREV", "FALSE")
+        cfg.set(sec, "FREEZE", "FALSE")
+    cfg.set("TRAIN", "LAMBDA_P", "0")
+    cfg.set("TRAIN", "N_FRAMES", str(n_frames))
+    real_vgg, real_cuda = torchvision.models.vgg16, torch.Tensor.cuda
+    torchvision.models.vgg16 = lambda pretrained=True: real_vgg(weights=None)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        torch.manual_seed(seed)
+        model = ref_model.FullModel(cfg)
+        B, H, W = 2, 64, 64
+        frames = synthetic.frames(B, H, W, n_frames=n_frames, seed=seed + 1).view(B, n_frames, 3, H, W)
+        targets = synthetic.frames(B, H, W, n_frames=n_frames - 1, seed=seed + 2).view(B, n_frames - 1, 3, H, W)
+        t = synthetic.random_timesteps(B, n_frames - 1, seed=seed + 3).view(B, n_frames - 1, 1, 1, 1)
+        with torch.no_grad():
+            est, extras = model(frames, t, inference_mode=True)
+        est_tr, losses = model(frames, t, target_images=targets, iteration=2, inference_mode=False)
+        losses.mean(dim=0)[0].backward()
+        g1 = model.stage1_model.final_conv.weight.grad.clone()
+        g2 = model.stage2_model.final_conv.weight.grad.clone()
+    finally:
+        torchvision.models.vgg16, torch.Tensor.cuda = real_vgg, real_cuda
+    rec = {"frames": frames, "targets": targets, "t": t.reshape(B, n_frames - 1), "est": est,
+           "losses": losses.detach(), "est_train": est_tr.detach(), "grad_stage1_final": g1, "grad_stage2_final": g2,
+           "seed": torch.tensor(seed)}
+    for i, e in enumerate(extras):
+        rec["extra%d" % i] = e
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.detach().numpy() for k, v in rec.items()})
+    print("%-16s N_FRAMES=%d -> %.1f KB" % (name, n_frames, os.path.getsize(os.path.join(HERE, name + ".npz")) / 1024))
+
+
+if __name__ == "__main__":
+    run_loop_case("loop_frames2", 2, seed=4242)
+    run_loop_case("loop_frames4", 4, seed=4343)

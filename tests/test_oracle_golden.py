@@ -87,3 +87,29 @@ def test_oracle_properties():
     sat = out5.clone()
     sat[:, 0] = 40.0
     assert torch.isfinite(c_oracle.compute_output_image(img6, in16, sat, t)).all()
+
+
+# ---- model loop (rows a6-a8) ---------------------------------------------------------------------
+from util import loop_cases, seeded_unets  # noqa: E402
+
+
+@pytest.mark.parametrize("name", loop_cases())
+def test_loop_oracle_matches_reference_fullmodel(name):
+    """oracle.torch_oracle.model_forward (window-by-window restatement of superslomo_r.py:250-293)
+    against the reference's own FullModel run on CPU (tests/golden/make_golden.py::run_loop_case).
+    Also pins that the in-tree U-Nets rebuild the reference's weights from the seed."""
+    d = load_golden(name)
+    s1, s2 = seeded_unets(d["seed"].item())
+    t = d["t"].view(*d["t"].shape, 1, 1, 1)
+    with torch.no_grad():
+        est, extras = torch_oracle.model_forward(s1, s2, d["frames"], t)
+    assert_close_fp32(est, d["est"], "inference frame", tol=1e-6)
+    for i, e in enumerate(extras):
+        assert_close_fp32(e, d["extra%d" % i], "inference extra %d" % i, tol=1e-6)
+    est_tr, losses = torch_oracle.model_forward(s1, s2, d["frames"], t, target_images=d["targets"],
+                                                )
+    assert_close_fp32(est_tr, d["est_train"], "training frame", tol=1e-6)
+    assert_close_fp32(losses, d["losses"], "losses [B,4]", tol=2e-5)
+    losses.mean(dim=0)[0].backward()
+    assert_close_fp32(s1.final_conv.weight.grad, d["grad_stage1_final"], "stage-1 final_conv grad", tol=1e-5)
+    assert_close_fp32(s2.final_conv.weight.grad, d["grad_stage2_final"], "stage-2 final_conv grad", tol=1e-5)

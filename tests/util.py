@@ -16,7 +16,25 @@ BF16_RTOL = 2.0 ** -7
 
 
 def golden_cases():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """hot-path fixtures (warp / compute_inputs / compute_output_image)"""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("loop_"))
+
+
+def loop_cases():
+    """model-loop fixtures (the reference's FullModel, rows a6-a8)"""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if n.startswith("loop_"))
+
+
+def seeded_unets(seed, device="cpu"):
+    """The two U-Nets with the weights the golden generator's reference FullModel had: same seed,
+    same construction order (stage 1 then stage 2), same state_dict keys."""
+    from ssm_b200 import unets
+    torch.manual_seed(int(seed))
+    s1 = unets.FlowUNet(6, 4, 1, cross_skip=True)
+    s2 = unets.FlowUNet(16, 5, 2, cross_skip=True)
+    return s1.to(device), s2.to(device)
 
 
 def load_golden(name):

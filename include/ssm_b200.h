@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 2
+#define SSM_ABI_VERSION 3
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -137,6 +137,23 @@ int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* pa
                  const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
                  int B, int N, int H, int W, int dtype, int coord_mode,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2 -> a4 shortcut for callers that hold flow_pred_tensor (the timestep-batched loop) -------
+ * Same results as ssm_fuse_fwd / ssm_fuse_bwd given input_tensor = compute_inputs(img, flow4, t):
+ * the estimated flows input_tensor[:, 6:10] (flow_interpolation.py:353,356,402-413) are recomputed
+ * in-kernel from flow4 (B x 4 x H x W) and t with the arithmetic of ssm_flow_pack_fwd instead of
+ * being read back, which removes 4 of the 12 streamed channels per timestep.  In the backward the
+ * gradient goes straight to grad_flow4 (B x 4 x H x W, summed over the N timesteps in registers
+ * through the coefficients of :353,356): the B x N x 16 gradient of input_tensor that autograd
+ * builds for the reference (12 zero channels + 4) never exists. */
+int ssm_fuse_flow_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const ssm_tensor* out5,
+                      const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                      int dtype, int coord_mode, void* stream);
+int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                      const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
+                      int B, int N, int H, int W, int dtype, int coord_mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
  * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */

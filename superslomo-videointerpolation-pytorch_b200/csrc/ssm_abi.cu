@@ -222,9 +222,12 @@ struct PackBwd {
 
 struct FuseFwd {
     const ssm_tensor* img6; const void* packed; const ssm_tensor *flows4, *out5; const float* t;
-    const ssm_tensor* out3; int B, N, H, W; cudaStream_t s;
+    const ssm_tensor* out3; int B, N, H, W; cudaStream_t s; bool recomp;
     template <typename T, int MODE, bool PACKED> int run() {
-        fuse_fwd_kernel<T, MODE, PACKED><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+        return recomp ? go<T, MODE, PACKED, true>() : go<T, MODE, PACKED, false>();
+    }
+    template <typename T, int MODE, bool PACKED, bool RECOMP> int go() {
+        fuse_fwd_kernel<T, MODE, PACKED, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
             cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(out3), N, make_geom(H, W));
         SSM_LAUNCH_CHECK("ssm_fuse_fwd");
         return SSM_OK;
@@ -233,13 +236,16 @@ struct FuseFwd {
 
 struct FuseBwd {
     const ssm_tensor *g3, *img6; const void* packed; const ssm_tensor *flows4, *out5; const float* t;
-    const ssm_tensor *gout5, *gflows4, *gimg6; int B, N, H, W; void* ws; cudaStream_t s;
+    const ssm_tensor *gout5, *gflows4, *gimg6; int B, N, H, W; void* ws; cudaStream_t s; bool recomp;
     template <typename T, int MODE, bool PACKED> int run() {
+        return recomp ? go<T, MODE, PACKED, true>() : go<T, MODE, PACKED, false>();
+    }
+    template <typename T, int MODE, bool PACKED, bool RECOMP> int go() {
         const Geom g = make_geom(H, W);
         const bool want_img = gimg6 && gimg6->data;
         const long long npx = (long long)H * W;
         if (!want_img) {
-            fuse_bwd_kernel<T, MODE, PACKED, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            fuse_bwd_kernel<T, MODE, PACKED, false, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
                 cview<T>(g3), cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
                 mview<T>(gflows4), nullptr, nullptr, N, g);
             SSM_LAUNCH_CHECK("ssm_fuse_bwd");
@@ -250,13 +256,13 @@ struct FuseBwd {
         float* stage = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
         cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
         if (e != cudaSuccess) return cuda_fail(e, "ssm_fuse_bwd memset");
-        fuse_bwd_kernel<T, MODE, PACKED, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+        fuse_bwd_kernel<T, MODE, PACKED, true, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
             cview<T>(g3), cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
             mview<T>(gflows4), stage, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd");
         const int cb = count_bits_for((long long)N * npx);
-        fuse_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            stage, cview<T>(flows4), cview<T>(out5), acc, N, g, hdr, cb);
+        fuse_scatter_kernel<T, MODE, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            stage, cview<T>(flows4), cview<T>(out5), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd (scatter)");
         const long long total = (long long)B * 6 * npx;
         scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg6), 6, npx, total, hdr, cb);
@@ -395,32 +401,33 @@ int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const vo
                      PackBwd{grad16, img6, packed, flow4, t, grad_flow4, grad_img6, B, N, H, W, workspace, (cudaStream_t)stream});
 }
 
-int ssm_fuse_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flows4, const ssm_tensor* out5,
-                 const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
-                 int dtype, int coord_mode, void* stream) {
+static int fuse_fwd_impl(const ssm_tensor* img6, const void* packed, const ssm_tensor* flows4, const ssm_tensor* out5,
+                         const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                         int dtype, int coord_mode, void* stream, bool recomp) {
     SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
-    SSM_TRY(check_tensor(flows4, "flows4", dtype, true));
+    SSM_TRY(check_tensor(flows4, recomp ? "flow4" : "flows4", dtype, true));
     SSM_TRY(check_tensor(out5, "out5", dtype, true));
     SSM_TRY(check_tensor(out3, "out3", dtype, true));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
-    return dispatch3(dtype, coord_mode, packed != nullptr, FuseFwd{img6, packed, flows4, out5, t, out3, B, N, H, W, (cudaStream_t)stream});
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     FuseFwd{img6, packed, flows4, out5, t, out3, B, N, H, W, (cudaStream_t)stream, recomp});
 }
 
-int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
-                 const ssm_tensor* flows4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
-                 const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
-                 int B, int N, int H, int W, int dtype, int coord_mode,
-                 void* workspace, size_t workspace_bytes, void* stream) {
+static int fuse_bwd_impl(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                         const ssm_tensor* flows4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                         const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
+                         int B, int N, int H, int W, int dtype, int coord_mode,
+                         void* workspace, size_t workspace_bytes, void* stream, bool recomp) {
     SSM_TRY(check_packed(packed));
     SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
     SSM_TRY(check_tensor(grad3, "grad3", dtype, true));
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
-    SSM_TRY(check_tensor(flows4, "flows4", dtype, true));
+    SSM_TRY(check_tensor(flows4, recomp ? "flow4" : "flows4", dtype, true));
     SSM_TRY(check_tensor(out5, "out5", dtype, true));
     SSM_TRY(check_tensor(grad_out5, "grad_out5", dtype, false));
-    SSM_TRY(check_tensor(grad_flows4, "grad_flows4", dtype, false));
+    SSM_TRY(check_tensor(grad_flows4, recomp ? "grad_flow4" : "grad_flows4", dtype, false));
     SSM_TRY(check_tensor(grad_img6, "grad_img6", dtype, false));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
     if (grad_img6 && grad_img6->data) {
@@ -431,7 +438,37 @@ int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* pa
     }
     return dispatch3(dtype, coord_mode, packed != nullptr,
                      FuseBwd{grad3, img6, packed, flows4, out5, t, grad_out5, grad_flows4, grad_img6, B, N, H, W,
-                             workspace, (cudaStream_t)stream});
+                             workspace, (cudaStream_t)stream, recomp});
+}
+
+int ssm_fuse_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flows4, const ssm_tensor* out5,
+                 const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                 int dtype, int coord_mode, void* stream) {
+    return fuse_fwd_impl(img6, packed, flows4, out5, t, out3, B, N, H, W, dtype, coord_mode, stream, false);
+}
+
+int ssm_fuse_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                 const ssm_tensor* flows4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                 const ssm_tensor* grad_flows4, const ssm_tensor* grad_img6,
+                 int B, int N, int H, int W, int dtype, int coord_mode,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    return fuse_bwd_impl(grad3, img6, packed, flows4, out5, t, grad_out5, grad_flows4, grad_img6, B, N, H, W, dtype,
+                         coord_mode, workspace, workspace_bytes, stream, false);
+}
+
+int ssm_fuse_flow_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const ssm_tensor* out5,
+                      const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
+                      int dtype, int coord_mode, void* stream) {
+    return fuse_fwd_impl(img6, packed, flow4, out5, t, out3, B, N, H, W, dtype, coord_mode, stream, true);
+}
+
+int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const ssm_tensor* out5, const float* t, const ssm_tensor* grad_out5,
+                      const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
+                      int B, int N, int H, int W, int dtype, int coord_mode,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    return fuse_bwd_impl(grad3, img6, packed, flow4, out5, t, grad_out5, grad_flow4, grad_img6, B, N, H, W, dtype,
+                         coord_mode, workspace, workspace_bytes, stream, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,12 +527,11 @@ int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const f
         ssm_tensor T_flow{d_flow, (int64_t)(4 * npx), 0, (int64_t)npx};
         ssm_tensor T_out5{d_out5, (int64_t)(5 * N * npx), (int64_t)(5 * npx), (int64_t)npx};
         ssm_tensor T_in16{d_in16, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
-        ssm_tensor T_fl4{d_in16 + 6 * npx, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
         ssm_tensor T_out3{d_out3, (int64_t)(3 * N * npx), (int64_t)(3 * npx), (int64_t)npx};
         const void* rgbx = N >= 2 ? d_rgbx : nullptr;
         if (rgbx) rc = ssm_pack_frames(&T_img, d_rgbx, 1, H, W, SSM_DTYPE_F32, s);
         if (rc == SSM_OK) rc = ssm_flow_pack_fwd(&T_img, rgbx, &T_flow, d_t, &T_in16, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
-        if (rc == SSM_OK) rc = ssm_fuse_fwd(&T_img, rgbx, &T_fl4, &T_out5, d_t, &T_out3, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
+        if (rc == SSM_OK) rc = ssm_fuse_flow_fwd(&T_img, rgbx, &T_flow, &T_out5, d_t, &T_out3, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
         SSM_H(cudaMemcpyAsync(out3_host + (size_t)b * N * 3 * npx, d_out3, (size_t)N * 3 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (in16_host)
             SSM_H(cudaMemcpyAsync(in16_host + (size_t)b * N * 16 * npx, d_in16, (size_t)N * 16 * npx * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -181,15 +181,17 @@ __device__ __forceinline__ void gather3(const T* __restrict__ frame, long long s
     }
 }
 
-// accumulate d(bilerp)/d(ix), d(bilerp)/d(iy) times upstream gradient g
+// accumulate d(bilerp)/d(ix), d(bilerp)/d(iy) times upstream gradient g.  ATen sums the eight
+// tap terms -nw*(ys-iy)*g + ne*(ys-iy)*g - ... one by one; grouping them by row / column is the
+// same sum up to rounding (masked taps have value 0 either way) and takes a third of the
+// instructions: d/dix = (ne-nw)*(ys-iy) + (se-sw)*(iy-fy), d/diy = (sw-nw)*(xe-ix) + (se-ne)*(ix-fx).
 __device__ __forceinline__ void bilerp_grad(const Quad& v, const Taps& t, float g, float& gix, float& giy) {
-    float xe = t.fx + 1.0f, ys = t.fy + 1.0f;
-    float dyn = ys - t.iy, dys = t.iy - t.fy;   // weights of the north / south rows
-    float dxw = xe - t.ix, dxe = t.ix - t.fx;   // weights of the west / east columns
-    gix -= v.nw * dyn * g; giy -= v.nw * dxw * g;
-    gix += v.ne * dyn * g; giy -= v.ne * dxe * g;
-    gix -= v.sw * dys * g; giy += v.sw * dxw * g;
-    gix += v.se * dys * g; giy += v.se * dxe * g;
+    const float dys = t.iy - t.fy, dyn = (t.fy + 1.0f) - t.iy;   // weights of the south / north rows
+    const float dxe = t.ix - t.fx, dxw = (t.fx + 1.0f) - t.ix;   // weights of the east / west columns
+    const float dx = fmaf(v.ne - v.nw, dyn, (v.se - v.sw) * dys);
+    const float dy = fmaf(v.sw - v.nw, dxw, (v.se - v.ne) * dxe);
+    gix = fmaf(dx, g, gix);
+    giy = fmaf(dy, g, giy);
 }
 
 // flow_interpolation.py:353,356 coefficients, evaluated as torch does on the B x 1 x 1 x 1 tensor

@@ -191,8 +191,13 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
 // registers (deterministic).  With IMG_GRAD the direct image gradients (channels 0:3 and 13:16 of
 // grad16, summed over timesteps) go to an fp32 staging buffer and max |grad16[:, 3:6|10:13]| is
 // recorded; the warped-image part is added by the scatter pass (ssm_scatter.cuh).
+// The streaming loads of timestep n+1 are issued before the gathers of timestep n (two dependent
+// long-latency phases overlap across iterations, as in fuse_fwd_kernel).
+#ifndef SSM_PACK_BWD_MIN_BLOCKS
+#define SSM_PACK_BWD_MIN_BLOCKS 4
+#endif
 template <typename T, int MODE, bool PACKED, bool IMG_GRAD>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, IMG_GRAD ? 3 : SSM_PACK_BWD_MIN_BLOCKS)
 flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict__ packed, View<const T> flow4,
                      const float* __restrict__ tv, View<T> gflow4, float* __restrict__ gimg_direct,
                      ScatterHdr* hdr, int N, Geom g) {
@@ -209,38 +214,62 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict_
         float d01x = 0, d01y = 0, d10x = 0, d10y = 0;
         float di0[3] = {0, 0, 0}, di1[3] = {0, 0, 0};
         const float* tp = tv + ti.b * N;
-        const T* G = g16.p + ti.b * g16.sb + p;
-        for (int n = 0; n < N; ++n, G += g16.sn) {
-            const Coef k = make_coef(__ldg(tp + n));
-            float gw1[3], gw0[3];
+        const T* __restrict__ G = g16.p + ti.b * g16.sb + p;
+        const int gsc = (int)g16.sc;   // fits 32 bits (checked on the host)
+        // gs[0:3] = d/d(warped I1) (ch 3:6), gs[3:7] = direct flow terms (ch 6:10), gs[7:10] = d/d(warped I0)
+        float gs[10], gd[6];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                gw1[c] = lds_(G + (3 + c) * g16.sc);
-                gw0[c] = lds_(G + (10 + c) * g16.sc);
-                if (IMG_GRAD) {
+        for (int k = 0; k < 10; ++k) gs[k] = lds_(G + (3 + k) * gsc);
+        if (IMG_GRAD) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { gd[c] = lds_(G + c * gsc); gd[3 + c] = lds_(G + (13 + c) * gsc); }
+        }
+        for (int n = 0; n < N; ++n) {
+            const Coef k = make_coef(__ldg(tp + n));
+            float gw1[3], gw0[3], gdir[4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { gw1[c] = gs[c]; gw0[c] = gs[7 + c]; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gdir[c] = gs[3 + c];
+            if (IMG_GRAD) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
                     amax = fmaxf(amax, fmaxf(fabsf(gw1[c]), fabsf(gw0[c])));
-                    di1[c] += lds_(G + (0 + c) * g16.sc);
-                    di0[c] += lds_(G + (13 + c) * g16.sc);
+                    di1[c] += gd[c];
+                    di0[c] += gd[3 + c];
+                }
+            }
+            if (n + 1 < N) {
+                G += g16.sn;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) gs[c] = lds_(G + (3 + c) * gsc);
+                if (IMG_GRAD) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { gd[c] = lds_(G + c * gsc); gd[3 + c] = lds_(G + (13 + c) * gsc); }
                 }
             }
             if (!want_flow) continue;
             const float e0x = est_t0(k, f01x, f10x), e0y = est_t0(k, f01y, f10y);
             const float e1x = est_t1(k, f01x, f10x), e1y = est_t1(k, f01y, f10y);
-            const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);
-            const Taps t0 = make_taps<MODE>(ti.x, ti.y, e0x, e0y, g);
-            Quad q1[3], q0[3];
-            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
-            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
             float g1x = 0, g1y = 0, g0x = 0, g0y = 0;
+            {
+                const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);
+                Quad q1[3];
+                gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                bilerp_grad(q1[c], t1, gw1[c], g1x, g1y);
-                bilerp_grad(q0[c], t0, gw0[c], g0x, g0y);
+                for (int c = 0; c < 3; ++c) bilerp_grad(q1[c], t1, gw1[c], g1x, g1y);
             }
-            const float de1x = lds_(G + 6 * g16.sc) + coord_grad_to_flow<MODE>(g1x, g.xgrad, g.xnorm, g.xinv);
-            const float de1y = lds_(G + 7 * g16.sc) + coord_grad_to_flow<MODE>(g1y, g.ygrad, g.ynorm, g.yinv);
-            const float de0x = lds_(G + 8 * g16.sc) + coord_grad_to_flow<MODE>(g0x, g.xgrad, g.xnorm, g.xinv);
-            const float de0y = lds_(G + 9 * g16.sc) + coord_grad_to_flow<MODE>(g0y, g.ygrad, g.ynorm, g.yinv);
+            {
+                const Taps t0 = make_taps<MODE>(ti.x, ti.y, e0x, e0y, g);
+                Quad q0[3];
+                gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) bilerp_grad(q0[c], t0, gw0[c], g0x, g0y);
+            }
+            const float de1x = gdir[0] + coord_grad_to_flow<MODE>(g1x, g.xgrad, g.xnorm, g.xinv);
+            const float de1y = gdir[1] + coord_grad_to_flow<MODE>(g1y, g.ygrad, g.ynorm, g.yinv);
+            const float de0x = gdir[2] + coord_grad_to_flow<MODE>(g0x, g.xgrad, g.xnorm, g.xinv);
+            const float de0y = gdir[3] + coord_grad_to_flow<MODE>(g0y, g.ygrad, g.ynorm, g.yinv);
             d01x += k.c00 * de0x + k.c10 * de1x;
             d01y += k.c00 * de0y + k.c10 * de1y;
             d10x += k.c01 * de0x - k.c11 * de1x;
@@ -267,14 +296,24 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict_
 // =============================================================================================
 // a3 + a4: extract_outputs + compute_output_image   flow_interpolation.py:374-429
 //     batched over N timesteps (the loop of superslomo_r.py:215-238)
+//     RECOMP: the estimated flows F_t1, F_t0 (input_tensor[:, 6:10]) are not read back but recomputed
+//     from the stage-1 flows and t with the arithmetic of flow_pack_fwd_kernel (bit-identical to the
+//     stored values): `flows4` is then flow_pred_tensor (B x 4 x H x W) and 4 of the 12 streamed
+//     channels per timestep disappear.
 // =============================================================================================
-template <typename T, int MODE, bool PACKED>
 #ifndef SSM_FUSE_MIN_BLOCKS
 #define SSM_FUSE_MIN_BLOCKS 4
 #endif
-#ifndef SSM_FUSE_PREFETCH
-#define SSM_FUSE_PREFETCH 1
-#endif
+// the estimated flows of one timestep in input_tensor order (F_t1.x, F_t1.y, F_t0.x, F_t0.y), rounded
+// to the storage type exactly as flow_pack_fwd_kernel stores them
+template <typename T>
+__device__ __forceinline__ void est_flows(float tt, const float (&f)[4], float (&xs)[4]) {
+    const Coef k = make_coef(tt);
+    xs[0] = storage_round<T>(est_t1(k, f[0], f[2])); xs[1] = storage_round<T>(est_t1(k, f[1], f[3]));
+    xs[2] = storage_round<T>(est_t0(k, f[0], f[2])); xs[3] = storage_round<T>(est_t0(k, f[1], f[3]));
+}
+
+template <typename T, int MODE, bool PACKED, bool RECOMP>
 __global__ void __launch_bounds__(TILE_THREADS, SSM_FUSE_MIN_BLOCKS)
 fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const T> out5,
                 const float* __restrict__ tv, View<T> out3, int N, Geom g) {
@@ -289,36 +328,31 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
     T* __restrict__ O = out3.p + ti.b * out3.sb + p;
     // channel strides fit 32 bits (checked on the host): one IMAD.WIDE per address
     const int xsc = (int)flows4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;
-    // The 9 streaming loads of timestep n+1 are issued before the gathers of timestep n, so that two
+    // The streaming loads of timestep n+1 are issued before the gathers of timestep n, so that two
     // dependent long-latency phases (HBM stream, then L2/L1 gather) overlap across iterations.
-    float xs[4], ys[5];
-    if (SSM_FUSE_PREFETCH) {
+    float xs[4], ys[5], f[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+    for (int k = 0; k < 4; ++k) (RECOMP ? f[k] : xs[k]) = lds_(X + k * xsc);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
-    }
+    for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
     for (int n = 0; n < N; ++n, O += out3.sn) {
         const float tt = __ldg(tp + n);
         const float omt = __fsub_rn(1.0f, tt);
-        if (!SSM_FUSE_PREFETCH) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
-            X += flows4.sn; Y += out5.sn;
-        }
+        if (RECOMP) est_flows<T>(tt, f, xs);
         const float logit = ys[0];
         const float f1x = __fadd_rn(xs[0], ys[1]);                                   // :412
         const float f1y = __fadd_rn(xs[1], ys[2]);
         const float f0x = __fadd_rn(xs[2], ys[3]);                                   // :413
         const float f0y = __fadd_rn(xs[3], ys[4]);
-        if (SSM_FUSE_PREFETCH && n + 1 < N) {
-            X += flows4.sn; Y += out5.sn;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+        if (n + 1 < N) {
+            Y += out5.sn;
 #pragma unroll
             for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+            if (!RECOMP) {
+                X += flows4.sn;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
+            }
         }
         const float v1 = sigmoid_(logit);                                            // :386-388
         const float v0 = 1.0f - v1;                                                  // :390
@@ -342,8 +376,36 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
 // (input_tensor[:, 6:10]).  With STAGE, d/d(warped I0), d/d(warped I1) are written to an fp32
 // staging buffer (B x N x 6 x H x W) and their max magnitude is recorded for the deterministic
 // image-gradient pass (ssm_scatter.cuh).
-template <typename T, int MODE, bool PACKED, bool STAGE>
-__global__ void __launch_bounds__(TILE_THREADS)
+//
+// With G = d/d(out3), S = (1-t) V0 w0 + t V1 w1, Z = (1-t) V0 + t V1 (SURVEY.md section 8 note):
+//   d/d(w_f,c) = k_f V_f G_c,  k_0 = (1-t)/Z, k_1 = t/Z
+//   A_f = sum_c G_c w_f,c ;  dZ = -(k_0 V0 A_0 + k_1 V1 A_1) / Z ;  dV_0 = k_0 A_0 + (1-t) dZ ; dV_1 alike
+// so each frame contributes three scalars (A_f and the two coordinate gradients) and the frames are
+// processed one after the other: 12 gathered values live at a time instead of 24.
+#ifndef SSM_FUSE_BWD_MIN_BLOCKS
+#define SSM_FUSE_BWD_MIN_BLOCKS 4
+#endif
+template <typename T, bool PACKED, bool STAGE>
+__device__ __forceinline__ void fuse_bwd_frame(const T* __restrict__ frame, long long sc, const Taps& t, int W,
+                                               const float (&gc)[3], float kv, float& A, float& gx, float& gy,
+                                               float* __restrict__ st, long long npx, float& amax) {
+    Quad q[3];
+    gather3<T, PACKED>(frame, sc, t, W, q);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        A = fmaf(gc[c], bilerp(q[c], t), A);
+        const float ds = kv * gc[c];                   // d/d(warped frame)
+        bilerp_grad(q[c], t, ds, gx, gy);
+        if (STAGE) { st[c * npx] = ds; amax = fmaxf(amax, fabsf(ds)); }
+    }
+}
+
+// RECOMP (see fuse_fwd_kernel): `flows4` is flow_pred_tensor (B x 4 x H x W) and `gflows4` its
+// gradient (B x 4 x H x W), accumulated over the N timesteps in registers through the coefficients
+// of flow_interpolation.py:353,356 -- no B x N x 4 gradient (nor the 12 zero channels around it in
+// the gradient of input_tensor) is ever materialised.
+template <typename T, int MODE, bool PACKED, bool STAGE, bool RECOMP>
+__global__ void __launch_bounds__(TILE_THREADS, STAGE ? 2 : SSM_FUSE_BWD_MIN_BLOCKS)
 fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ packed, View<const T> flows4,
                 View<const T> out5, const float* __restrict__ tv, View<T> gout5, View<T> gflows4,
                 float* __restrict__ stage, ScatterHdr* hdr, int N, Geom g) {
@@ -354,60 +416,86 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ pack
         const long long npx = (long long)g.H * g.W;
         const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
         const float* tp = tv + ti.b * N;
+        const T* __restrict__ X = flows4.p + ti.b * flows4.sb + p;
+        const T* __restrict__ Y = out5.p + ti.b * out5.sb + p;
+        const T* __restrict__ G = g3.p + ti.b * g3.sb + p;
+        T* __restrict__ O5 = gout5.p ? gout5.p + ti.b * gout5.sb + p : nullptr;
+        T* __restrict__ O4 = gflows4.p ? gflows4.p + ti.b * gflows4.sb + p : nullptr;
+        // channel strides fit 32 bits (checked on the host)
+        const int xsc = (int)flows4.sc, ysc = (int)out5.sc, gsc = (int)g3.sc;
+        const int o5sc = (int)gout5.sc, o4sc = (int)gflows4.sc;
+        float xs[4], ys[5], gs[3], f[4];
+        float d01x = 0, d01y = 0, d10x = 0, d10y = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) (RECOMP ? f[k] : xs[k]) = lds_(X + k * xsc);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gs[k] = lds_(G + k * gsc);
         for (int n = 0; n < N; ++n) {
             const float tt = __ldg(tp + n);
             const float omt = __fsub_rn(1.0f, tt);
-            const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
-            const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
-            const T* G = g3.p + ti.b * g3.sb + n * g3.sn + p;
-            const float v1 = sigmoid_(lds_(Y));
-            const float v0 = 1.0f - v1;
-            const float f1x = __fadd_rn(lds_(X), lds_(Y + out5.sc));
-            const float f1y = __fadd_rn(lds_(X + flows4.sc), lds_(Y + 2 * out5.sc));
-            const float f0x = __fadd_rn(lds_(X + 2 * flows4.sc), lds_(Y + 3 * out5.sc));
-            const float f0y = __fadd_rn(lds_(X + 3 * flows4.sc), lds_(Y + 4 * out5.sc));
-            const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
-            const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
-            Quad q0[3], q1[3];
-            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
-            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
-            const float z = omt * v0 + tt * v1;
-            const float rz = __frcp_rn(z);
-            float dz = 0, dv0 = 0, dv1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
-            float* st = STAGE ? stage + ((long long)(ti.b * N + n) * 6) * npx + p : nullptr;
+            if (RECOMP) est_flows<T>(tt, f, xs);
+            const float logit = ys[0];
+            const float f1x = __fadd_rn(xs[0], ys[1]);
+            const float f1y = __fadd_rn(xs[1], ys[2]);
+            const float f0x = __fadd_rn(xs[2], ys[3]);
+            const float f0y = __fadd_rn(xs[3], ys[4]);
+            const float gc[3] = {gs[0], gs[1], gs[2]};
+            if (n + 1 < N) {     // streaming loads of the next timestep, in flight during the gathers
+                Y += out5.sn; G += g3.sn;
+                if (!RECOMP) {
+                    X += flows4.sn;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float s0 = bilerp(q0[c], t0), s1 = bilerp(q1[c], t1);
-                const float o = (omt * (v0 * s0) + tt * (v1 * s1)) * rz;
-                const float gc = lds_(G + c * g3.sc);
-                const float ds = gc * rz;          // d/d(weighted_sum)
-                dz -= gc * o * rz;                 // d/d(normalization_factor)
-                const float dw0 = omt * ds, dw1 = tt * ds;
-                dv0 += dw0 * s0; dv1 += dw1 * s1;
-                const float ds0 = dw0 * v0, ds1 = dw1 * v1;   // d/d(warped frames)
-                bilerp_grad(q0[c], t0, ds0, g0x, g0y);
-                bilerp_grad(q1[c], t1, ds1, g1x, g1y);
-                if (STAGE) {
-                    st[c * npx] = ds0; st[(3 + c) * npx] = ds1;
-                    amax = fmaxf(amax, fmaxf(fabsf(ds0), fabsf(ds1)));
+                    for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * xsc);
                 }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) ys[k] = lds_(Y + k * ysc);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) gs[k] = lds_(G + k * gsc);
             }
-            dv0 += omt * dz; dv1 += tt * dz;
+            const float v1 = sigmoid_(logit);
+            const float v0 = 1.0f - v1;
+            const float rz = __frcp_rn(omt * v0 + tt * v1);
+            const float k0 = omt * rz, k1 = tt * rz;
+            float A0 = 0, A1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
+            float* st = STAGE ? stage + ((long long)(ti.b * N + n) * 6) * npx + p : nullptr;
+            {
+                const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
+                fuse_bwd_frame<T, PACKED, STAGE>(fr.f0, fr.sc, t0, g.W, gc, k0 * v0, A0, g0x, g0y, st, npx, amax);
+            }
+            {
+                const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
+                fuse_bwd_frame<T, PACKED, STAGE>(fr.f1, fr.sc, t1, g.W, gc, k1 * v1, A1, g1x, g1y,
+                                                 STAGE ? st + 3 * npx : nullptr, npx, amax);
+            }
+            const float dz = -rz * (k0 * v0 * A0 + k1 * v1 * A1);      // d/d(normalization_factor)
+            const float dv0 = k0 * A0 + omt * dz, dv1 = k1 * A1 + tt * dz;
             const float df1x = coord_grad_to_flow<MODE>(g1x, g.xgrad, g.xnorm, g.xinv);
             const float df1y = coord_grad_to_flow<MODE>(g1y, g.ygrad, g.ynorm, g.yinv);
             const float df0x = coord_grad_to_flow<MODE>(g0x, g.xgrad, g.xnorm, g.xinv);
             const float df0y = coord_grad_to_flow<MODE>(g0y, g.ygrad, g.ynorm, g.yinv);
-            if (gout5.p) {
-                T* o = gout5.p + ti.b * gout5.sb + n * gout5.sn + p;
-                sts_(o, (dv1 - dv0) * (v1 * (1.0f - v1)));
-                sts_(o + gout5.sc, df1x); sts_(o + 2 * gout5.sc, df1y);
-                sts_(o + 3 * gout5.sc, df0x); sts_(o + 4 * gout5.sc, df0y);
+            if (O5) {
+                sts_(O5, (dv1 - dv0) * (v1 * (1.0f - v1)));
+                sts_(O5 + o5sc, df1x); sts_(O5 + 2 * o5sc, df1y);
+                sts_(O5 + 3 * o5sc, df0x); sts_(O5 + 4 * o5sc, df0y);
+                O5 += gout5.sn;
             }
-            if (gflows4.p) {
-                T* o = gflows4.p + ti.b * gflows4.sb + n * gflows4.sn + p;
-                sts_(o, df1x); sts_(o + gflows4.sc, df1y);
-                sts_(o + 2 * gflows4.sc, df0x); sts_(o + 3 * gflows4.sc, df0y);
+            if (RECOMP) {
+                const Coef k = make_coef(tt);
+                d01x += k.c00 * df0x + k.c10 * df1x;
+                d01y += k.c00 * df0y + k.c10 * df1y;
+                d10x += k.c01 * df0x - k.c11 * df1x;
+                d10y += k.c01 * df0y - k.c11 * df1y;
+            } else if (O4) {
+                sts_(O4, df1x); sts_(O4 + o4sc, df1y);
+                sts_(O4 + 2 * o4sc, df0x); sts_(O4 + 3 * o4sc, df0y);
+                O4 += gflows4.sn;
             }
+        }
+        if (RECOMP && O4) {
+            sts_(O4, d01x); sts_(O4 + o4sc, d01y);
+            sts_(O4 + 2 * o4sc, d10x); sts_(O4 + 3 * o4sc, d10y);
         }
     }
     if (STAGE) record_absmax(&hdr->absmax_bits, amax);

@@ -105,10 +105,10 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
 }
 
 // ---- a4: scatter of the staged d/d(warped I0), d/d(warped I1) through the refined flows ---------
-template <typename T, int MODE>
+template <typename T, int MODE, bool RECOMP>
 __global__ void __launch_bounds__(TILE_THREADS)
 fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<const T> out5,
-                    long long* __restrict__ acc, int N, Geom g,
+                    const float* __restrict__ tv, long long* __restrict__ acc, int N, Geom g,
                     const ScatterHdr* __restrict__ hdr, int count_bits) {
     TileIdx ti = tile_index(g.H, g.W);
     if (!ti.valid) return;
@@ -116,13 +116,26 @@ fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<
     const int p = ti.y * g.W + ti.x;
     const long long npx = (long long)g.H * g.W;
     long long* a0 = acc + (long long)ti.b * 6 * npx;
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    if (RECOMP) {
+        const T* F = flows4.p + ti.b * flows4.sb + p;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = lds_(F + k * flows4.sc);
+    }
     for (int n = 0; n < N; ++n) {
-        const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
+        float xs[4];
+        if (RECOMP) {
+            est_flows<T>(__ldg(tv + ti.b * N + n), f, xs);
+        } else {
+            const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * flows4.sc);
+        }
         const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
-        const float f1x = __fadd_rn(lds_(X), lds_(Y + out5.sc));
-        const float f1y = __fadd_rn(lds_(X + flows4.sc), lds_(Y + 2 * out5.sc));
-        const float f0x = __fadd_rn(lds_(X + 2 * flows4.sc), lds_(Y + 3 * out5.sc));
-        const float f0y = __fadd_rn(lds_(X + 3 * flows4.sc), lds_(Y + 4 * out5.sc));
+        const float f1x = __fadd_rn(xs[0], lds_(Y + out5.sc));
+        const float f1y = __fadd_rn(xs[1], lds_(Y + 2 * out5.sc));
+        const float f0x = __fadd_rn(xs[2], lds_(Y + 3 * out5.sc));
+        const float f0y = __fadd_rn(xs[3], lds_(Y + 4 * out5.sc));
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
         const float* st = stage + ((long long)(ti.b * N + n) * 6) * npx + p;

@@ -44,6 +44,11 @@ class SynthesisMixin:
         """input_tensor B x N x 16, output_tensor B x N x 5, t B x N -> B x N x 3 x H x W."""
         return F_ssm.fuse(img_tensor, input_tensor, output_tensor, t)
 
+    def compute_output_image_from_flow(self, img_tensor, flow_pred_tensor, output_tensor, t):
+        """compute_output_image for callers that still hold flow_pred_tensor (B x 4): the estimated flows
+        input_tensor[:, 6:10] are recomputed in-kernel.  output_tensor B x N x 5, t B x N -> B x N x 3."""
+        return F_ssm.fuse_from_flow(img_tensor, flow_pred_tensor, output_tensor, t)
+
 
 def patch_reference(flow_interpolation_module, layers_module=None, losses_module=None):
     """Install the B200 path into an imported copy of the reference's scripts/models package:
@@ -56,7 +61,7 @@ def patch_reference(flow_interpolation_module, layers_module=None, losses_module
     from .layers import warp
     cls = flow_interpolation_module.FlowInterpolationModel
     for name in ("compute_inputs", "extract_outputs", "compute_output_image",
-                 "compute_inputs_batched", "compute_output_image_batched"):
+                 "compute_inputs_batched", "compute_output_image_batched", "compute_output_image_from_flow"):
         setattr(cls, name, getattr(SynthesisMixin, name))
     flow_interpolation_module.warp = warp
     for mod in (layers_module, losses_module):

@@ -285,6 +285,72 @@ def fuse(img6, in16, out5, t, coord_mode=None, packed=None):
 
 
 # ---------------------------------------------------------------------------------------------
+class _FuseFlow(torch.autograd.Function):
+    """compute_output_image for N timesteps with the estimated flows recomputed from flow_pred_tensor
+    (ssm_fuse_flow_fwd/bwd): same results as _Fuse on input_tensor = compute_inputs(img, flow, t)."""
+
+    @staticmethod
+    def forward(ctx, img6, flow4, out5, tvec, mode, packed):
+        _same(img6, flow4, out5)
+        img6, flow4, out5 = _abi.dense_planes(img6), _abi.dense_planes(flow4), _abi.dense_planes(out5)
+        B, C6, H, W = img6.shape
+        if out5.dim() != 5 or C6 != 6 or flow4.shape != (B, 4, H, W) or out5.shape[0] != B \
+                or out5.shape[2:] != (5, H, W):
+            raise RuntimeError("fuse_from_flow: expected img B x 6, flow B x 4, output B x N x 5 (x H x W), "
+                               "got %s, %s, %s" % (tuple(img6.shape), tuple(flow4.shape), tuple(out5.shape)))
+        N = out5.shape[1]
+        if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+            packed = pack_frames(img6)
+        out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
+        with torch.cuda.device(img6.device):
+            rc = _abi.lib().ssm_fuse_flow_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
+                                              _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)),
+                                              ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(out, True)),
+                                              B, N, H, W, _abi.dtype_code(img6), mode, _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_flow_fwd")
+        ctx.save_for_backward(img6, flow4, out5, tvec, packed)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g3):
+        img6, flow4, out5, tvec, packed = ctx.saved_tensors
+        B, _, H, W = img6.shape
+        N = out5.shape[1]
+        need_i, need_f, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_i or need_f or need_y):
+            return None, None, None, None, None, None
+        g3 = _abi.dense_planes(g3.to(img6.dtype))
+        gi = torch.empty_like(img6, memory_format=torch.contiguous_format) if need_i else None
+        gf = torch.empty_like(flow4, memory_format=torch.contiguous_format) if need_f else None
+        gy = torch.empty_like(out5, memory_format=torch.contiguous_format) if need_y else None
+        L = _abi.lib()
+        ws, ws_ptr, ws_bytes = None, None, 0
+        if need_i:
+            ws_bytes = L.ssm_fuse_bwd_workspace_bytes(B, N, H, W)
+            ws = _workspace(ws_bytes, img6.device)
+            ws_ptr = ctypes.c_void_p(ws.data_ptr())
+        with torch.cuda.device(img6.device):
+            rc = L.ssm_fuse_flow_bwd(_abi.ref(_abi.desc(g3, True)), _abi.ref(_abi.desc(img6, False)),
+                                     _packed_ptr(packed, img6), _abi.ref(_abi.desc(flow4, False)),
+                                     _abi.ref(_abi.desc(out5, True)), ctypes.c_void_p(tvec.data_ptr()),
+                                     _abi.ref(_abi.desc(gy, True)), _abi.ref(_abi.desc(gf, False)),
+                                     _abi.ref(_abi.desc(gi, False)), B, N, H, W, _abi.dtype_code(img6), ctx.mode,
+                                     ws_ptr, ws_bytes, _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_flow_bwd")
+        return gi, gf, gy, None, None, None
+
+
+def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None):
+    """Fused frames for every (pair, timestep) from the stage-1 flows: img6 B x 6, flow4 B x 4,
+    out5 B x N x 5 -> B x N x 3.  Equals fuse(img6, flow_pack(img6, flow4, t), out5, t) without reading
+    the 16-channel tensor back; gradients go to flow4 directly."""
+    B, N = out5.shape[0], out5.shape[1]
+    tvec = _t_vector(t, B * N, img6.device)
+    return _FuseFlow.apply(img6, flow4, out5, tvec, _resolve_mode(coord_mode), packed)
+
+
+# ---------------------------------------------------------------------------------------------
 def synthesize_host(img6, flow4, out5, t, coord_mode=None, return_inputs=False, out=None, scratch=None):
     """Whole path on HOST tensors (pinned memory recommended) through ssm_synthesize_host: copies
     in, runs the fused kernels for all N timesteps of every pair, copies the frames out.

@@ -11,7 +11,11 @@ What changes against the reference loop:
     and visualise loops call the whole model, stage 1 included, once per timestep
     (evaluate_interpolation_results.py:234-242, visualize_interpolation.py:139-144);
   * the inference extras come out of the tensors already at hand instead of being recomputed
-    (get_intermediate_outputs, :108-150).
+    (get_intermediate_outputs, :108-150);
+  * compute_output_image takes the stage-1 flows and recomputes input_tensor[:, 6:10] in-kernel
+    (ssm_fuse_flow_fwd/bwd) instead of reading the 16-channel tensor back, so in training the flow
+    gradient reaches stage 1 without the dense B x 16 gradient (12 zero channels) autograd builds for
+    the reference's slice.
 The two U-Nets are ordinary torch modules (out of scope); any pair with the reference's interface
 can be passed in, e.g. the reference's own FlowComputationModel / FlowInterpolationModel.
 """
@@ -85,13 +89,15 @@ class FullModel(nn.Module, SynthesisMixin):
         out5 = torch.stack(self.stage2_model(in16, encs), dim=1)      # B x W x 5 x H x W
         if inference_mode:
             sel = slice(mid, mid + 1)
-            frame = F_ssm.fuse(pairs[:, mid], in16[:, sel], out5[:, sel], t_bw[:, mid])[:, 0]
+            frame = F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5[:, sel], t_bw[:, mid])[:, 0]
             x, y = in16[:, mid], out5[:, mid]
             v_0t = 1 - torch.sigmoid(y[:, 0:1])
             extras = (flows[:, mid, 0:2], flows[:, mid, 2:4], x[:, 6:8], x[:, 8:10],
                       x[:, 6:8] + y[:, 1:3], x[:, 8:10] + y[:, 3:5], v_0t)
             return frame, extras
-        frames = F_ssm.fuse(flat(pairs), flat(in16).unsqueeze(1), flat(out5).unsqueeze(1), t_bw.reshape(-1))
+        # the estimated flows are recomputed from the stage-1 flows: no B x W x 16 gradient with 12 zero
+        # channels is built for in16, the flow gradient goes to `flows` directly
+        frames = F_ssm.fuse_from_flow(flat(pairs), flat(flows), flat(out5).unsqueeze(1), t_bw.reshape(-1))
         frames = frames.view(B, Wn, 3, *frames.shape[-2:])
         losses = 0
         for w in range(Wn):
@@ -129,5 +135,5 @@ class FullModel(nn.Module, SynthesisMixin):
             if encs[0] is not None:
                 e = [enc.repeat_interleave(n, dim=0) for enc in encs]
             out5 = self.stage2_model(x, e)[mid].view(B, n, 5, *in16.shape[-2:])
-            frames.append(F_ssm.fuse(pairs[:, mid], in16[:, mid], out5, tn, packed=rgbx[mid]))
+            frames.append(F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5, tn, packed=rgbx[mid]))
         return torch.cat(frames, dim=1)

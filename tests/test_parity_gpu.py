@@ -110,6 +110,48 @@ def test_batched_kernels_vs_c_oracle(mode_name, mode, B, N, H, W, kind, smooth):
     assert_close_fp32(a2.grad, ref_gimg2, "fuse grad img", tol=1e-5 * max(1, N // 2))
 
 
+@pytest.mark.parametrize("mode_name,mode", MODES)
+@pytest.mark.parametrize("B,N,H,W,kind,dtype", [
+    (2, 3, 64, 96, "smooth", torch.float32),
+    (1, 7, 45, 77, "border", torch.float32),
+    (2, 1, 352, 352, "smooth", torch.float32),
+    (2, 3, 64, 96, "smooth", torch.bfloat16),
+])
+def test_fuse_from_flow_equals_two_step_path(mode_name, mode, B, N, H, W, kind, dtype):
+    """ssm_fuse_flow_fwd/bwd recompute input_tensor[:, 6:10] from flow_pred_tensor: the frames must be
+    bit-identical to fuse(flow_pack(...)), the out5 gradient too, and the flow gradient must equal the
+    chain through the 16-channel tensor (and the C oracle's) to rounding."""
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=300 + H + N, kind=kind)
+    g3 = torch.randn(B, N, 3, H, W, generator=torch.Generator().manual_seed(8))
+    cast = lambda x, grad=False: x.to(DEV).to(dtype).requires_grad_(grad)
+    a, f, y, td = cast(img6, True), cast(flow4, True), cast(out5, True), _dev(t)
+    frames = ssm_b200.fuse_from_flow(a, f, y, td, coord_mode=mode_name)
+    frames.backward(cast(g3))
+    a2, f2, y2 = cast(img6, True), cast(flow4, True), cast(out5, True)
+    in16 = ssm_b200.flow_pack(a2.detach(), f2, td, n_timesteps=N, coord_mode=mode_name)
+    frames2 = ssm_b200.fuse(a2, in16, y2, td, coord_mode=mode_name)
+    # only the path through in16[:, 6:10] -> fuse: cut the warped-image channels of flow_pack out of the graph
+    frames2.backward(cast(g3))
+    assert torch.equal(frames, frames2), "recomputed estimated flows changed the frames"
+    assert torch.equal(y.grad, y2.grad)
+    assert torch.equal(a.grad, a2.grad)
+    if dtype == torch.float32:
+        # flow gradient of the two-step path = coefficients applied to grad in16[6:10] (+ zero through the
+        # warped channels, whose upstream gradient is zero here)
+        assert_close_fp32(f.grad, f2.grad, "fuse_from_flow grad flow vs two-step", tol=1e-5 * max(1, N // 2))
+        ref_gflow = torch.zeros_like(flow4)
+        for n in range(N):
+            tn = t[:, n]
+            r16 = c_oracle.compute_inputs(img6, flow4, tn, coord_mode=mode)
+            _, gx, _ = c_oracle.compute_output_image_backward(g3[:, n].contiguous(), img6, r16,
+                                                              out5[:, n].contiguous(), tn, coord_mode=mode, need_img=False)
+            _, gf = c_oracle.compute_inputs_backward(gx, img6, flow4, tn, coord_mode=mode, need_img=False)
+            ref_gflow += gf
+        assert_close_fp32(f.grad, ref_gflow, "fuse_from_flow grad flow vs C oracle", tol=1e-5 * max(1, N // 2))
+    else:
+        assert_close_bf16(f.grad, f2.grad.float(), "fuse_from_flow grad flow (bf16)")
+
+
 @pytest.mark.parametrize("C", [1, 3, 5])
 def test_warp_channels_and_partial_grads(C):
     B, H, W = 2, 40, 72

@@ -25,6 +25,7 @@ ap.add_argument("--height", type=int, default=1088)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f32")
+ap.add_argument("--from-flow", action="store_true", help="fuse_from_flow (estimated flows recomputed in-kernel)")
 a = ap.parse_args()
 
 H, W, B, N = a.height, a.width, a.pairs, a.timesteps
@@ -51,7 +52,7 @@ def ev():
 
 times = {"rgbx": [], "flow_pack": [], "fuse": [], "fuse_bwd": [], "flow_pack_bwd": []}
 for _ in range(a.reps):
-    e = [ev() for _ in range(6)]
+    e = [ev() for _ in range(7)]
     if a.bwd:
         f = flow4.clone().requires_grad_(True)
         y = out5.clone().requires_grad_(True)
@@ -64,14 +65,19 @@ for _ in range(a.reps):
         e[1].record()
         in16 = ssm_b200.flow_pack(im, f, t, n_timesteps=N, packed=rgbx)
         e[2].record()
-        fr = ssm_b200.fuse(im, in16, y, t, packed=rgbx)
+        fr = ssm_b200.fuse_from_flow(im, f, y, t, packed=rgbx) if a.from_flow else ssm_b200.fuse(im, in16, y, t, packed=rgbx)
         e[3].record()
     if a.bwd:
         g3 = torch.randn_like(fr)
         torch.cuda.synchronize()
         e[3].record()
-        (gin16, gy) = torch.autograd.grad(fr, (in16, y), g3, retain_graph=True) if not a.img_grad else torch.autograd.grad(fr, (in16, y, im), g3, retain_graph=True)[:2]
+        src = f if a.from_flow else in16
+        (gin16, gy) = torch.autograd.grad(fr, (src, y), g3, retain_graph=True) if not a.img_grad else torch.autograd.grad(fr, (src, y, im), g3, retain_graph=True)[:2]
         e[4].record()
+        if a.from_flow:   # stand-in for the stage-2 U-Net's gradient of its 16-channel input
+            gin16 = torch.randn_like(in16)
+            torch.cuda.synchronize()
+        e[6].record()
         torch.autograd.grad(in16, (f, im) if a.img_grad else (f,), gin16)
         e[5].record()
     torch.cuda.synchronize()
@@ -80,11 +86,11 @@ for _ in range(a.reps):
     times["fuse"].append(e[2].elapsed_time(e[3]) if not a.bwd else float("nan"))
     if a.bwd:
         times["fuse_bwd"].append(e[3].elapsed_time(e[4]))
-        times["flow_pack_bwd"].append(e[4].elapsed_time(e[5]))
+        times["flow_pack_bwd"].append(e[6].elapsed_time(e[5]))
     del in16, fr, rgbx
 
-algo = {"rgbx": 14 * esz * NPX * B, "flow_pack": (10 + 16 * N) * esz * NPX * B, "fuse": (6 + 12 * N) * esz * NPX * B,
-        "fuse_bwd": (6 + 21 * N) * esz * NPX * B, "flow_pack_bwd": (14 + 10 * N) * esz * NPX * B}
+algo = {"rgbx": 14 * esz * NPX * B, "flow_pack": (10 + 16 * N) * esz * NPX * B, "fuse": ((10 + 8 * N) if a.from_flow else (6 + 12 * N)) * esz * NPX * B,
+        "fuse_bwd": ((10 + 13 * N) if a.from_flow else (6 + 21 * N)) * esz * NPX * B, "flow_pack_bwd": (14 + 10 * N) * esz * NPX * B}
 out = {"args": vars(a)}
 for k, v in times.items():
     v = [x for x in v[1:] if x == x]

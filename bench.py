@@ -7,8 +7,8 @@
 Workload (BASELINE.json configs[1]): 16 synthetic 1088x1920 (1080p padded to /32) frame pairs per
 GPU, 7 intermediate timesteps, fp32.  One step = one pass of the hot path over the batch:
 an RGBx staging copy of the frames (one launch), compute_inputs for all 7 timesteps (one fused launch)
-and extract_outputs/compute_output_image for all 7 timesteps (one fused launch) = 112 interpolated
-frames per GPU.  The two flow U-Nets are out of
+and extract_outputs/compute_output_image for all 7 timesteps (one fused launch, estimated flows
+recomputed in-kernel from the stage-1 flows: ssm_fuse_flow_fwd) = 112 interpolated frames per GPU.  The two flow U-Nets are out of
 scope (they stay on PyTorch/cuDNN); the stage-2 output is a seeded surrogate.
 
   value      frames/s, inputs resident in HBM, device-timed with CUDA events, max over ranks
@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the backward-kernel timings")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -206,7 +207,7 @@ def main():
         with torch.no_grad():
             rgbx = ssm_b200.pack_frames(img6)              # RGBx staging copy, shared by both kernels
             in16 = ssm_b200.flow_pack(img6, flow4 if flow is None else flow, t, n_timesteps=NT, packed=rgbx)
-            return ssm_b200.fuse(img6, in16, out5, t, packed=rgbx)
+            return in16, ssm_b200.fuse_from_flow(img6, flow4 if flow is None else flow, out5, t, packed=rgbx)
 
     def barrier():
         if world > 1:
@@ -232,7 +233,7 @@ def main():
             ev[k][1].record()
             in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT, packed=rgbx)
             ev[k][2].record()
-            frames = ssm_b200.fuse(img6, in16, out5, t, packed=rgbx)
+            frames = ssm_b200.fuse_from_flow(img6, flow4, out5, t, packed=rgbx)
             ev[k][3].record()
     end.record()
     barrier()
@@ -251,7 +252,9 @@ def main():
     # roofline of the dominant kernel: algorithmic bytes = (10 + 16 N) * 4 B/px per pair
     peak, peak_src = _peaks()
     pack_bytes = (10 + 16 * NT) * 4 * NPX * B
-    fuse_bytes = (6 + 12 * NT) * 4 * NPX * B
+    # a3+a4 with the estimated flows recomputed from flow4: reads I (6) + F (4) per pair and out5 (5) per
+    # timestep, writes 3 per timestep (the reference-shaped call that re-reads in16[:, 6:10] is (6 + 12 N))
+    fuse_bytes = (10 + 8 * NT) * 4 * NPX * B
     pack_gbs = pack_bytes / (pack_ms * 1e-3) / 1e9
     fuse_gbs = fuse_bytes / (fuse_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "flow_pack_fwd_kernel<float>", "achieved": pack_gbs, "peak": peak,
@@ -292,6 +295,34 @@ def main():
                   "path_algorithmic_gbs": (pack_bytes + fuse_bytes) / (ms * 1e-3) / 1e9,
                   "path_frac_of_peak": (pack_bytes + fuse_bytes) / (ms * 1e-3) / 1e9 / peak}
         del flow_s
+
+    # ---- training backward of the same kernels (flow / U-Net-output gradients; frames are data) ----
+    train = None
+    if rank == 0 and not args.no_train:
+        fg, yg = flow4.clone().requires_grad_(True), out5.clone().requires_grad_(True)
+        rgbx = ssm_b200.pack_frames(img6)
+        in16 = ssm_b200.flow_pack(img6, fg, t, n_timesteps=NT, packed=rgbx)
+        frames = ssm_b200.fuse_from_flow(img6, fg, yg, t, packed=rgbx)
+        g3, g16 = torch.randn_like(frames), torch.randn_like(in16)
+        tb = {"fuse_flow_bwd": [], "flow_pack_bwd": []}
+        for i in range(8):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            torch.autograd.grad(frames, (fg, yg), g3, retain_graph=True)
+            e[1].record()
+            torch.autograd.grad(in16, (fg,), g16, retain_graph=True)
+            e[2].record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                tb["fuse_flow_bwd"].append(e[0].elapsed_time(e[1]))
+                tb["flow_pack_bwd"].append(e[1].elapsed_time(e[2]))
+        nbytes = {"fuse_flow_bwd": (10 + 13 * NT) * 4 * NPX * B, "flow_pack_bwd": (14 + 10 * NT) * 4 * NPX * B}
+        train = {}
+        for k, v in tb.items():
+            ms = statistics.median(v)
+            train[k] = {"ms": ms, "algorithmic_gbs": nbytes[k] / (ms * 1e-3) / 1e9,
+                        "frac_of_peak": nbytes[k] / (ms * 1e-3) / 1e9 / peak}
+        del fg, yg, rgbx, in16, frames, g3, g16
 
     # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
     e2e = None
@@ -334,10 +365,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
-                       "frames_per_step": frames_per_step, "l2": "inputs_exceed_l2 (6.1 GB read, 18 GB written per step)",
+                       "frames_per_step": frames_per_step, "l2": "inputs_exceed_l2 (8.7 GB read, 18.9 GB written per step)",
                        "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
                        "parallelism": "pairs sharded over %d rank(s), no collective" % world},
-            "roofline": roofline, "kernels": kernels, "smooth_flow_variant": smooth, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -155,6 +155,31 @@ int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const voi
                       int B, int N, int H, int W, int dtype, int coord_mode,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a4 + a9: compute_output_image fused with the loss front-end of SSMLosses
+ *      [reference scripts/models/losses.py:104-170, 213-233; SURVEY.md section 8(f) rank 1].
+ * Besides out3 (the fused frame, as ssm_fuse_flow_fwd) it returns, per pair b, the sums over all
+ * 3*H*W elements of the three L1 maps the reference builds with ~30 more ATen launches and two more
+ * warp calls per window:  sums[b*(2N+1) + 2n]   = sum |out3[b,n] - target[b,n]|           (:111)
+ *                         sums[b*(2N+1) + 2n+1] = sum |g(I0,F^_t0) - target| + |g(I1,F^_t1) - target|  (:152-154,166-167; 0 if !stage2_loss)
+ *                         sums[b*(2N+1) + 2N]   = sum |g(I1,F01) - I0| + |g(I0,F10) - I1|  (:160-163; 0 if !stage1_loss)
+ * (the stage-2 warps are the ones compute_output_image performs anyway).  The caller divides by
+ * 3*H*W and applies the lambda weights (:213-233).  target: B x N x 3 x H x W.  sums: DEVICE pointer
+ * to B*(2N+1) floats.  Deterministic: per-CTA partial sums in `workspace`
+ * (ssm_fuse_loss_workspace_bytes) added per pair in a fixed order in fp64.
+ * Backward: grad3 (may be NULL) is the dense upstream gradient of out3, grad_sums (device,
+ * B*(2N+1) floats) the gradient of `sums`; writes grad_out5 (B x N x 5) and grad_flow4 (B x 4).
+ * Frames and targets are data here: no image gradients (use ssm_fuse_flow_bwd + ssm_warp_bwd). */
+size_t ssm_fuse_loss_workspace_bytes(int B, int N, int H, int W);
+int ssm_fuse_loss_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const ssm_tensor* out5,
+                      const ssm_tensor* target, const float* t, const ssm_tensor* out3, float* sums,
+                      int B, int N, int H, int W, int dtype, int coord_mode, int stage1_loss, int stage2_loss,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int ssm_fuse_loss_bwd(const ssm_tensor* grad3, const float* grad_sums, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const ssm_tensor* out5, const ssm_tensor* target, const ssm_tensor* out3,
+                      const float* t, const ssm_tensor* grad_out5, const ssm_tensor* grad_flow4,
+                      int B, int N, int H, int W, int dtype, int coord_mode, int stage1_loss, int stage2_loss,
+                      void* stream);
+
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
  * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */
 size_t ssm_warp_bwd_workspace_bytes(int B, int C, int H, int W);

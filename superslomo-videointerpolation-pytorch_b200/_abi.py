@@ -21,6 +21,7 @@ EXPORTS = (
     "ssm_warp_fwd", "ssm_warp_bwd",
     "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
     "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd",
+    "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd", "ssm_fuse_loss_workspace_bytes",
     "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
     "ssm_packed_frames_bytes", "ssm_pack_frames",
     "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
@@ -61,13 +62,16 @@ def lib():
     L.ssm_fuse_bwd.argtypes = [P, P, V, P, P, V, P, P, P, I, I, I, I, I, I, V, Z, V]
     L.ssm_fuse_flow_fwd.argtypes = L.ssm_fuse_fwd.argtypes
     L.ssm_fuse_flow_bwd.argtypes = L.ssm_fuse_bwd.argtypes
+    L.ssm_fuse_loss_fwd.argtypes = [P, V, P, P, P, V, P, V, I, I, I, I, I, I, I, I, V, Z, V]
+    L.ssm_fuse_loss_bwd.argtypes = [P, V, P, V, P, P, P, P, V, P, P, I, I, I, I, I, I, I, I, V]
     for n in ("ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
-              "ssm_packed_frames_bytes", "ssm_synthesize_host_scratch_bytes"):
+              "ssm_packed_frames_bytes", "ssm_synthesize_host_scratch_bytes", "ssm_fuse_loss_workspace_bytes"):
         getattr(L, n).argtypes = [I, I, I, I]
         getattr(L, n).restype = Z
     L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I, V, Z]
     for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
-              "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_synthesize_host"):
+              "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
+              "ssm_synthesize_host"):
         getattr(L, n).restype = I
     _lib = L
     return L

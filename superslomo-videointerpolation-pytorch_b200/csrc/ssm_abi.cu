@@ -271,6 +271,34 @@ struct FuseBwd {
     }
 };
 
+struct FuseLossFwd {
+    const ssm_tensor* img6; const void* packed; const ssm_tensor *flow4, *out5, *target; const float* t;
+    const ssm_tensor* out3; float* sums; int B, N, H, W, s1, s2; float* partials; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        const unsigned grid = tile_grid(B, H, W);
+        fuse_loss_fwd_kernel<T, MODE, PACKED><<<grid, TILE_THREADS, 0, s>>>(
+            cview<T>(img6), (const T*)packed, cview<T>(flow4), cview<T>(out5), cview<T>(target), t, mview<T>(out3),
+            partials, N, make_geom(H, W), s1, s2);
+        SSM_LAUNCH_CHECK("ssm_fuse_loss_fwd");
+        loss_reduce_kernel<<<B, 256, 0, s>>>(partials, (int)(grid / B), 2 * N + 1, sums);
+        SSM_LAUNCH_CHECK("ssm_fuse_loss_fwd (reduce)");
+        return SSM_OK;
+    }
+};
+
+struct FuseLossBwd {
+    const ssm_tensor* g3; const float* gsum; const ssm_tensor* img6; const void* packed;
+    const ssm_tensor *flow4, *out5, *target, *out3; const float* t; const ssm_tensor *gout5, *gflow4;
+    int B, N, H, W, s1, s2; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        fuse_loss_bwd_kernel<T, MODE, PACKED><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(g3), gsum, cview<T>(img6), (const T*)packed, cview<T>(flow4), cview<T>(out5), cview<T>(target),
+            cview<T>(out3), t, mview<T>(gout5), mview<T>(gflow4), N, make_geom(H, W), s1, s2);
+        SSM_LAUNCH_CHECK("ssm_fuse_loss_bwd");
+        return SSM_OK;
+    }
+};
+
 // exhaustive check of div_rn_const against the IEEE division for one divisor.
 // out[0] += dividends whose NORMALISED COORDINATE rn(q - 1) differs (what the path consumes,
 // layers.py:112); out[1] += dividends whose raw quotient differs; out[2] = one such dividend's bits.
@@ -469,6 +497,55 @@ int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const voi
                       void* workspace, size_t workspace_bytes, void* stream) {
     return fuse_bwd_impl(grad3, img6, packed, flow4, out5, t, grad_out5, grad_flow4, grad_img6, B, N, H, W, dtype,
                          coord_mode, workspace, workspace_bytes, stream, true);
+}
+
+size_t ssm_fuse_loss_workspace_bytes(int B, int N, int H, int W) {
+    if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(float) * (size_t)tile_grid(B, H, W) * (2 * (size_t)N + 1);
+}
+
+int ssm_fuse_loss_fwd(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const ssm_tensor* out5,
+                      const ssm_tensor* target, const float* t, const ssm_tensor* out3, float* sums,
+                      int B, int N, int H, int W, int dtype, int coord_mode, int stage1_loss, int stage2_loss,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_packed(packed));
+    SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_tensor(out5, "out5", dtype, true));
+    SSM_TRY(check_tensor(target, "target", dtype, true));
+    SSM_TRY(check_tensor(out3, "out3", dtype, true));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    if (!sums) return fail(SSM_ERR_NULL, "sums is NULL");
+    if (!workspace || workspace_bytes < ssm_fuse_loss_workspace_bytes(B, N, H, W))
+        return fail(SSM_ERR_WORKSPACE, "ssm_fuse_loss_fwd: needs %zu workspace bytes, got %zu",
+                    ssm_fuse_loss_workspace_bytes(B, N, H, W), workspace ? workspace_bytes : (size_t)0);
+    if (((uintptr_t)workspace) % 4 != 0 || ((uintptr_t)sums) % 4 != 0) return fail(SSM_ERR_ALIGN, "workspace / sums must be 4-byte aligned");
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     FuseLossFwd{img6, packed, flow4, out5, target, t, out3, sums, B, N, H, W, stage1_loss != 0,
+                                 stage2_loss != 0, (float*)workspace, (cudaStream_t)stream});
+}
+
+int ssm_fuse_loss_bwd(const ssm_tensor* grad3, const float* grad_sums, const ssm_tensor* img6, const void* packed,
+                      const ssm_tensor* flow4, const ssm_tensor* out5, const ssm_tensor* target, const ssm_tensor* out3,
+                      const float* t, const ssm_tensor* grad_out5, const ssm_tensor* grad_flow4,
+                      int B, int N, int H, int W, int dtype, int coord_mode, int stage1_loss, int stage2_loss,
+                      void* stream) {
+    SSM_TRY(check_packed(packed));
+    SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(grad3, "grad3", dtype, false));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_tensor(out5, "out5", dtype, true));
+    SSM_TRY(check_tensor(target, "target", dtype, true));
+    SSM_TRY(check_tensor(out3, "out3", dtype, true));
+    SSM_TRY(check_tensor(grad_out5, "grad_out5", dtype, false));
+    SSM_TRY(check_tensor(grad_flow4, "grad_flow4", dtype, false));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    if (!grad_sums) return fail(SSM_ERR_NULL, "grad_sums is NULL");
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     FuseLossBwd{grad3, grad_sums, img6, packed, flow4, out5, target, out3, t, grad_out5, grad_flow4,
+                                 B, N, H, W, stage1_loss != 0, stage2_loss != 0, (cudaStream_t)stream});
 }
 
 // ---------------------------------------------------------------------------------------------

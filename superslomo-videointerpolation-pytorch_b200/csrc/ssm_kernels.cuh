@@ -501,4 +501,257 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ pack
     if (STAGE) record_absmax(&hdr->absmax_bits, amax);
 }
 
+// =============================================================================================
+// a9 + a4 fused: compute_output_image together with the loss
+// front-end of scripts/models/losses.py -- the L1 reconstruction term |I_t - target| (:111, :217),
+// the stage-2 warp loss |g(I0, F^_t0) - target| + |g(I1, F^_t1) - target| (:152-154, :166-167, whose
+// two warps are exactly the ones compute_output_image performs, flow_interpolation.py:416-418) and
+// the stage-1 warp loss |g(I1, F01) - I0| + |g(I0, F10) - I1| (:160-163).  The kernel writes the fused
+// frame and per-CTA partial sums of the three L1 terms; loss_reduce_kernel adds the partials of
+// each sample in a fixed order (deterministic, fp64).  The per-sample means and the lambda weights
+// (losses.py:213-233) are applied by the caller.
+// partials: [grid][2 N + 1] floats = (rec, warp2) per timestep, then warp1.
+// =============================================================================================
+__device__ __forceinline__ float block_sum(float v, float* red) {   // result valid in thread 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < TILE_THREADS / 32; ++w) r += red[w];
+    }
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float sign_(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+template <typename T, int MODE, bool PACKED>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+fuse_loss_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flow4, View<const T> out5,
+                     View<const T> target, const float* __restrict__ tv, View<T> out3, float* __restrict__ partials,
+                     int N, Geom g, int stage1_on, int stage2_on) {
+    __shared__ float red[TILE_THREADS / 32];
+    const TileIdx ti = tile_index(g.H, g.W);
+    const int p = ti.y * g.W + ti.x;
+    const long long npx = (long long)g.H * g.W;
+    const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
+    const float* tp = tv + ti.b * N;
+    float* part = partials + (long long)blockIdx.x * (2 * N + 1);
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    float w1sum = 0.0f;
+    if (ti.valid) {
+        const T* F = flow4.p + ti.b * flow4.sb + p;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = lds_(F + k * (int)flow4.sc);
+        if (stage1_on) {                                              // losses.py:160-163
+            float c0[3], c1[3];
+            if (PACKED) { load_px(fr.f0 + (long long)p * 4, c0); load_px(fr.f1 + (long long)p * 4, c1); }
+            else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { c0[c] = ldg_(fr.f0 + c * fr.sc + p); c1[c] = ldg_(fr.f1 + c * fr.sc + p); }
+            }
+            const Taps ta = make_taps<MODE>(ti.x, ti.y, f[0], f[1], g);   // warp(img_1, flow_01) vs img_0
+            const Taps tb = make_taps<MODE>(ti.x, ti.y, f[2], f[3], g);   // warp(img_0, flow_10) vs img_1
+            Quad qa[3], qb[3];
+            gather3<T, PACKED>(fr.f1, fr.sc, ta, g.W, qa);
+            gather3<T, PACKED>(fr.f0, fr.sc, tb, g.W, qb);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                w1sum += fabsf(storage_round<T>(bilerp(qa[c], ta)) - c0[c]) + fabsf(storage_round<T>(bilerp(qb[c], tb)) - c1[c]);
+        }
+    }
+    for (int n = 0; n < N; ++n) {
+        float rec = 0.0f, w2 = 0.0f;
+        if (ti.valid) {
+            const float tt = __ldg(tp + n);
+            const float omt = __fsub_rn(1.0f, tt);
+            float xs[4];
+            est_flows<T>(tt, f, xs);
+            const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
+            const T* TG = target.p + ti.b * target.sb + n * target.sn + p;
+            T* O = out3.p + ti.b * out3.sb + n * out3.sn + p;
+            const int ysc = (int)out5.sc, tsc = (int)target.sc, osc = (int)out3.sc;
+            const float logit = lds_(Y);
+            const float f1x = __fadd_rn(xs[0], lds_(Y + ysc)), f1y = __fadd_rn(xs[1], lds_(Y + 2 * ysc));
+            const float f0x = __fadd_rn(xs[2], lds_(Y + 3 * ysc)), f0y = __fadd_rn(xs[3], lds_(Y + 4 * ysc));
+            float tg[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tg[c] = lds_(TG + c * tsc);
+            const float v1 = sigmoid_(logit);
+            const float v0 = 1.0f - v1;
+            const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
+            const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
+            Quad q0[3], q1[3];
+            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
+            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
+            const float rz = __frcp_rn(omt * v0 + tt * v1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float s0 = bilerp(q0[c], t0), s1 = bilerp(q1[c], t1);
+                const float o = storage_round<T>((omt * (v0 * s0) + tt * (v1 * s1)) * rz);
+                sts_(O + c * osc, o);
+                rec += fabsf(o - tg[c]);                                              // losses.py:111
+                if (stage2_on) w2 += fabsf(storage_round<T>(s0) - tg[c]) + fabsf(storage_round<T>(s1) - tg[c]);   // :166-167
+            }
+        }
+        const float r = block_sum(rec, red);
+        const float w = block_sum(w2, red);
+        if (threadIdx.x == 0) { part[2 * n] = r; part[2 * n + 1] = w; }
+    }
+    const float w1 = block_sum(w1sum, red);
+    if (threadIdx.x == 0) part[2 * N] = w1;
+}
+
+// sums[b][k] = sum over the tiles of pair b of partials[b * tiles + tile][k], k < K = 2 N + 1.
+// One CTA per pair; fixed assignment of tiles to threads and a fixed-order tree: deterministic.
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(const float* __restrict__ partials, int tiles, int K, float* __restrict__ sums) {
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    for (int k = 0; k < K; ++k) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < tiles; i += 256) acc += (double)partials[((long long)b * tiles + i) * K + k];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sums[(long long)b * K + k] = (float)red[0];
+        __syncthreads();
+    }
+}
+
+// Backward of fuse_loss_fwd_kernel: gradients w.r.t. the U-Net output (B x N x 5) and the stage-1
+// flows (B x 4, summed over timesteps and over both loss paths).  g3 (may be null) is the dense
+// upstream gradient of the fused frames (e.g. from the perceptual loss); gsum[b][2N+1] holds
+// dL/d(rec_n), dL/d(warp2_n), dL/d(warp1).  The L1 terms differentiate to sign() (torch: sign(0) = 0);
+// the fused frame is re-read (out3) so that the effective frame gradient is known before the gathers
+// and the per-frame reduced form of fuse_bwd_kernel applies.  Frames and targets are data: no image
+// gradients here (callers that need them use the unfused path).
+template <typename T, int MODE, bool PACKED>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+fuse_loss_bwd_kernel(View<const T> g3, const float* __restrict__ gsum, View<const T> img6, const T* __restrict__ packed,
+                     View<const T> flow4, View<const T> out5, View<const T> target, View<const T> out3,
+                     const float* __restrict__ tv, View<T> gout5, View<T> gflow4, int N, Geom g,
+                     int stage1_on, int stage2_on) {
+    const TileIdx ti = tile_index(g.H, g.W);
+    if (!ti.valid) return;
+    const int p = ti.y * g.W + ti.x;
+    const long long npx = (long long)g.H * g.W;
+    const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
+    const float* tp = tv + ti.b * N;
+    const float* gs = gsum + (long long)ti.b * (2 * N + 1);
+    float f[4];
+    {
+        const T* F = flow4.p + ti.b * flow4.sb + p;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = lds_(F + k * (int)flow4.sc);
+    }
+    float d01x = 0, d01y = 0, d10x = 0, d10y = 0;
+    if (stage1_on) {
+        const float gw1 = __ldg(gs + 2 * N);
+        float c0[3], c1[3];
+        if (PACKED) { load_px(fr.f0 + (long long)p * 4, c0); load_px(fr.f1 + (long long)p * 4, c1); }
+        else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { c0[c] = ldg_(fr.f0 + c * fr.sc + p); c1[c] = ldg_(fr.f1 + c * fr.sc + p); }
+        }
+        float gax = 0, gay = 0, gbx = 0, gby = 0;
+        {
+            const Taps ta = make_taps<MODE>(ti.x, ti.y, f[0], f[1], g);
+            Quad qa[3];
+            gather3<T, PACKED>(fr.f1, fr.sc, ta, g.W, qa);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bilerp_grad(qa[c], ta, gw1 * sign_(storage_round<T>(bilerp(qa[c], ta)) - c0[c]), gax, gay);
+        }
+        {
+            const Taps tb = make_taps<MODE>(ti.x, ti.y, f[2], f[3], g);
+            Quad qb[3];
+            gather3<T, PACKED>(fr.f0, fr.sc, tb, g.W, qb);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bilerp_grad(qb[c], tb, gw1 * sign_(storage_round<T>(bilerp(qb[c], tb)) - c1[c]), gbx, gby);
+        }
+        d01x = coord_grad_to_flow<MODE>(gax, g.xgrad, g.xnorm, g.xinv);
+        d01y = coord_grad_to_flow<MODE>(gay, g.ygrad, g.ynorm, g.yinv);
+        d10x = coord_grad_to_flow<MODE>(gbx, g.xgrad, g.xnorm, g.xinv);
+        d10y = coord_grad_to_flow<MODE>(gby, g.ygrad, g.ynorm, g.yinv);
+    }
+    for (int n = 0; n < N; ++n) {
+        const float tt = __ldg(tp + n);
+        const float omt = __fsub_rn(1.0f, tt);
+        const float grec = __ldg(gs + 2 * n), gw2 = stage2_on ? __ldg(gs + 2 * n + 1) : 0.0f;
+        float xs[4];
+        est_flows<T>(tt, f, xs);
+        const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
+        const T* TG = target.p + ti.b * target.sb + n * target.sn + p;
+        const T* O = out3.p + ti.b * out3.sb + n * out3.sn + p;
+        const int ysc = (int)out5.sc, tsc = (int)target.sc, osc = (int)out3.sc;
+        const float logit = lds_(Y);
+        const float f1x = __fadd_rn(xs[0], lds_(Y + ysc)), f1y = __fadd_rn(xs[1], lds_(Y + 2 * ysc));
+        const float f0x = __fadd_rn(xs[2], lds_(Y + 3 * ysc)), f0y = __fadd_rn(xs[3], lds_(Y + 4 * ysc));
+        float tg[3], gc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            tg[c] = lds_(TG + c * tsc);
+            gc[c] = grec * sign_(lds_(O + c * osc) - tg[c]);
+            if (g3.p) gc[c] += lds_(g3.p + ti.b * g3.sb + n * g3.sn + p + c * (int)g3.sc);
+        }
+        const float v1 = sigmoid_(logit);
+        const float v0 = 1.0f - v1;
+        const float rz = __frcp_rn(omt * v0 + tt * v1);
+        const float k0 = omt * rz, k1 = tt * rz;
+        float A0 = 0, A1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
+        {
+            const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
+            Quad q[3];
+            gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sv = bilerp(q[c], t0);
+                A0 = fmaf(gc[c], sv, A0);
+                bilerp_grad(q[c], t0, k0 * v0 * gc[c] + gw2 * sign_(storage_round<T>(sv) - tg[c]), g0x, g0y);
+            }
+        }
+        {
+            const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
+            Quad q[3];
+            gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sv = bilerp(q[c], t1);
+                A1 = fmaf(gc[c], sv, A1);
+                bilerp_grad(q[c], t1, k1 * v1 * gc[c] + gw2 * sign_(storage_round<T>(sv) - tg[c]), g1x, g1y);
+            }
+        }
+        const float dz = -rz * (k0 * v0 * A0 + k1 * v1 * A1);
+        const float dv0 = k0 * A0 + omt * dz, dv1 = k1 * A1 + tt * dz;
+        const float df1x = coord_grad_to_flow<MODE>(g1x, g.xgrad, g.xnorm, g.xinv);
+        const float df1y = coord_grad_to_flow<MODE>(g1y, g.ygrad, g.ynorm, g.yinv);
+        const float df0x = coord_grad_to_flow<MODE>(g0x, g.xgrad, g.xnorm, g.xinv);
+        const float df0y = coord_grad_to_flow<MODE>(g0y, g.ygrad, g.ynorm, g.yinv);
+        if (gout5.p) {
+            T* o = gout5.p + ti.b * gout5.sb + n * gout5.sn + p;
+            const int o5sc = (int)gout5.sc;
+            sts_(o, (dv1 - dv0) * (v1 * (1.0f - v1)));
+            sts_(o + o5sc, df1x); sts_(o + 2 * o5sc, df1y);
+            sts_(o + 3 * o5sc, df0x); sts_(o + 4 * o5sc, df0y);
+        }
+        const Coef k = make_coef(tt);
+        d01x += k.c00 * df0x + k.c10 * df1x;
+        d01y += k.c00 * df0y + k.c10 * df1y;
+        d10x += k.c01 * df0x - k.c11 * df1x;
+        d10y += k.c01 * df0y - k.c11 * df1y;
+    }
+    if (gflow4.p) {
+        T* o = gflow4.p + ti.b * gflow4.sb + p;
+        const int osc = (int)gflow4.sc;
+        sts_(o, d01x); sts_(o + osc, d01y);
+        sts_(o + 2 * osc, d10x); sts_(o + 3 * osc, d10y);
+    }
+}
+
 }  // namespace ssm

@@ -351,6 +351,81 @@ def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None):
 
 
 # ---------------------------------------------------------------------------------------------
+class _FuseLoss(torch.autograd.Function):
+    """compute_output_image + the L1 loss front-end of SSMLosses (ssm_fuse_loss_fwd/bwd):
+    flow_interpolation.py:394-429 with losses.py:111, 152-167."""
+
+    @staticmethod
+    def forward(ctx, img6, flow4, out5, target, tvec, stage1_loss, stage2_loss, mode, packed):
+        _same(img6, flow4, out5, target)
+        img6, flow4 = _abi.dense_planes(img6), _abi.dense_planes(flow4)
+        out5, target = _abi.dense_planes(out5), _abi.dense_planes(target)
+        B, C6, H, W = img6.shape
+        if out5.dim() != 5 or C6 != 6 or flow4.shape != (B, 4, H, W) or out5.shape[0] != B \
+                or out5.shape[2:] != (5, H, W) or target.shape != (B, out5.shape[1], 3, H, W):
+            raise RuntimeError("fuse_loss: expected img B x 6, flow B x 4, output B x N x 5, target B x N x 3 "
+                               "(x H x W), got %s, %s, %s, %s" % (tuple(img6.shape), tuple(flow4.shape),
+                                                                 tuple(out5.shape), tuple(target.shape)))
+        N = out5.shape[1]
+        if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+            packed = pack_frames(img6)
+        L = _abi.lib()
+        out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
+        sums = torch.empty((B, 2 * N + 1), dtype=torch.float32, device=img6.device)
+        ws_bytes = L.ssm_fuse_loss_workspace_bytes(B, N, H, W)
+        ws = _workspace(ws_bytes, img6.device)
+        with torch.cuda.device(img6.device):
+            rc = L.ssm_fuse_loss_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
+                                     _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)),
+                                     _abi.ref(_abi.desc(target, True)), ctypes.c_void_p(tvec.data_ptr()),
+                                     _abi.ref(_abi.desc(out, True)), ctypes.c_void_p(sums.data_ptr()),
+                                     B, N, H, W, _abi.dtype_code(img6), mode, int(stage1_loss), int(stage2_loss),
+                                     ctypes.c_void_p(ws.data_ptr()), ws_bytes, _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_loss_fwd")
+        ctx.save_for_backward(img6, flow4, out5, target, tvec, packed, out)
+        ctx.mode, ctx.s1, ctx.s2 = mode, int(stage1_loss), int(stage2_loss)
+        return out, sums
+
+    @staticmethod
+    def backward(ctx, g3, gsums):
+        img6, flow4, out5, target, tvec, packed, out = ctx.saved_tensors
+        B, _, H, W = img6.shape
+        N = out5.shape[1]
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
+            raise RuntimeError("fuse_loss treats frames and targets as data (no image gradients): use "
+                               "fuse_from_flow + warp for a graph that differentiates the images")
+        need_f, need_y = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_f or need_y):
+            return (None,) * 9
+        g3 = _abi.dense_planes(g3.to(img6.dtype)) if g3 is not None else None
+        gsums = (gsums if gsums is not None else torch.zeros((B, 2 * N + 1), device=img6.device)).float().contiguous()
+        gf = torch.empty_like(flow4, memory_format=torch.contiguous_format) if need_f else None
+        gy = torch.empty_like(out5, memory_format=torch.contiguous_format) if need_y else None
+        with torch.cuda.device(img6.device):
+            rc = _abi.lib().ssm_fuse_loss_bwd(
+                _abi.ref(_abi.desc(g3, True)), ctypes.c_void_p(gsums.data_ptr()), _abi.ref(_abi.desc(img6, False)),
+                _packed_ptr(packed, img6), _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)),
+                _abi.ref(_abi.desc(target, True)), _abi.ref(_abi.desc(out, True)), ctypes.c_void_p(tvec.data_ptr()),
+                _abi.ref(_abi.desc(gy, True)), _abi.ref(_abi.desc(gf, False)), B, N, H, W, _abi.dtype_code(img6),
+                ctx.mode, ctx.s1, ctx.s2, _abi.stream_ptr(img6.device))
+        _abi.check(rc, "ssm_fuse_loss_bwd")
+        return None, gf, gy, None, None, None, None, None, None
+
+
+def fuse_loss(img6, flow4, out5, target, t, stage1_loss=True, stage2_loss=True, coord_mode=None, packed=None):
+    """Fused frames AND the sums of the L1 loss maps of losses.py in one pass.
+
+    img6 B x 6, flow4 B x 4, out5 B x N x 5, target B x N x 3 -> (frames B x N x 3, sums B x (2N+1)) with
+    sums[:, 2n] = sum |frame_n - target_n|, sums[:, 2n+1] = stage-2 warp loss sum of timestep n,
+    sums[:, 2N] = stage-1 warp loss sum (zero when the corresponding flag is off).  Both outputs are
+    differentiable w.r.t. flow4 and out5; frames and targets are data."""
+    B, N = out5.shape[0], out5.shape[1]
+    tvec = _t_vector(t, B * N, img6.device)
+    return _FuseLoss.apply(img6, flow4, out5, target, tvec, bool(stage1_loss), bool(stage2_loss),
+                           _resolve_mode(coord_mode), packed)
+
+
+# ---------------------------------------------------------------------------------------------
 def synthesize_host(img6, flow4, out5, t, coord_mode=None, return_inputs=False, out=None, scratch=None):
     """Whole path on HOST tensors (pinned memory recommended) through ssm_synthesize_host: copies
     in, runs the fused kernels for all N timesteps of every pair, copies the frames out.

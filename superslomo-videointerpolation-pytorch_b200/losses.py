@@ -13,6 +13,7 @@ per-sample mean (kept per sample because the reference gathers it across DataPar
 import torch
 import torch.nn as nn
 
+from . import functional as F_ssm
 from .layers import warp
 
 
@@ -59,3 +60,23 @@ class SSMLosses(nn.Module):
         wl = _sample_mean(lambda_w * wl)
         total = rec + wl + per
         return torch.cat([total, rec, wl, per], dim=1)     # [B, 4]
+
+    def fused_forward(self, img_tensor, flowC_output, flowI_output, t, target_image):
+        """compute_output_image and this module's forward() in one fused pass (ssm_fuse_loss_fwd/bwd):
+        img_tensor B x 6, flowC_output B x 4, flowI_output B x 5, t B values, target_image B x 3
+        -> (interpolated_image B x 3, losses [B, 4]).  Same values as
+        forward(img, flowC_output, compute_inputs(...), flowI_output, compute_output_image(...), target)
+        without the two extra warps (losses.py:152-154) and ~30 elementwise launches per window."""
+        lambda_r, lambda_p, lambda_w = self.loss_weights
+        frames, sums = F_ssm.fuse_loss(img_tensor, flowC_output, flowI_output.unsqueeze(1), target_image.unsqueeze(1),
+                                       t, stage1_loss=not self.stage1_frozen, stage2_loss=not self.stage2_frozen)
+        frame = frames[:, 0]
+        count = float(target_image[0].numel())
+        rec = (lambda_r / count) * sums[:, 0:1]
+        wl = (lambda_w / count) * (sums[:, 1:2] + sums[:, 2:3])
+        if self.perceptual_features is not None and lambda_p != 0:
+            fa, fb = self.perceptual_features(frame), self.perceptual_features(target_image)
+            per = _sample_mean(lambda_p * (fa - fb) ** 2)
+        else:
+            per = torch.zeros_like(rec)
+        return frame, torch.cat([rec + wl + per, rec, wl, per], dim=1).to(frame.dtype)

@@ -95,6 +95,12 @@ class FullModel(nn.Module, SynthesisMixin):
             extras = (flows[:, mid, 0:2], flows[:, mid, 2:4], x[:, 6:8], x[:, 8:10],
                       x[:, 6:8] + y[:, 1:3], x[:, 8:10] + y[:, 3:5], v_0t)
             return frame, extras
+        if isinstance(self.loss, SSMLosses) and not pairs.requires_grad and not target_images.requires_grad:
+            # fused: frames + L1 reconstruction + warp losses of every window in one launch
+            frames, losses = self.loss.fused_forward(flat(pairs), flat(flows), flat(out5), t_bw.reshape(-1),
+                                                     flat(target_images))
+            frames = frames.view(B, Wn, 3, *frames.shape[-2:])
+            return frames[:, mid], losses.view(B, Wn, 4).sum(dim=1) / Wn
         # the estimated flows are recomputed from the stage-1 flows: no B x W x 16 gradient with 12 zero
         # channels is built for in16, the flow gradient goes to `flows` directly
         frames = F_ssm.fuse_from_flow(flat(pairs), flat(flows), flat(out5).unsqueeze(1), t_bw.reshape(-1))

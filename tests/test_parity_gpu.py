@@ -152,6 +152,49 @@ def test_fuse_from_flow_equals_two_step_path(mode_name, mode, B, N, H, W, kind, 
         assert_close_bf16(f.grad, f2.grad.float(), "fuse_from_flow grad flow (bf16)")
 
 
+@pytest.mark.parametrize("s1,s2", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("B,N,H,W,kind", [(3, 1, 64, 96, "smooth"), (2, 1, 45, 77, "border"), (2, 3, 40, 72, "smooth")])
+def test_fused_loss_front_end_vs_reference_ops(B, N, H, W, kind, s1, s2):
+    """ssm_fuse_loss_fwd/bwd vs the reference's loss front-end restated with torch ops on the C oracle's
+    warps (losses.py:111, 152-167): loss sums, frames and the gradients of a weighted loss w.r.t. the
+    stage-1 flows and the stage-2 output."""
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=500 + H + N, kind=kind)
+    target = synthetic.frames(B * N, H, W, n_frames=1, seed=77).view(B, N, 3, H, W)
+    g3 = torch.randn(B, N, 3, H, W, generator=torch.Generator().manual_seed(3)) * 1e-3
+    wts = torch.rand(B, 2 * N + 1, generator=torch.Generator().manual_seed(4)) + 0.5
+    a, f, y = _dev(img6), _dev(flow4, True), _dev(out5, True)
+    frames, sums = ssm_b200.fuse_loss(a, f, y, _dev(target), _dev(t), stage1_loss=s1, stage2_loss=s2)
+    ((sums * _dev(wts)).sum() / (3 * H * W) + (frames * _dev(g3)).sum()).backward()
+    # reference composition on the GPU path's own unfused ops (already pinned to the oracle above)
+    f2, y2 = _dev(flow4, True), _dev(out5, True)
+    fr2 = ssm_b200.fuse_from_flow(a, f2, y2, _dev(t))
+    in16 = ssm_b200.flow_pack(a, f2, _dev(t), n_timesteps=N)
+    tg = _dev(target)
+    ref = torch.zeros(B, 2 * N + 1, device=DEV)
+    cols = []
+    for n in range(N):
+        rec = (fr2[:, n] - tg[:, n]).abs().flatten(1).sum(1)
+        w2 = torch.zeros_like(rec)
+        if s2:
+            ft1 = in16[:, n, 6:8] + y2[:, n, 1:3]
+            ft0 = in16[:, n, 8:10] + y2[:, n, 3:5]
+            w2 = ((ssm_b200.warp(a[:, 0:3], ft0) - tg[:, n]).abs() + (ssm_b200.warp(a[:, 3:6], ft1) - tg[:, n]).abs()).flatten(1).sum(1)
+        cols += [rec, w2]
+    w1 = torch.zeros(B, device=DEV)
+    if s1:
+        w1 = ((ssm_b200.warp(a[:, 3:6], f2[:, 0:2]) - a[:, 0:3]).abs() + (ssm_b200.warp(a[:, 0:3], f2[:, 2:4]) - a[:, 3:6]).abs()).flatten(1).sum(1)
+    ref = torch.stack(cols + [w1], dim=1)
+    ((ref * _dev(wts)).sum() / (3 * H * W) + (fr2 * _dev(g3)).sum()).backward()
+    assert_close_fp32(frames, fr2, "fused-loss frames")
+    rel = ((sums - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+    assert rel <= 2e-6, "loss sums: relative error %.3e" % rel
+    # the loss gradients carry a 1/(3HW) factor: compare relative to the largest reference gradient
+    for got, want, what in ((y.grad, y2.grad, "out5"), (f.grad, f2.grad, "flow4")):
+        scale = want.abs().max().item()
+        assert max_err(got, want) <= 2e-5 * scale, "fused-loss grad %s: max err %.3e vs scale %.3e" % (
+            what, max_err(got, want), scale)
+
+
 @pytest.mark.parametrize("C", [1, 3, 5])
 def test_warp_channels_and_partial_grads(C):
     B, H, W = 2, 40, 72

@@ -180,6 +180,30 @@ int ssm_fuse_loss_bwd(const ssm_tensor* grad3, const float* grad_sums, const ssm
                       int B, int N, int H, int W, int dtype, int coord_mode, int stage1_loss, int stage2_loss,
                       void* stream);
 
+/* ---- the steps either side of the path --------------------------
+ * ssm_frames_from_u8: F uint8 images (H_in x W_in x 3, cv2 BGR if bgr != 0, else RGB; byte strides
+ * src_frame_stride / src_row_stride) -> normalised frames of H x W (H_in x W_in placed at (top, left),
+ * the rest filled with pad_value3[c]) written as planar F x 3 x H x W (`planar`, may be NULL) and/or
+ * as the RGBx copy of ssm_pack_frames (`rgbx`, F x H x W x 4, may be NULL) in one pass.
+ * lut_device: DEVICE float[3][256], lut[c][v] = normalised value of byte v in output channel c
+ * (R, G, B); the caller fills it with the reference's expression so the result is bit-identical to
+ * [scripts/visualize_interpolation.py:61-88, 257-262] (pad with 0 BEFORE normalising: pad_value3[c] =
+ * lut[c][0]) or [scripts/utils/dataloaders/augmentations.py:181-190 + default_reader.py:266-271] (zero
+ * pad AFTER normalising: pad_value3 = 0).  pad_value3: HOST float[3].  W must be a multiple of 4.
+ * A frame pair (B x 6 x H x W) is two consecutive frames of this layout.
+ * ssm_frames_to_u8: the inverse [scripts/evaluate_interpolation_results.py:143-163, 192-202;
+ * scripts/visualize_interpolation.py:221-232, 264-268]: crop H_out x W_out at (top, left),
+ * (x * std3[c] + mean3[c]) * scale with separately rounded operations, then numpy's astype(uint8)
+ * (truncate, out-of-range values wrap; saturate != 0 clamps to [0, 255] first), RGB or BGR bytes.
+ * mean3 / std3: HOST float[3]. */
+int ssm_frames_from_u8(const unsigned char* src, long long src_frame_stride, int src_row_stride, int bgr,
+                       int F, int H_in, int W_in, int H, int W, int top, int left,
+                       const float* lut_device, const float* pad_value3, const ssm_tensor* planar, void* rgbx,
+                       int dtype, void* stream);
+int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int left, int H_out, int W_out,
+                     const float* mean3, const float* std3, float scale, int bgr, int saturate,
+                     unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int dtype, void* stream);
+
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
  * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */
 size_t ssm_warp_bwd_workspace_bytes(int B, int C, int H, int W);

@@ -139,3 +139,57 @@ def interpolate_frames(stage1, stage2, image_tensor, n_intermediate):
         t = torch.full((B, T - 1, 1, 1, 1), float(idx), device=image_tensor.device) / float(n_intermediate + 1)
         out.append(model_forward(stage1, stage2, image_tensor, t)[0])
     return torch.stack(out, dim=1)
+
+
+# ---- frame pre/post-processing.  Parity unpinned: the reference
+# holds these steps inside classes that need cv2 / a CUDA device / config files to instantiate
+# (Interpolator, Evaluator), so they are restated here from the cited lines and not checked against an
+# imported reference; each is a handful of torch / numpy calls.
+PIXEL_MEAN = (0.485, 0.456, 0.406)
+PIXEL_STD = (0.229, 0.224, 0.225)
+
+
+def load_batch_and_normalize(bgr_u8, device="cpu"):
+    """scripts/visualize_interpolation.py:61-88 (load_batch) then :257-262 (normalize_tensor).
+    bgr_u8: T x H x W x 3 uint8 numpy array as cv2.imread returns it -> 1 x T x 3 x H32 x W32 fp32."""
+    import numpy as np
+    frame_buffer = np.ascontiguousarray(bgr_u8[:, :, :, ::-1])[None, ...]            # :68-72  RGB, 1 T H W C
+    frame_buffer = torch.from_numpy(frame_buffer).float().to(device)                 # :73
+    frame_buffer = frame_buffer.permute(0, 1, 4, 2, 3)                               # :74
+    _, _, _, H, W = frame_buffer.shape
+    padding = [0, 0, 0, 0]                                                           # l, r, top, bottom
+    if H % 32 != 0:
+        h_pad = 32 - (H % 32)
+        padding[2] = h_pad // 2
+        padding[3] = h_pad - padding[2]
+    if W % 32 != 0:
+        w_pad = 32 - (W % 32)
+        padding[0] = w_pad // 2
+        padding[1] = w_pad - padding[0]
+    frame_buffer = F.pad(frame_buffer, padding, mode="constant", value=0)            # :87
+    pix_mean = torch.tensor(PIXEL_MEAN).view(1, 1, -1, 1, 1).to(device)              # :258-260
+    pix_std = torch.tensor(PIXEL_STD).view(1, 1, -1, 1, 1).to(device)
+    return (frame_buffer / 255.0 - pix_mean) / pix_std
+
+
+def reader_normalize_and_pad(rgb_u8, pad_tb):
+    """scripts/utils/dataloaders/augmentations.py:181-200 (Normalize on the uint8 numpy array: float64
+    arithmetic; ToTensor) then default_reader.py:266-271 (EvalPad(ZeroPad2d([0, 0, pad, pad]))) and the
+    .float() the trainer applies.  rgb_u8: T x H x W x 3 -> T x 3 x (H + 2 pad) x W fp32."""
+    import numpy as np
+    sample = (rgb_u8 / 255.0 - np.asarray(PIXEL_MEAN)) / np.asarray(PIXEL_STD)
+    sample = torch.from_numpy(sample.copy()).permute(0, 3, 1, 2)
+    return torch.nn.ZeroPad2d([0, 0, pad_tb, pad_tb])(sample).float()
+
+
+def crop_denormalize_u8(batch, h_start, w_start, h_in, w_in):
+    """scripts/evaluate_interpolation_results.py:143-163 (get_crop, convert_tensor_to_numpy_image) and
+    :192-202 (denormalize).  batch: B x 3 x H x W fp32 -> B x h_in x w_in x 3 uint8 (RGB)."""
+    import numpy as np
+    batch = batch.permute(0, 2, 3, 1)
+    batch = batch[:, h_start:h_start + h_in, w_start:w_start + w_in, ...]
+    pix_mean = torch.tensor(PIXEL_MEAN).view(1, 1, 1, -1).to(batch.device)
+    pix_std = torch.tensor(PIXEL_STD).view(1, 1, 1, -1).to(batch.device)
+    batch = batch * pix_std + pix_mean
+    batch = batch * 255.0
+    return batch.cpu().data.numpy().astype(np.uint8)

@@ -22,6 +22,7 @@ EXPORTS = (
     "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
     "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd",
     "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd", "ssm_fuse_loss_workspace_bytes",
+    "ssm_frames_from_u8", "ssm_frames_to_u8",
     "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
     "ssm_packed_frames_bytes", "ssm_pack_frames",
     "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
@@ -64,6 +65,9 @@ def lib():
     L.ssm_fuse_flow_bwd.argtypes = L.ssm_fuse_bwd.argtypes
     L.ssm_fuse_loss_fwd.argtypes = [P, V, P, P, P, V, P, V, I, I, I, I, I, I, I, I, V, Z, V]
     L.ssm_fuse_loss_bwd.argtypes = [P, V, P, V, P, P, P, P, V, P, P, I, I, I, I, I, I, I, I, V]
+    F3, LL = ctypes.POINTER(ctypes.c_float), ctypes.c_longlong
+    L.ssm_frames_from_u8.argtypes = [V, LL, I, I, I, I, I, I, I, I, I, V, F3, P, V, I, V]
+    L.ssm_frames_to_u8.argtypes = [P, I, I, I, I, I, I, I, F3, F3, ctypes.c_float, I, I, V, LL, I, I, V]
     for n in ("ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
               "ssm_packed_frames_bytes", "ssm_synthesize_host_scratch_bytes", "ssm_fuse_loss_workspace_bytes"):
         getattr(L, n).argtypes = [I, I, I, I]
@@ -71,7 +75,7 @@ def lib():
     L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I, V, Z]
     for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
               "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
-              "ssm_synthesize_host"):
+              "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host"):
         getattr(L, n).restype = I
     _lib = L
     return L

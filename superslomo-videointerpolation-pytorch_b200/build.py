@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssm_b200.so")
 SOURCES = ["ssm_abi.cu"]
-HEADERS = ["ssm_device.cuh", "ssm_kernels.cuh", "ssm_scatter.cuh"]
+HEADERS = ["ssm_device.cuh", "ssm_kernels.cuh", "ssm_scatter.cuh", "ssm_frames.cuh"]
 
 
 def _nvcc():

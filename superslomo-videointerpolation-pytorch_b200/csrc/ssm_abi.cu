@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "ssm_frames.cuh"
 #include "ssm_scatter.cuh"
 
 namespace {
@@ -546,6 +547,60 @@ int ssm_fuse_loss_bwd(const ssm_tensor* grad3, const float* grad_sums, const ssm
     return dispatch3(dtype, coord_mode, packed != nullptr,
                      FuseLossBwd{grad3, grad_sums, img6, packed, flow4, out5, target, out3, t, grad_out5, grad_flow4,
                                  B, N, H, W, stage1_loss != 0, stage2_loss != 0, (cudaStream_t)stream});
+}
+
+int ssm_frames_from_u8(const unsigned char* src, long long src_frame_stride, int src_row_stride, int bgr,
+                       int F, int H_in, int W_in, int H, int W, int top, int left,
+                       const float* lut_device, const float* pad_value3, const ssm_tensor* planar, void* rgbx,
+                       int dtype, void* stream) {
+    if (F <= 0 || H_in <= 0 || W_in <= 0 || H <= 0 || W <= 0)
+        return fail(SSM_ERR_SHAPE, "ssm_frames_from_u8: F, H_in, W_in, H, W must be positive");
+    if (top < 0 || left < 0 || top + H_in > H || left + W_in > W)
+        return fail(SSM_ERR_SHAPE, "ssm_frames_from_u8: the %d x %d source at (%d, %d) does not fit %d x %d", H_in, W_in, top, left, H, W);
+    if (W % 4 != 0) return fail(SSM_ERR_SHAPE, "ssm_frames_from_u8: padded width must be a multiple of 4 (got %d)", W);
+    if ((long long)H * W > MAX_PLANE) return fail(SSM_ERR_SHAPE, "H*W too large (%d x %d)", H, W);
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
+    if (!src || !lut_device || !pad_value3) return fail(SSM_ERR_NULL, "ssm_frames_from_u8: src, lut_device or pad_value3 is NULL");
+    const bool want_planar = planar && planar->data;
+    if (!want_planar && !rgbx) return fail(SSM_ERR_NULL, "ssm_frames_from_u8: neither planar nor rgbx requested");
+    SSM_TRY(check_tensor(planar, "planar", dtype, false));
+    if (want_planar && ((uintptr_t)planar->data % 16 != 0 || planar->stride_b % 4 != 0 || planar->stride_c % 4 != 0) && dtype == SSM_DTYPE_F32)
+        return fail(SSM_ERR_ALIGN, "ssm_frames_from_u8: planar must be 16-byte aligned with strides multiple of 4");
+    SSM_TRY(check_packed(rgbx));
+    const long long quads = (long long)F * H * (W / 4);
+    const unsigned grid = (unsigned)((quads + 255) / 256 < 148ll * 32 ? (quads + 255) / 256 : 148ll * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        frames_from_u8_kernel<float><<<grid, 256, 0, s>>>(src, src_frame_stride, src_row_stride, bgr != 0, H_in, W_in, H, W, top, left,
+            lut_device, pad_value3[0], pad_value3[1], pad_value3[2], mview<float>(planar), (float*)rgbx, quads);
+    else
+        frames_from_u8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, src_frame_stride, src_row_stride, bgr != 0, H_in, W_in, H, W, top, left,
+            lut_device, pad_value3[0], pad_value3[1], pad_value3[2], mview<__nv_bfloat16>(planar), (__nv_bfloat16*)rgbx, quads);
+    SSM_LAUNCH_CHECK("ssm_frames_from_u8");
+    return SSM_OK;
+}
+
+int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int left, int H_out, int W_out,
+                     const float* mean3, const float* std3, float scale, int bgr, int saturate,
+                     unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int dtype, void* stream) {
+    if (F <= 0 || H <= 0 || W <= 0 || H_out <= 0 || W_out <= 0)
+        return fail(SSM_ERR_SHAPE, "ssm_frames_to_u8: F, H, W, H_out, W_out must be positive");
+    if (top < 0 || left < 0 || top + H_out > H || left + W_out > W)
+        return fail(SSM_ERR_SHAPE, "ssm_frames_to_u8: the %d x %d crop at (%d, %d) leaves %d x %d", H_out, W_out, top, left, H, W);
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
+    if (!dst || !mean3 || !std3) return fail(SSM_ERR_NULL, "ssm_frames_to_u8: dst, mean3 or std3 is NULL");
+    SSM_TRY(check_tensor(planar, "planar", dtype, true));
+    const long long total = (long long)F * H_out * W_out;
+    const unsigned grid = (unsigned)((total + 255) / 256 < 148ll * 32 ? (total + 255) / 256 : 148ll * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        frames_to_u8_kernel<float><<<grid, 256, 0, s>>>(cview<float>(planar), H, W, top, left, H_out, W_out, mean3[0], mean3[1], mean3[2],
+            std3[0], std3[1], std3[2], scale, bgr != 0, saturate != 0, dst, dst_frame_stride, dst_row_stride, total);
+    else
+        frames_to_u8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(cview<__nv_bfloat16>(planar), H, W, top, left, H_out, W_out, mean3[0], mean3[1], mean3[2],
+            std3[0], std3[1], std3[2], scale, bgr != 0, saturate != 0, dst, dst_frame_stride, dst_row_stride, total);
+    SSM_LAUNCH_CHECK("ssm_frames_to_u8");
+    return SSM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -96,3 +96,30 @@ def test_sharding_world_size_2_gloo(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29511", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_frame_oracle_restatement_shapes_and_padding():
+    """load_batch pads with byte 0 BEFORE normalising (visualize_interpolation.py:87,137): the border is
+    (0 - mean) / std, not 0; the reader pads with zeros AFTER normalising (default_reader.py:266-271)."""
+    import numpy as np
+    from oracle import torch_oracle
+    img = np.full((2, 100, 52, 3), 255, dtype=np.uint8)
+    out = torch_oracle.load_batch_and_normalize(img)
+    assert out.shape == (1, 2, 3, 128, 64)
+    assert torch.allclose(out[0, 0, :, 0, 0], (0 - torch.tensor(torch_oracle.PIXEL_MEAN)) / torch.tensor(torch_oracle.PIXEL_STD))
+    assert torch.allclose(out[0, 0, :, 14, 6], (1 - torch.tensor(torch_oracle.PIXEL_MEAN)) / torch.tensor(torch_oracle.PIXEL_STD))
+    rd = torch_oracle.reader_normalize_and_pad(img, 8)
+    assert rd.shape == (2, 3, 116, 52) and rd[:, :, :8].abs().max() == 0
+    back = torch_oracle.crop_denormalize_u8(out[0], 14, 6, 100, 52)
+    assert back.shape == (2, 100, 52, 3) and back.min() >= 254
+
+
+def test_frames_host_helpers():
+    import ssm_b200
+    assert ssm_b200.frames.center_padding(720, 1280) == (736, 1280, 8, 0)
+    assert ssm_b200.frames.center_padding(1080, 1920) == (1088, 1920, 4, 0)
+    assert ssm_b200.frames.center_padding(100, 52) == (128, 64, 14, 6)
+    lut = ssm_b200.normalisation_lut(device="cpu")
+    assert lut.shape == (3, 256) and abs(lut[0, 255].item() - (1 - 0.485) / 0.229) < 1e-6
+    with pytest.raises(RuntimeError):
+        ssm_b200.frames_from_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))     # CPU tensor: refused

@@ -66,7 +66,9 @@ class FullModel(nn.Module, SynthesisMixin):
     def _stage1(self, image_pairs):
         """-> flows B x W x 4 x H x W, encodings list (or None)."""
         outs = self.stage1_model(image_pairs)
-        flows = torch.stack([o[1] for o in outs], dim=1)
+        # the synthesis path runs in the frames' dtype (fp32 unless the caller stores frames in bf16): under
+        # autocast the U-Nets return bf16, which would silently cost the coordinates 16 bits
+        flows = torch.stack([o[1] for o in outs], dim=1).to(image_pairs.dtype)
         encs = [o[0] for o in outs]
         return flows, encs
 
@@ -86,7 +88,7 @@ class FullModel(nn.Module, SynthesisMixin):
         # compute_inputs for every window in one launch (windows folded into the pair axis)
         in16 = F_ssm.flow_pack(flat(pairs), flat(flows), t_bw.reshape(-1), n_timesteps=1)   # (B*W) x 1 x 16
         in16 = in16.view(B, Wn, 16, *in16.shape[-2:])
-        out5 = torch.stack(self.stage2_model(in16, encs), dim=1)      # B x W x 5 x H x W
+        out5 = torch.stack(self.stage2_model(in16, encs), dim=1).to(pairs.dtype)      # B x W x 5 x H x W
         if inference_mode:
             sel = slice(mid, mid + 1)
             frame = F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5[:, sel], t_bw[:, mid])[:, 0]
@@ -140,6 +142,6 @@ class FullModel(nn.Module, SynthesisMixin):
             e = None
             if encs[0] is not None:
                 e = [enc.repeat_interleave(n, dim=0) for enc in encs]
-            out5 = self.stage2_model(x, e)[mid].view(B, n, 5, *in16.shape[-2:])
+            out5 = self.stage2_model(x, e)[mid].to(pairs.dtype).view(B, n, 5, *in16.shape[-2:])
             frames.append(F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5, tn, packed=rgbx[mid]))
         return torch.cat(frames, dim=1)

@@ -57,6 +57,16 @@ class FlowUNet(nn.Module):
         self.fuse_conv = conv(64, 32, kernel_size=3)
         self.final_conv = nn.Conv2d(32, out_channels, kernel_size=3, stride=1, padding=1, bias=True)
 
+    channels_last = False     # set_channels_last(): NHWC activations/weights for cuDNN's tensor-core kernels
+
+    def set_channels_last(self, on=True):
+        """SURVEY.md section 8(f) rank 2 (plumbing around the path): run the convolutions in channels-last
+        memory format.  The 16-channel input written by compute_inputs is converted once at conv1a; the
+        4/5-channel output is converted back to the planar layout the synthesis kernels read."""
+        self.channels_last = bool(on)
+        self.to(memory_format=torch.channels_last if on else torch.contiguous_format)
+        return self
+
     def _encode(self, x):
         skips = []
         for level in range(1, 6):
@@ -81,9 +91,15 @@ class FlowUNet(nn.Module):
     def forward_flat(self, x, enc_stage1=None):
         """x: M x C x H x W (windows/timesteps already folded into M) -> (bottleneck M x 512 x H/32 x W/32,
         output M x C_out x H x W)."""
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+            if enc_stage1 is not None:
+                enc_stage1 = enc_stage1.contiguous(memory_format=torch.channels_last)
         skips, pooled = self._encode(x)
         h = self.conv6(pooled)
-        return h, self._decode(h, skips, enc_stage1)
+        out = self._decode(h, skips, enc_stage1)
+        # the synthesis kernels read planar NCHW: hand the (4- or 5-channel) result back in that layout
+        return h, (out.contiguous() if self.channels_last else out)
 
     def forward(self, unet_in, stage1_encoder_output=None):
         B, T = unet_in.shape[0], unet_in.shape[1]

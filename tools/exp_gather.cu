@@ -202,6 +202,49 @@ __global__ void __launch_bounds__(256) k_nogather(const float* __restrict__ fl, 
     out[(long long)b * NPX + (long long)y * W + x] = acc;
 }
 
+// K1-like / K2-like kernels: the gathers of both frames per timestep PLUS the streaming traffic of
+// the real kernels (K2: 5 loads + 3 stores per timestep with a +-0.5 px white-noise residual on the
+// sample position; K1: 16 stores per timestep), with TEXW of the 8 warps of a CTA gathering through
+// the texture unit (tex2Dgather on R32F) and the others through the LSU (RGBx LDG.128).
+template <int TEXW, int NSTORE, bool JITTER>
+__global__ void __launch_bounds__(256, 4) k_like(cudaTextureObject_t tex, const float4* __restrict__ img, const float* __restrict__ fl,
+                                                 const float* __restrict__ y5, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    const bool use_tex = (threadIdx.x >> 5) < TEXW;
+    const long long p = (long long)y * W + x;
+    for (int n = 0; n < N; ++n) {
+        float jx0 = 0, jy0 = 0, jx1 = 0, jy1 = 0, lg = 0;
+        if (JITTER) {
+            const float* Y = y5 + ((long long)(b * N + n) * 5) * NPX + p;
+            lg = __ldcs(Y); jx1 = __ldcs(Y + NPX); jy1 = __ldcs(Y + 2 * NPX); jx0 = __ldcs(Y + 3 * NPX); jy0 = __ldcs(Y + 4 * NPX);
+        }
+        float acc[3] = {lg, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            Smp s = sample_pos(fl, b, x, y, n, f);
+            if (JITTER) {
+                float ix = fminf(fmaxf(s.x0 + s.wx + (f ? jx1 : jx0), 0.f), W - 1.001f), iy = fminf(fmaxf(s.y0 + s.wy + (f ? jy1 : jy0), 0.f), H - 1.001f);
+                s.x0 = (int)ix; s.y0 = (int)iy; s.wx = ix - s.x0; s.wy = iy - s.y0;
+            }
+            if (use_tex) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int l = b * 6 + f * 3 + c;
+                    float4 g = tex2Dgather<float4>(tex, (l & 3) * W + s.x0 + 1.0f, (l >> 2) * H + s.y0 + 1.0f, 0);
+                    acc[c] += lerp4(g.w, g.z, g.x, g.y, s.wx, s.wy);
+                }
+            } else {
+                const float4* q = img + ((long long)b * 2 + f) * NPX + (long long)s.y0 * W + s.x0;
+                float4 a = __ldg(q), bb = __ldg(q + 1), c = __ldg(q + W), d = __ldg(q + W + 1);
+                acc[0] += lerp4(a.x, bb.x, c.x, d.x, s.wx, s.wy); acc[1] += lerp4(a.y, bb.y, c.y, d.y, s.wx, s.wy); acc[2] += lerp4(a.z, bb.z, c.z, d.z, s.wx, s.wy);
+            }
+        }
+        float* O = out + ((long long)(b * N + n) * NSTORE) * NPX + p;
+#pragma unroll
+        for (int k = 0; k < NSTORE; ++k) __stcs(O + (long long)k * NPX, acc[k % 3] + k);
+    }
+}
+
 template <typename F> float time_ms(F&& launch, int reps = 10) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     for (int i = 0; i < 3; ++i) launch();
@@ -251,6 +294,11 @@ int main() {
     printf("{\"upload_r32f_layers_ms\": %.3f, \"upload_rgba32f_layers_ms\": %.3f}\n", up1, up4);
 
     const int grid = B * (W / 32) * (H / 8);
+    float *y5, *big;
+    CK(cudaMalloc(&y5, (size_t)B * N * 5 * NPX * 4)); CK(cudaMalloc(&big, (size_t)B * N * 16 * NPX * 4));
+    make_flow<<<(int)(((long long)B * 4 * NPX + T - 1) / T), T>>>(y5, 1, 0.5f, 777u);      // white noise, sigma 0.5 px (first 4/35 of y5 ...)
+    for (int r = 0; r < 9; ++r) make_flow<<<(int)(((long long)B * 4 * NPX + T - 1) / T), T>>>(y5 + (size_t)r * B * 4 * NPX * 7 / 8, 1, 0.5f, 778u + r);
+    CK(cudaDeviceSynchronize());
     const double samples = (double)B * NPX * N * 2;
     const int grids[2] = {8, 64};
     for (int gi = 0; gi < 2; ++gi) {
@@ -272,6 +320,10 @@ int main() {
         run("texpoint_b84", [&] { k_texpoint<1><<<grid, 256>>>(tex4, flow, out); });
         run("mixed", [&] { k_texgather<0, true><<<grid, 256>>>(tex1, p16, flow, out); });
         run("mixed_b84", [&] { k_texgather<1, true><<<grid, 256>>>(tex1, p16, flow, out); });
+#define LIKE(TW) \
+        run("k2like_texw" #TW, [&] { k_like<TW, 3, true><<<grid, 256>>>(tex1, p16, flow, y5, big); }); \
+        run("k1like_texw" #TW, [&] { k_like<TW, 16, false><<<grid, 256>>>(tex1, p16, flow, y5, big); });
+        LIKE(0) LIKE(2) LIKE(3) LIKE(4) LIKE(5) LIKE(6) LIKE(8)
         for (auto& r : rs)
             printf("{\"flow_grid\": \"1/%d\", \"variant\": \"%s\", \"ms\": %.3f, \"ns_per_warp_sample\": %.2f, \"cyc_per_warp_sample_per_sm\": %.1f, \"checksum\": %.6f}\n",
                    grids[gi], r.name, r.ms, r.ms * 1e6 / (samples / 32), r.ms * 1e-3 * 1.9e9 * 148 / (samples / 32), r.sum);

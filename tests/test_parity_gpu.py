@@ -385,6 +385,67 @@ def test_full_size_properties():
         assert_close_fp32(frames[b:b + 1, n], r3, "full-size fuse (%d,%d)" % (b, n))
 
 
+def test_c5_4k_31_timesteps_properties():
+    """BASELINE.json configs[4]: one 2176x3840 pair, 31 intermediate times (k/32): the (pair, timestep)
+    shards of 8 ranks (4/4/4/4/4/4/4/3) reproduce the single-launch result bit for bit, the recomputed-flow
+    kernel equals the two-step path, and one timestep is checked against the C oracle."""
+    from ssm_b200 import sharding
+    B, N, H, W = 1, 31, 2176, 3840
+    img6 = synthetic.frames(B, H, W, seed=42, device=DEV)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=43, device=DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=44, device=DEV)
+    t = synthetic.timesteps(B, N, device=DEV)
+    assert abs(t[0, 0].item() - 1 / 32) < 1e-7 and abs(t[0, 30].item() - 31 / 32) < 1e-7
+    in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=N)
+    frames = ssm_b200.fuse_from_flow(img6, flow4, out5, t)
+    assert torch.isfinite(frames).all()
+    assert torch.equal(ssm_b200.fuse(img6, in16, out5, t), frames)
+    counts = []
+    for rank in range(8):
+        (p, t0, t1), = sharding.shard_work(1, N, rank, 8)
+        counts.append(t1 - t0)
+        part = ssm_b200.fuse_from_flow(img6, flow4, out5[:, t0:t1].contiguous(), t[:, t0:t1].contiguous())
+        assert torch.equal(part, frames[:, t0:t1]), "rank %d shard differs" % rank
+    assert counts == [4, 4, 4, 4, 4, 4, 4, 3]
+    n = 17
+    i6, f4, tn = img6.cpu(), flow4.cpu(), t[:, n].cpu()
+    r16 = c_oracle.compute_inputs(i6, f4, tn)
+    assert_close_fp32(in16[:, n], r16, "4K flow_pack n=17")
+    assert_close_fp32(frames[:, n], c_oracle.compute_output_image(i6, r16, out5[:, n].cpu().contiguous(), tn), "4K fuse n=17")
+
+
+def test_c3_training_backward_is_linear_in_the_upstream_gradient():
+    """BASELINE.json configs[2] shape (64 crops of 352x352, per-sample random t): the backward of the
+    path is a linear map of the upstream gradient -- bwd(2 g1 - 3 g2) = 2 bwd(g1) - 3 bwd(g2) -- which
+    checks every gradient kernel at full batch size without an oracle run; one sample is also checked
+    against the C oracle."""
+    B, N, H, W = 64, 1, 352, 352
+    img6 = synthetic.frames(B, H, W, seed=42, device=DEV)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=8.0, seed=43, device=DEV).requires_grad_(True)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=44, device=DEV).requires_grad_(True)
+    t = synthetic.random_timesteps(B, 1, seed=45).to(DEV)
+    in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=1)
+    frames = ssm_b200.fuse_from_flow(img6, flow4, out5, t)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    g1, g2 = torch.randn(frames.shape, device=DEV, generator=gen), torch.randn(frames.shape, device=DEV, generator=gen)
+    h1, h2 = torch.randn(in16.shape, device=DEV, generator=gen), torch.randn(in16.shape, device=DEV, generator=gen)
+
+    def bwd(g, h):
+        return torch.autograd.grad([frames, in16], [flow4, out5], [g, h], retain_graph=True)
+
+    a, b, c = bwd(g1, h1), bwd(g2, h2), bwd(2 * g1 - 3 * g2, 2 * h1 - 3 * h2)
+    for x, y, z, what in ((a[0], b[0], c[0], "flow"), (a[1], b[1], c[1], "out5")):
+        want = 2 * x - 3 * y
+        assert max_err(z, want) <= 1e-5 * max(1.0, want.abs().max().item()), "backward not linear in grad (%s)" % what
+    s = 37
+    i6, f4, y5, ts = img6[s:s + 1].cpu(), flow4[s:s + 1].detach().cpu(), out5[s:s + 1, 0].detach().cpu(), t[s:s + 1, 0].cpu()
+    r16 = c_oracle.compute_inputs(i6, f4, ts)
+    _, gx, gy = c_oracle.compute_output_image_backward(g1[s:s + 1, 0].cpu(), i6, r16, y5, ts, need_img=False)
+    _, gf = c_oracle.compute_inputs_backward(gx + h1[s:s + 1, 0].cpu(), i6, f4, ts, need_img=False)
+    assert_close_fp32(a[1][s:s + 1, 0], gy, "C3 grad out5, sample 37")
+    assert_close_fp32(a[0][s:s + 1], gf, "C3 grad flow, sample 37", tol=2e-5)
+
+
 def test_host_entry_point_matches_device_path():
     """ssm_synthesize_host (host buffers, copies inside) == device path."""
     B, N, H, W = 4, 3, 64, 96

@@ -7,7 +7,7 @@ from .functional import (flow_pack, fuse, fuse_from_flow, fuse_loss, get_coord_m
                          synthesize_host_scratch_bytes)
 from .layers import avg_pool, conv, warp
 from .flow_interpolation import SynthesisMixin, patch_reference
-from . import frames, losses, sharding, superslomo_r, synthetic, unets
+from . import formats, frames, losses, sharding, superslomo_r, synthetic, unets
 from .frames import frames_from_u8, frames_to_u8, normalisation_lut
 from .superslomo_r import FullModel
 

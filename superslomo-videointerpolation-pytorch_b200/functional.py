@@ -384,6 +384,7 @@ class _FuseLoss(torch.autograd.Function):
         _abi.check(rc, "ssm_fuse_loss_fwd")
         ctx.save_for_backward(img6, flow4, out5, target, tvec, packed, out)
         ctx.mode, ctx.s1, ctx.s2 = mode, int(stage1_loss), int(stage2_loss)
+        ctx.set_materialize_grads(False)      # an unused output arrives as None, not as a dense zero tensor
         return out, sums
 
     @staticmethod
@@ -395,7 +396,7 @@ class _FuseLoss(torch.autograd.Function):
             raise RuntimeError("fuse_loss treats frames and targets as data (no image gradients): use "
                                "fuse_from_flow + warp for a graph that differentiates the images")
         need_f, need_y = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        if not (need_f or need_y):
+        if not (need_f or need_y) or (g3 is None and gsums is None):
             return (None,) * 9
         g3 = _abi.dense_planes(g3.to(img6.dtype)) if g3 is not None else None
         gsums = (gsums if gsums is not None else torch.zeros((B, 2 * N + 1), device=img6.device)).float().contiguous()

@@ -123,3 +123,56 @@ def test_frames_host_helpers():
     assert lut.shape == (3, 256) and abs(lut[0, 255].item() - (1 - 0.485) / 0.229) < 1e-6
     with pytest.raises(RuntimeError):
         ssm_b200.frames_from_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))     # CPU tensor: refused
+
+
+def test_sliding_window_matches_reference_rule():
+    """visualize_interpolation.py:270-288: windows of n_frames indices centred on each adjacent pair,
+    clamped at the ends; the 240-fps mode keeps every 8th image."""
+    from ssm_b200 import formats
+
+    def reference_rule(n_images, n_frames, fps240):
+        paths = list(range(n_images))[::8] if fps240 else list(range(n_images))
+        out = []
+        for s, e in zip(range(len(paths))[:-1], range(len(paths))[1:]):
+            left, right = s - ((n_frames - 1) // 2), e + ((n_frames - 1) // 2)
+            locs = [min(max(i, 0), len(paths) - 1) for i in range(left, right + 1)]
+            out.append([paths[i] for i in locs])
+        return out
+
+    for n_images, n_frames, fps in [(5, 2, False), (5, 4, False), (3, 6, False), (20, 4, True), (2, 2, False), (1, 2, False)]:
+        assert list(formats.sliding_window(n_images, n_frames, 8 if fps else 1)) == reference_rule(n_images, n_frames, fps)
+    assert list(formats.sliding_window(4, 4)) == [[0, 0, 1, 2], [0, 1, 2, 3], [1, 2, 3, 3]]
+    assert formats.output_name("d", 7) == "d/img_00007.png"
+
+
+def test_flo_round_trip_and_header(tmp_path):
+    """Middlebury .flo as scripts/utils/flo_utils.py:39-84 writes it: float 202021.25, int32 w, int32 h, data."""
+    import numpy as np
+    from ssm_b200 import formats
+    flow = torch.randn(2, 5, 7)
+    p = str(tmp_path / "a.flo")
+    formats.write_flo(p, flow)
+    raw = open(p, "rb").read()
+    assert len(raw) == 12 + 5 * 7 * 2 * 4
+    assert np.frombuffer(raw[:4], "<f4")[0] == np.float32(202021.25) and raw[:4] == b"PIEH"
+    assert tuple(np.frombuffer(raw[4:12], "<i4")) == (7, 5)
+    back = formats.read_flo(p)
+    assert back.shape == (5, 7, 2) and np.array_equal(back, flow.permute(1, 2, 0).numpy())
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """reference layout: stage1_state_dict / stage2_state_dict in one file (main.py:231-237)."""
+    from ssm_b200 import formats, unets
+
+    class M:
+        pass
+    a, b = M(), M()
+    for m, seed in ((a, 1), (b, 2)):
+        torch.manual_seed(seed)
+        m.stage1_model, m.stage2_model = unets.FlowUNet(6, 4, 1, True), unets.FlowUNet(16, 5, 2, True)
+    p = str(tmp_path / "ckpt.pt")
+    formats.save_checkpoint(a, p, iteration=12)
+    assert set(torch.load(p)) >= {"stage1_state_dict", "stage2_state_dict"}
+    assert formats.load_checkpoint(b, p) == 12
+    for x, y in zip(a.stage2_model.parameters(), b.stage2_model.parameters()):
+        assert torch.equal(x, y)

@@ -140,8 +140,11 @@ warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, 
 //     batched over N timesteps (absorbs the loop + torch.stack of superslomo_r.py:167-179 and the
 //     three torch.cat of :364-367): reads 10 channels once, writes 16 channels per timestep.
 // =============================================================================================
+#ifndef SSM_PACK_MIN_BLOCKS
+#define SSM_PACK_MIN_BLOCKS 4
+#endif
 template <typename T, int MODE, bool PACKED>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, SSM_PACK_MIN_BLOCKS)
 flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flow4,
                      const float* __restrict__ tv, View<T> out16, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);

@@ -19,8 +19,14 @@
 
 namespace ssm {
 
-constexpr int TILE_W = 32;
-constexpr int TILE_H = 8;
+#ifndef SSM_TILE_W
+#define SSM_TILE_W 32
+#endif
+#ifndef SSM_TILE_H
+#define SSM_TILE_H 8
+#endif
+constexpr int TILE_W = SSM_TILE_W;   // a multiple of 32: a warp is always 32 consecutive pixels of a row
+constexpr int TILE_H = SSM_TILE_H;
 constexpr int TILE_THREADS = TILE_W * TILE_H;
 
 struct TileIdx { int b, x, y; bool valid; };

@@ -302,6 +302,50 @@ def test_against_reference_ops_on_cuda():
         assert_close_fp32(new_cuda[k], aten[k], "mode=cuda vs reference ATen-CUDA: " + k)
 
 
+def test_speed_against_reference_ops_on_cuda():
+    """Same box, same device: the reference's per-timestep torch-op path (what the reference runs on a
+    GPU: ~110 ATen launches per timestep, cuDNN grid sampler) vs the three launches of the batched path,
+    at BASELINE configs[0] size (1 pair 736x1280, 7 timesteps) and for 4 pairs of 1088x1920.  Context
+    only (SURVEY.md section 8(d) last row); asserts just that the new path is not slower."""
+    import time
+    print()
+    for B, H, W in ((1, 736, 1280), (4, 1088, 1920)):
+        N = 7
+        img6 = synthetic.frames(B, H, W, seed=42, device=DEV)
+        flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=43, device=DEV)
+        out5 = synthetic.unet_out5(B, N, H, W, seed=44, device=DEV)
+        t = synthetic.timesteps(B, N, device=DEV)
+
+        def ref():
+            outs = []
+            for n in range(N):
+                tn = t[:, n].view(B, 1, 1, 1)
+                in16 = torch_oracle.compute_inputs(img6, flow4, tn)
+                outs.append(torch_oracle.compute_output_image(img6, in16, out5[:, n], tn))
+            return outs
+
+        def new():
+            rgbx = ssm_b200.pack_frames(img6)
+            in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=N, packed=rgbx)
+            return in16, ssm_b200.fuse_from_flow(img6, flow4, out5, t, packed=rgbx)
+
+        times = {}
+        with torch.no_grad():
+            for name, fn in (("reference torch ops (cuDNN sampler)", ref), ("ssm_b200", new)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                times[name] = (time.perf_counter() - t0) / 10
+        r, n_ = times["reference torch ops (cuDNN sampler)"], times["ssm_b200"]
+        print("  %d pair(s) %dx%d x %d timesteps: reference ops on CUDA %.2f ms (%.0f frames/s), ssm_b200 %.2f ms "
+              "(%.0f frames/s): %.1fx" % (B, H, W, N, 1e3 * r, B * N / r, 1e3 * n_, B * N / n_, r / n_))
+        assert n_ < r
+
+
 # ---------------------------------------------------------------------------------------------
 def test_image_gradient_is_deterministic():
     """Bit-identical run to run (the reference's atomicAdd scatter is not)."""

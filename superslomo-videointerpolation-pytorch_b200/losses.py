@@ -61,7 +61,7 @@ class SSMLosses(nn.Module):
         total = rec + wl + per
         return torch.cat([total, rec, wl, per], dim=1)     # [B, 4]
 
-    def fused_forward(self, img_tensor, flowC_output, flowI_output, t, target_image):
+    def fused_forward(self, img_tensor, flowC_output, flowI_output, t, target_image, packed=None):
         """compute_output_image and this module's forward() in one fused pass (ssm_fuse_loss_fwd/bwd):
         img_tensor B x 6, flowC_output B x 4, flowI_output B x 5, t B values, target_image B x 3
         -> (interpolated_image B x 3, losses [B, 4]).  Same values as
@@ -69,7 +69,7 @@ class SSMLosses(nn.Module):
         without the two extra warps (losses.py:152-154) and ~30 elementwise launches per window."""
         lambda_r, lambda_p, lambda_w = self.loss_weights
         frames, sums = F_ssm.fuse_loss(img_tensor, flowC_output, flowI_output.unsqueeze(1), target_image.unsqueeze(1),
-                                       t, stage1_loss=not self.stage1_frozen, stage2_loss=not self.stage2_frozen)
+                                       t, stage1_loss=not self.stage1_frozen, stage2_loss=not self.stage2_frozen, packed=packed)
         frame = frames[:, 0]
         count = float(target_image[0].numel())
         rec = (lambda_r / count) * sums[:, 0:1]

@@ -60,6 +60,12 @@ def _workspace(nbytes, device):
 def _t_vector(t, count, device):
     """t as `count` contiguous fp32 values on `device` (t is never differentiated)."""
     t = torch.as_tensor(t).detach()
+    if not t.is_cuda and t.numel() > 0:
+        # the reference asserts 0 < t < 1 (scripts/utils/validators.py:9-11); a host-side t is checked
+        # here, a device-side t is not (that would force a synchronisation on every call)
+        lo, hi = float(t.min()), float(t.max())
+        if not (0.0 < lo and hi < 1.0):
+            raise AssertionError("t must satisfy 0 < t < 1 (got values in [%g, %g])" % (lo, hi))
     t = t.to(device=device, dtype=torch.float32).reshape(-1)
     if t.numel() == 1 and count > 1:
         t = t.expand(count)

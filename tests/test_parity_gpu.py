@@ -490,6 +490,50 @@ def test_c3_training_backward_is_linear_in_the_upstream_gradient():
     assert_close_fp32(a[0][s:s + 1], gf, "C3 grad flow, sample 37", tol=2e-5)
 
 
+def test_streams_threads_and_argument_errors():
+    """Boundary behaviour: calls enqueue on the caller's current stream and
+    never synchronise; concurrent Python threads (nn.DataParallel style) are safe; bad arguments raise."""
+    import threading
+    B, N, H, W = 2, 3, 64, 96
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=700)
+    a, f, y, td = _dev(img6), _dev(flow4), _dev(out5), _dev(t)
+    want = ssm_b200.fuse_from_flow(a, f, y, td)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        got = ssm_b200.fuse_from_flow(a, f, y, td)
+    side.synchronize()
+    assert torch.equal(got, want)
+    results = [None] * 4
+
+    def worker(i):
+        with torch.cuda.stream(torch.cuda.Stream()):
+            r = ssm_b200.fuse(a, ssm_b200.flow_pack(a, f, td, n_timesteps=N), y, td)
+            torch.cuda.current_stream().synchronize()
+            results[i] = r
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert all(torch.equal(r, want) for r in results)
+    with pytest.raises(RuntimeError):
+        ssm_b200.flow_pack(a, f[:, :3], td, n_timesteps=N)                  # wrong channel count
+    with pytest.raises(RuntimeError):
+        ssm_b200.fuse_from_flow(a, f, y[:, :, :4], td)
+    with pytest.raises(RuntimeError):
+        ssm_b200.flow_pack(a, f.to(torch.bfloat16), td, n_timesteps=N)      # mixed storage types
+    with pytest.raises(RuntimeError):
+        ssm_b200.flow_pack(a, f, td[:, :2], n_timesteps=N)                  # t count
+    with pytest.raises(AssertionError):
+        ssm_b200.SynthesisMixin().compute_inputs(a, f, torch.full((B, 1, 1, 1), 1.0))   # validators.py:9-11
+    # non-finite flows are sampled outside the image (zeros), finite everywhere else
+    f_bad = f.clone()
+    f_bad[0, :, 5, 7] = float("inf")
+    out = ssm_b200.flow_pack(a, f_bad, td, n_timesteps=N)
+    assert torch.isfinite(out[:, :, 3:6]).all() and torch.isfinite(out[:, :, 10:13]).all()
+
+
 def test_host_entry_point_matches_device_path():
     """ssm_synthesize_host (host buffers, copies inside) == device path."""
     B, N, H, W = 4, 3, 64, 96

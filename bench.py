@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the backward-kernel timings")
+    ap.add_argument("--no-variants", action="store_true", help="skip the smooth-flow and bf16-storage variants")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -203,11 +204,28 @@ def main():
     out5 = synthetic.unet_out5(B, NT, H, W, seed=seed0 + 2, device=dev)
     t = synthetic.timesteps(B, NT, device=dev)
 
-    def step(flow=None):
+    # caller-owned result buffers (out=): the steady-state loop makes no allocator calls, so no
+    # cudaMalloc (which synchronises and maps pages) can land inside the timed region
+    rgbx_buf = torch.empty((B, 2, H, W, 4), dtype=torch.float32, device=dev)
+    in16_buf = torch.empty((B, NT, 16, H, W), dtype=torch.float32, device=dev)
+    frames_buf = torch.empty((B, NT, 3, H, W), dtype=torch.float32, device=dev)
+
+    def step(flow=None, y=None, events=None):
+        """One pass of the hot path over the batch: RGBx staging copy + the two fused launches."""
+        f = flow4 if flow is None else flow
         with torch.no_grad():
-            rgbx = ssm_b200.pack_frames(img6)              # RGBx staging copy, shared by both kernels
-            in16 = ssm_b200.flow_pack(img6, flow4 if flow is None else flow, t, n_timesteps=NT, packed=rgbx)
-            return in16, ssm_b200.fuse_from_flow(img6, flow4 if flow is None else flow, out5, t, packed=rgbx)
+            if events:
+                events[0].record()
+            rgbx = ssm_b200.pack_frames(img6, out=rgbx_buf)      # RGBx staging copy, shared by both kernels
+            if events:
+                events[1].record()
+            in16 = ssm_b200.flow_pack(img6, f, t, n_timesteps=NT, packed=rgbx, out=in16_buf)
+            if events:
+                events[2].record()
+            frames = ssm_b200.fuse_from_flow(img6, f, out5 if y is None else y, t, packed=rgbx, out=frames_buf)
+            if events:
+                events[3].record()
+        return in16, frames
 
     def barrier():
         if world > 1:
@@ -226,15 +244,8 @@ def main():
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    with torch.no_grad():
-        for k in range(K):
-            ev[k][0].record()
-            rgbx = ssm_b200.pack_frames(img6)
-            ev[k][1].record()
-            in16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT, packed=rgbx)
-            ev[k][2].record()
-            frames = ssm_b200.fuse_from_flow(img6, flow4, out5, t, packed=rgbx)
-            ev[k][3].record()
+    for k in range(K):
+        step(events=ev[k])
     end.record()
     barrier()
     clocks = sampler.stop()
@@ -246,6 +257,7 @@ def main():
     rgbx_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
     pack_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
     fuse_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev)
+    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
     frames_per_step = B * NT * world
     value = frames_per_step * K / (elapsed_ms * 1e-3)
 
@@ -271,30 +283,57 @@ def main():
         "flow_pack_fwd": {"ms": pack_ms, "algorithmic_gbs": pack_gbs, "frac_of_peak": pack_gbs / peak},
         "fuse_fwd": {"ms": fuse_ms, "algorithmic_gbs": fuse_gbs, "frac_of_peak": fuse_gbs / peak},
         "path": {"ms": path_ms, "algorithmic_gbs": path_gbs, "frac_of_peak": path_gbs / peak},
+        "step_ms_distribution": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
     }
-    del in16, frames, rgbx
 
     # same kernels on a smooth flow field (control grid at 1/64 resolution): real optical flow is
     # piecewise smooth; the headline workload above uses SURVEY 8(d)'s much rougher 1/8-resolution field
-    smooth = None
-    if rank == 0:
-        flow_s = torch.nn.functional.interpolate(
-            torch.randn((B, 4, H // 64, W // 64), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) * 20.0,
-            size=(H, W), mode="bilinear", align_corners=False).contiguous()
-        for _ in range(3):
-            step(flow_s)
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
         es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         es[0].record()
-        for _ in range(10):
-            step(flow_s)
+        for _ in range(reps):
+            fn()
         es[1].record()
         torch.cuda.synchronize()
-        ms = es[0].elapsed_time(es[1]) / 10
-        smooth = {"ms_per_step": ms, "frames_per_s": B * NT / (ms * 1e-3),
-                  "path_algorithmic_gbs": (pack_bytes + fuse_bytes) / (ms * 1e-3) / 1e9,
-                  "path_frac_of_peak": (pack_bytes + fuse_bytes) / (ms * 1e-3) / 1e9 / peak}
-        del flow_s
+        return es[0].elapsed_time(es[1]) / reps
+
+    def variant(ms, nbytes):
+        return {"ms_per_step": ms, "frames_per_s": B * NT / (ms * 1e-3),
+                "path_algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "path_frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+
+    smooth = smooth_res = bf16 = None
+    if rank == 0 and not args.no_variants:
+        gen = torch.Generator(device=dev).manual_seed(7)
+
+        def lowres(ch, div, scale, lead=()):
+            c = torch.randn(lead + (B, ch, H // div, W // div), device=dev, generator=gen) * scale
+            return torch.nn.functional.interpolate(c.view(-1, ch, H // div, W // div), size=(H, W), mode="bilinear",
+                                                   align_corners=False).view(lead + (B, ch, H, W)).contiguous()
+        flow_s = lowres(4, 64, 20.0)
+        smooth = variant(timed(lambda: step(flow_s)), pack_bytes + fuse_bytes)
+        # ... and with a spatially smooth stage-2 output as well (a trained U-Net's residual flows and
+        # visibility logits are smooth; the surrogate of the headline workload is white noise)
+        y_s = torch.empty_like(out5)
+        for n in range(NT):
+            y_s[:, n] = lowres(5, 16, 1.0)
+        y_s[:, :, 0] *= 2.0
+        y_s[:, :, 1:] *= 0.5
+        smooth_res = variant(timed(lambda: step(flow_s, y_s)), pack_bytes + fuse_bytes)
+        del flow_s, y_s
+        # bf16 storage, fp32 arithmetic (north_star tolerance 2e-2): half the bytes per element
+        img_h, flow_h, out5_h = img6.bfloat16(), flow4.bfloat16(), out5.bfloat16()
+
+        def step_bf16():
+            with torch.no_grad():
+                r = ssm_b200.pack_frames(img_h)
+                a = ssm_b200.flow_pack(img_h, flow_h, t, n_timesteps=NT, packed=r)
+                return a, ssm_b200.fuse_from_flow(img_h, flow_h, out5_h, t, packed=r)
+        bf16 = variant(timed(step_bf16), (pack_bytes + fuse_bytes) // 2)
+        bf16["note"] = "bf16 storage of every tensor, fp32 arithmetic; not the headline (the reference is fp32)"
+        del img_h, flow_h, out5_h
 
     # ---- training backward of the same kernels (flow / U-Net-output gradients; frames are data) ----
     train = None
@@ -368,7 +407,8 @@ def main():
                        "frames_per_step": frames_per_step, "l2": "inputs_exceed_l2 (8.7 GB read, 18.9 GB written per step)",
                        "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
                        "parallelism": "pairs sharded over %d rank(s), no collective" % world},
-            "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth,
+            "smooth_flow_and_unet_output_variant": smooth_res, "bf16_storage_variant": bf16, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line))

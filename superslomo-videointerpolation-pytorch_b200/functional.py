@@ -57,6 +57,23 @@ def _workspace(nbytes, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
+def _out_buffer(out, shape, like, what):
+    """Caller-owned result buffer (`out=`): validated, or allocated when None.  A serving loop that
+    owns its buffers makes no allocator calls in steady state (the C ABI itself never allocates)."""
+    if out is None:
+        return torch.empty(shape, dtype=like.dtype, device=like.device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != like.dtype or out.device != like.device \
+            or not out.is_contiguous():
+        raise RuntimeError("%s: out= must be a contiguous %s %s tensor on %s (got %s %s on %s)"
+                           % (what, tuple(shape), like.dtype, like.device, tuple(out.shape), out.dtype, out.device))
+    return out
+
+
+def _no_grad_for_out(out, what, *inputs):
+    if out is not None and torch.is_grad_enabled() and any(x.requires_grad for x in inputs):
+        raise RuntimeError("%s: out= is for inference; it cannot be combined with inputs that require grad" % what)
+
+
 def _t_vector(t, count, device):
     """t as `count` contiguous fp32 values on `device` (t is never differentiated)."""
     t = torch.as_tensor(t).detach()
@@ -72,6 +89,13 @@ def _t_vector(t, count, device):
     if t.numel() != count:
         raise RuntimeError("ssm_b200: t has %d values, expected %d (one per pair and timestep)" % (t.numel(), count))
     return t.contiguous()
+
+
+class _NoCtx:
+    """stand-in for the autograd context when a forward is called directly with out= (inference)"""
+
+    def save_for_backward(self, *tensors):
+        pass
 
 
 # ---------------------------------------------------------------------------------------------
@@ -126,7 +150,7 @@ def warp(x, flo, coord_mode=None):
 
 
 # ---------------------------------------------------------------------------------------------
-def pack_frames(img6):
+def pack_frames(img6, out=None):
     """RGBx re-layout of a batch of frame pairs (ssm_pack_frames): B x 6 x H x W planar ->
     B x 2 x H x W x 4 pixel-interleaved, so each bilinear tap of the gathers is one memory request.
     Optional: flow_pack / fuse build it themselves when they are given N >= 2 timesteps; build it
@@ -136,7 +160,7 @@ def pack_frames(img6):
     B, C6, H, W = img6.shape
     if C6 != 6:
         raise RuntimeError("pack_frames: expected B x 6 x H x W, got %s" % (tuple(img6.shape),))
-    packed = torch.empty((B, 2, H, W, 4), dtype=img6.dtype, device=img6.device)
+    packed = _out_buffer(out, (B, 2, H, W, 4), img6, "pack_frames")
     with torch.cuda.device(img6.device):
         rc = _abi.lib().ssm_pack_frames(_abi.ref(_abi.desc(img6, False)), ctypes.c_void_p(packed.data_ptr()),
                                         B, H, W, _abi.dtype_code(img6), _abi.stream_ptr(img6.device))
@@ -162,7 +186,7 @@ class _FlowPack(torch.autograd.Function):
     """compute_inputs for N timesteps -- reference scripts/models/flow_interpolation.py:338-372"""
 
     @staticmethod
-    def forward(ctx, img6, flow4, tvec, N, mode, packed):
+    def forward(ctx, img6, flow4, tvec, N, mode, packed, out=None):
         _same(img6, flow4)
         img6, flow4 = _abi.dense_planes(img6), _abi.dense_planes(flow4)
         B, C6, H, W = img6.shape
@@ -171,7 +195,7 @@ class _FlowPack(torch.autograd.Function):
                                % (tuple(img6.shape), tuple(flow4.shape)))
         if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
             packed = pack_frames(img6)
-        out = torch.empty((B, N, 16, H, W), dtype=img6.dtype, device=img6.device)
+        out = _out_buffer(out, (B, N, 16, H, W), img6, "flow_pack")
         with torch.cuda.device(img6.device):
             rc = _abi.lib().ssm_flow_pack_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
                                               _abi.ref(_abi.desc(flow4, False)),
@@ -210,13 +234,18 @@ class _FlowPack(torch.autograd.Function):
         return gi, gf, None, None, None, None
 
 
-def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None, packed=None):
+def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None, packed=None, out=None):
     """Stage-2 input for n_timesteps intermediate times of every pair: B x N x 16 x H x W.
 
     t holds B*N values (t[b, n]); a single value is broadcast.  packed: optional result of
-    pack_frames(img6) to share the RGBx copy between flow_pack and fuse."""
+    pack_frames(img6) to share the RGBx copy between flow_pack and fuse.  out: optional caller-owned
+    result buffer (inference only)."""
     B = img6.shape[0]
     tvec = _t_vector(t, B * n_timesteps, img6.device)
+    if out is not None:
+        _no_grad_for_out(out, "flow_pack", img6, flow4)
+        with torch.no_grad():
+            return _FlowPack.forward(_NoCtx(), img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode), packed, out)
     return _FlowPack.apply(img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode), packed)
 
 
@@ -225,7 +254,7 @@ class _Fuse(torch.autograd.Function):
     """extract_outputs + compute_output_image for N timesteps -- flow_interpolation.py:374-429"""
 
     @staticmethod
-    def forward(ctx, img6, in16, out5, tvec, mode, packed):
+    def forward(ctx, img6, in16, out5, tvec, mode, packed, out=None):
         _same(img6, in16, out5)
         img6, in16, out5 = _abi.dense_planes(img6), _abi.dense_planes(in16), _abi.dense_planes(out5)
         B, C6, H, W = img6.shape
@@ -235,7 +264,7 @@ class _Fuse(torch.autograd.Function):
                                "(x H x W), got %s, %s, %s" % (tuple(img6.shape), tuple(in16.shape), tuple(out5.shape)))
         if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
             packed = pack_frames(img6)
-        out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
+        out = _out_buffer(out, (B, N, 3, H, W), img6, "fuse")
         flows4 = in16[:, :, 6:10]
         with torch.cuda.device(img6.device):
             rc = _abi.lib().ssm_fuse_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
@@ -283,10 +312,15 @@ class _Fuse(torch.autograd.Function):
         return gi, gx, gy, None, None, None
 
 
-def fuse(img6, in16, out5, t, coord_mode=None, packed=None):
-    """Fused frames for every (pair, timestep): img6 B x 6, in16 B x N x 16, out5 B x N x 5 -> B x N x 3."""
+def fuse(img6, in16, out5, t, coord_mode=None, packed=None, out=None):
+    """Fused frames for every (pair, timestep): img6 B x 6, in16 B x N x 16, out5 B x N x 5 -> B x N x 3.
+    out: optional caller-owned result buffer (inference only)."""
     B, N = in16.shape[0], in16.shape[1]
     tvec = _t_vector(t, B * N, img6.device)
+    if out is not None:
+        _no_grad_for_out(out, "fuse", img6, in16, out5)
+        with torch.no_grad():
+            return _Fuse.forward(_NoCtx(), img6, in16, out5, tvec, _resolve_mode(coord_mode), packed, out)
     return _Fuse.apply(img6, in16, out5, tvec, _resolve_mode(coord_mode), packed)
 
 
@@ -296,7 +330,7 @@ class _FuseFlow(torch.autograd.Function):
     (ssm_fuse_flow_fwd/bwd): same results as _Fuse on input_tensor = compute_inputs(img, flow, t)."""
 
     @staticmethod
-    def forward(ctx, img6, flow4, out5, tvec, mode, packed):
+    def forward(ctx, img6, flow4, out5, tvec, mode, packed, out=None):
         _same(img6, flow4, out5)
         img6, flow4, out5 = _abi.dense_planes(img6), _abi.dense_planes(flow4), _abi.dense_planes(out5)
         B, C6, H, W = img6.shape
@@ -307,7 +341,7 @@ class _FuseFlow(torch.autograd.Function):
         N = out5.shape[1]
         if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
             packed = pack_frames(img6)
-        out = torch.empty((B, N, 3, H, W), dtype=img6.dtype, device=img6.device)
+        out = _out_buffer(out, (B, N, 3, H, W), img6, "fuse_from_flow")
         with torch.cuda.device(img6.device):
             rc = _abi.lib().ssm_fuse_flow_fwd(_abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6),
                                               _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)),
@@ -347,12 +381,16 @@ class _FuseFlow(torch.autograd.Function):
         return gi, gf, gy, None, None, None
 
 
-def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None):
+def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None, out=None):
     """Fused frames for every (pair, timestep) from the stage-1 flows: img6 B x 6, flow4 B x 4,
     out5 B x N x 5 -> B x N x 3.  Equals fuse(img6, flow_pack(img6, flow4, t), out5, t) without reading
     the 16-channel tensor back; gradients go to flow4 directly."""
     B, N = out5.shape[0], out5.shape[1]
     tvec = _t_vector(t, B * N, img6.device)
+    if out is not None:
+        _no_grad_for_out(out, "fuse_from_flow", img6, flow4, out5)
+        with torch.no_grad():
+            return _FuseFlow.forward(_NoCtx(), img6, flow4, out5, tvec, _resolve_mode(coord_mode), packed, out)
     return _FuseFlow.apply(img6, flow4, out5, tvec, _resolve_mode(coord_mode), packed)
 
 

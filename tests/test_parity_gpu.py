@@ -534,6 +534,34 @@ def test_streams_threads_and_argument_errors():
     assert torch.isfinite(out[:, :, 3:6]).all() and torch.isfinite(out[:, :, 10:13]).all()
 
 
+def test_caller_owned_output_buffers():
+    """out= (caller-owned result buffers, inference): same bits as the allocating call, results land in
+    the given storage, and mismatched buffers / gradient-requiring inputs are rejected."""
+    B, N, H, W = 2, 3, 64, 96
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=1200)
+    a, f, y, td = _dev(img6), _dev(flow4), _dev(out5), _dev(t)
+    rgbx = torch.empty((B, 2, H, W, 4), device=DEV)
+    b16 = torch.full((B, N, 16, H, W), float("nan"), device=DEV)
+    b3 = torch.full((B, N, 3, H, W), float("nan"), device=DEV)
+    b3b = torch.full((B, N, 3, H, W), float("nan"), device=DEV)
+    r = ssm_b200.pack_frames(a, out=rgbx)
+    assert r.data_ptr() == rgbx.data_ptr() and torch.equal(rgbx, ssm_b200.pack_frames(a))
+    w16 = ssm_b200.flow_pack(a, f, td, n_timesteps=N, packed=rgbx, out=b16)
+    assert w16.data_ptr() == b16.data_ptr() and torch.equal(b16, ssm_b200.flow_pack(a, f, td, n_timesteps=N))
+    w3 = ssm_b200.fuse_from_flow(a, f, y, td, packed=rgbx, out=b3)
+    assert w3.data_ptr() == b3.data_ptr() and torch.equal(b3, ssm_b200.fuse_from_flow(a, f, y, td))
+    ssm_b200.fuse(a, b16, y, td, out=b3b)
+    assert torch.equal(b3b, b3)
+    with pytest.raises(RuntimeError):
+        ssm_b200.flow_pack(a, f, td, n_timesteps=N, out=b16[:, :2])                       # wrong shape
+    with pytest.raises(RuntimeError):
+        ssm_b200.fuse_from_flow(a, f, y, td, out=b3.bfloat16())                           # wrong dtype
+    with pytest.raises(RuntimeError):
+        ssm_b200.fuse_from_flow(a, _dev(flow4, True), y, td, out=b3)                      # needs autograd
+    with torch.no_grad():                                                                 # fine without it
+        ssm_b200.fuse_from_flow(a, _dev(flow4, True), y, td, out=b3)
+
+
 def test_host_entry_point_matches_device_path():
     """ssm_synthesize_host (host buffers, copies inside) == device path."""
     B, N, H, W = 4, 3, 64, 96

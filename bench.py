@@ -57,15 +57,53 @@ def _traffic():
 
 
 class ClockSampler:
+    """SM clock, power and clock-event (throttle) reasons of one GPU, polled DURING the timed region.
+    NVML in a background thread (first sample within a millisecond of start(), one every 10 ms: a 0.3 s
+    timed region still gets ~30 samples); `nvidia-smi -lms` as the fallback when pynvml is missing."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.01):
         self.gpu = gpu_index
-        self.proc = None
+        self.period = period_s
+        self.proc = self.thread = self.nvml = self.handle = None
+        self.rows = []          # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((sm, self.smax, power, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50",
@@ -74,29 +112,40 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
         sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
+        source = None
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            for a, b, c, mask in self.rows:
+                sm.append(a); smax.append(b); power.append(c)
+                reasons.update(k for k, v in bits.items() if mask & v)
+            source = "nvml"
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[4:8]):
-                if v == "Active":
-                    reasons.add(n)
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in out.splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                reasons.update(n for n, v in zip(self.NAMES, parts[4:8]) if v == "Active")
+            source = "nvidia-smi"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": source}
 
 
 # ---------------------------------------------------------------------------------------------

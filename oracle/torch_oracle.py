@@ -141,10 +141,11 @@ def interpolate_frames(stage1, stage2, image_tensor, n_intermediate):
     return torch.stack(out, dim=1)
 
 
-# ---- frame pre/post-processing.  Parity unpinned: the reference
-# holds these steps inside classes that need cv2 / a CUDA device / config files to instantiate
-# (Interpolator, Evaluator), so they are restated here from the cited lines and not checked against an
-# imported reference; each is a handful of torch / numpy calls.
+# ---- frame pre/post-processing.  Pinned: tests/golden/make_golden_frames.py
+# runs the reference's own methods unmodified on CPU (Interpolator.load_batch / normalize_tensor,
+# Evaluator.convert_tensor_to_numpy_image, the data loader's Normalize / ToTensor / EvalPad, called unbound
+# on a bare object so that the constructors, which build the model on a CUDA device, are not needed),
+# asserts that the restatements below are bit-equal and commits tests/golden/frames_prepost.npz.
 PIXEL_MEAN = (0.485, 0.456, 0.406)
 PIXEL_STD = (0.229, 0.224, 0.225)
 

@@ -84,3 +84,53 @@ def test_round_trip_u8():
     diff = (back.cpu().numpy().astype(np.int16) - bgr.astype(np.int16))
     # (v/255 - m)/s*s + m)*255 truncates: off by one below for the values whose round trip lands just under v
     assert diff.max() <= 0 and diff.min() >= -1
+
+
+# ---- against outputs of the reference itself (tests/golden/frames_prepost.npz, make_golden_frames.py) -------
+def _prepost():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_prepost.npz"))
+
+
+def test_from_u8_matches_reference_fixture():
+    """Interpolator.load_batch + normalize_tensor (run unmodified on CPU) on a ragged 45 x 70 clip."""
+    d = _prepost()
+    want = torch.from_numpy(d["vis_normalised"])[0]                      # T x 3 x 64 x 96
+    planar, rgbx, (top, left) = ssm_b200.frames_from_u8(torch.from_numpy(d["vis_bgr_u8"]).to(DEV), order="bgr",
+                                                        pad_mode="before", lut=ssm_b200.normalisation_lut(device="cpu"),
+                                                        want_rgbx=True)
+    assert (top, left) == (9, 13)
+    assert torch.equal(planar.cpu(), want)
+    assert torch.equal(rgbx[..., :3].permute(0, 3, 1, 2).cpu(), want)
+
+
+def test_from_u8_matches_reference_reader_fixture():
+    """augmentations.Normalize + ToTensor + EvalPad (run unmodified on CPU)."""
+    d = _prepost()
+    want = torch.from_numpy(d["reader_out"])
+    pad = int(d["reader_pad"][0])
+    rgb = torch.from_numpy(d["reader_rgb_u8"]).to(DEV)
+    # the reader pads rows only (ZeroPad2d([0, 0, pad, pad])): 40 + 2 * 12 = 64 rows, 64 columns
+    planar, _, (top, left) = ssm_b200.frames_from_u8(rgb, order="rgb", pad_mode="after",
+                                                     lut=ssm_b200.normalisation_lut(style="reader", device=DEV))
+    assert (top, left) == (pad, 0) and planar.shape == want.shape
+    assert torch.equal(planar.cpu(), want)
+
+
+def test_to_u8_matches_reference_fixture():
+    """Evaluator.convert_tensor_to_numpy_image (get_crop + denormalize + astype(uint8), run unmodified on
+    CPU): values that de-normalise into [0, 256) must be bit-exact; outside that range astype(uint8) of a
+    float is implementation-defined in numpy, the kernel wraps modulo 256 like x86 numpy does."""
+    d = _prepost()
+    h0, w0, h, w = [int(v) for v in d["eval_crop"]]
+    x = torch.from_numpy(d["eval_in"])
+    got = ssm_b200.frames_to_u8(x.to(DEV), top=h0, left=w0, h_out=h, w_out=w).cpu().numpy()
+    assert got.shape == d["eval_u8"].shape
+    assert np.array_equal(got, d["eval_u8"])
+    # visualiser flavour: denormalize_tensor then astype(uint8) on the full frame (visualize_interpolation.py:225-232, 264-268)
+    xin = torch.from_numpy(d["vis_denorm_in"])[0]
+    want = d["vis_denorm_out"][0].transpose(0, 2, 3, 1).astype(np.uint8)
+    got = ssm_b200.frames_to_u8(xin.to(DEV)).cpu().numpy()
+    v = d["vis_denorm_out"][0].transpose(0, 2, 3, 1)
+    inside = (v >= 0) & (v < 256)
+    assert np.array_equal(got[inside], want[inside])

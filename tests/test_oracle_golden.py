@@ -113,3 +113,24 @@ def test_loop_oracle_matches_reference_fullmodel(name):
     losses.mean(dim=0)[0].backward()
     assert_close_fp32(s1.final_conv.weight.grad, d["grad_stage1_final"], "stage-1 final_conv grad", tol=1e-5)
     assert_close_fp32(s2.final_conv.weight.grad, d["grad_stage2_final"], "stage-2 final_conv grad", tol=1e-5)
+
+
+# ---- pre/post frame steps: restatements pinned to the reference's own methods --------
+def _prepost():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_prepost.npz"))
+
+
+def test_prepost_oracle_matches_reference():
+    """tests/golden/make_golden_frames.py ran Interpolator.load_batch/normalize_tensor, Evaluator's
+    crop + denormalise + astype(uint8) and the data loader's Normalize/ToTensor/EvalPad unmodified on CPU;
+    the restatements in oracle/torch_oracle.py must reproduce them bit for bit."""
+    import numpy as np
+    d = _prepost()
+    got = torch_oracle.load_batch_and_normalize(d["vis_bgr_u8"])
+    assert torch.equal(got, torch.from_numpy(d["vis_normalised"]))
+    h0, w0, h, w = [int(v) for v in d["eval_crop"]]
+    assert np.array_equal(torch_oracle.crop_denormalize_u8(torch.from_numpy(d["eval_in"]), h0, w0, h, w), d["eval_u8"])
+    got = torch_oracle.reader_normalize_and_pad(d["reader_rgb_u8"], int(d["reader_pad"][0]))
+    assert torch.equal(got, torch.from_numpy(d["reader_out"]))

@@ -18,7 +18,7 @@ BF16_RTOL = 2.0 ** -7
 def golden_cases():
     """hot-path fixtures (warp / compute_inputs / compute_output_image)"""
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("loop_"))
+                  if not n.startswith("loop_") and not n.startswith("frames_"))
 
 
 def loop_cases():

@@ -245,6 +245,71 @@ __global__ void __launch_bounds__(256, 4) k_like(cudaTextureObject_t tex, const 
     }
 }
 
+
+// lane-paired gathers: lanes (2k, 2k+1) work on the two pixels of the pair together.  Each LDG.128 then
+// covers 16 samples x 32 contiguous bytes (west texel in the even lane, east texel in the odd lane) instead
+// of 32 samples x 16 bytes, so a request touches about half as many distinct rows.  Each lane computes the
+// west (or east) half of the bilinear sum of BOTH pixels and the halves are exchanged with SHFL.
+struct LP { float4 a0, a1, b0, b1; float wxA, wyA, wxB, wyB; };
+__device__ __forceinline__ void lp_gather(const float4* __restrict__ plane, const Smp& s, int role, float (&res)[3]) {
+    int off = s.y0 * W + s.x0;
+    int offp = __shfl_xor_sync(0xffffffffu, off, 1);
+    float wxp = __shfl_xor_sync(0xffffffffu, s.wx, 1), wyp = __shfl_xor_sync(0xffffffffu, s.wy, 1);
+    const int offA = role ? offp : off, offB = role ? off : offp;
+    const float wxA = role ? wxp : s.wx, wyA = role ? wyp : s.wy, wxB = role ? s.wx : wxp, wyB = role ? s.wy : wyp;
+    const float4* q = plane + role;
+    float4 a0 = __ldg(q + offA), a1 = __ldg(q + offA + W), b0 = __ldg(q + offB), b1 = __ldg(q + offB + W);
+    const float hA = role ? wxA : 1 - wxA, hB = role ? wxB : 1 - wxB;
+    float pA[3] = {hA * (a0.x * (1 - wyA) + a1.x * wyA), hA * (a0.y * (1 - wyA) + a1.y * wyA), hA * (a0.z * (1 - wyA) + a1.z * wyA)};
+    float pB[3] = {hB * (b0.x * (1 - wyB) + b1.x * wyB), hB * (b0.y * (1 - wyB) + b1.y * wyB), hB * (b0.z * (1 - wyB) + b1.z * wyB)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float got = __shfl_xor_sync(0xffffffffu, role ? pA[c] : pB[c], 1);
+        res[c] = (role ? pB[c] : pA[c]) + got;
+    }
+}
+__global__ void __launch_bounds__(256) k_lanepair(const float4* __restrict__ img, const float* __restrict__ fl, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    const int role = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            Smp s = sample_pos(fl, b, x, y, n, f);
+            float r[3]; lp_gather(img + ((long long)b * 2 + f) * NPX, s, role, r);
+            acc += r[0] + r[1] + r[2];
+        }
+    out[(long long)b * NPX + (long long)y * W + x] = acc;
+}
+template <int NSTORE, bool JITTER>
+__global__ void __launch_bounds__(256, 4) k_like_lp(const float4* __restrict__ img, const float* __restrict__ fl,
+                                                    const float* __restrict__ y5, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    const int role = threadIdx.x & 1;
+    const long long p = (long long)y * W + x;
+    for (int n = 0; n < N; ++n) {
+        float jx0 = 0, jy0 = 0, jx1 = 0, jy1 = 0, lg = 0;
+        if (JITTER) {
+            const float* Y = y5 + ((long long)(b * N + n) * 5) * NPX + p;
+            lg = __ldcs(Y); jx1 = __ldcs(Y + NPX); jy1 = __ldcs(Y + 2 * NPX); jx0 = __ldcs(Y + 3 * NPX); jy0 = __ldcs(Y + 4 * NPX);
+        }
+        float acc[3] = {lg, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            Smp s = sample_pos(fl, b, x, y, n, f);
+            if (JITTER) {
+                float ix = fminf(fmaxf(s.x0 + s.wx + (f ? jx1 : jx0), 0.f), W - 1.001f), iy = fminf(fmaxf(s.y0 + s.wy + (f ? jy1 : jy0), 0.f), H - 1.001f);
+                s.x0 = (int)ix; s.y0 = (int)iy; s.wx = ix - s.x0; s.wy = iy - s.y0;
+            }
+            float r[3]; lp_gather(img + ((long long)b * 2 + f) * NPX, s, role, r);
+            acc[0] += r[0]; acc[1] += r[1]; acc[2] += r[2];
+        }
+        float* O = out + ((long long)(b * N + n) * NSTORE) * NPX + p;
+#pragma unroll
+        for (int k = 0; k < NSTORE; ++k) __stcs(O + (long long)k * NPX, acc[k % 3] + k);
+    }
+}
+
 template <typename F> float time_ms(F&& launch, int reps = 10) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     for (int i = 0; i < 3; ++i) launch();
@@ -310,6 +375,7 @@ int main() {
         run("nogather", [&] { k_nogather<0><<<grid, 256>>>(flow, out); });
         run("planar4", [&] { k_planar4<0><<<grid, 256>>>(img, flow, out); });
         run("rgbx16", [&] { k_rgbx16<0><<<grid, 256>>>(p16, flow, out); });
+        run("lanepair", [&] { k_lanepair<<<grid, 256>>>(p16, flow, out); });
         run("pair32", [&] { k_pair32<0><<<grid, 256>>>(p32, flow, out); });
         run("planar4_b84", [&] { k_planar4<1><<<grid, 256>>>(img, flow, out); });
         run("rgbx16_b84", [&] { k_rgbx16<1><<<grid, 256>>>(p16, flow, out); });
@@ -323,6 +389,8 @@ int main() {
 #define LIKE(TW) \
         run("k2like_texw" #TW, [&] { k_like<TW, 3, true><<<grid, 256>>>(tex1, p16, flow, y5, big); }); \
         run("k1like_texw" #TW, [&] { k_like<TW, 16, false><<<grid, 256>>>(tex1, p16, flow, y5, big); });
+        run("k2like_lanepair", [&] { k_like_lp<3, true><<<grid, 256>>>(p16, flow, y5, big); });
+        run("k1like_lanepair", [&] { k_like_lp<16, false><<<grid, 256>>>(p16, flow, y5, big); });
         LIKE(0) LIKE(2) LIKE(3) LIKE(4) LIKE(5) LIKE(6) LIKE(8)
         for (auto& r : rs)
             printf("{\"flow_grid\": \"1/%d\", \"variant\": \"%s\", \"ms\": %.3f, \"ns_per_warp_sample\": %.2f, \"cyc_per_warp_sample_per_sm\": %.1f, \"checksum\": %.6f}\n",

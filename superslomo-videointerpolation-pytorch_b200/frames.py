@@ -48,12 +48,15 @@ def center_padding(h_in, w_in, multiple=32):
 
 
 def frames_from_u8(images, order="bgr", pad_mode="before", lut=None, dtype=torch.float32, want_planar=True,
-                   want_rgbx=False, multiple=32):
+                   want_rgbx=False, multiple=32, pad_values=None):
     """images: F x H_in x W_in x 3 uint8 CUDA tensor (rows and pixels dense).  Returns
     (planar F x 3 x H x W or None, rgbx F x H x W x 4 or None, (top, left)).
 
     pad_mode "before": pad with byte 0 and normalise everything (visualize_interpolation.py:87 then :137);
-    "after": normalise, then zero-pad (default_reader.py:266-271)."""
+    "after": normalise, then zero-pad (default_reader.py:266-271).
+    pad_values: the three fill values of the padding as host floats; when None and pad_mode is "before" they are
+    read back from the table (lut[:, 0]), which synchronises -- pass them (e.g. `lut[:, 0].tolist()` computed
+    once) to keep the call asynchronous and capturable into a CUDA graph."""
     if not images.is_cuda or images.dtype != torch.uint8:
         raise RuntimeError("frames_from_u8 needs a uint8 CUDA tensor (no CPU fallback); got %s on %s"
                            % (images.dtype, images.device))
@@ -66,12 +69,16 @@ def frames_from_u8(images, order="bgr", pad_mode="before", lut=None, dtype=torch
     if lut is None:
         lut = normalisation_lut(device=dev)
     lut = lut.to(device=dev, dtype=torch.float32).contiguous()
-    if pad_mode == "before":
-        pad = lut[:, 0].cpu()
-    elif pad_mode == "after":
-        pad = torch.zeros(3)
-    else:
+    if pad_mode not in ("before", "after"):
         raise ValueError("pad_mode must be 'before' or 'after'")
+    if pad_values is not None:
+        pad = [float(x) for x in pad_values]
+        if len(pad) != 3:
+            raise ValueError("pad_values must hold three floats (R, G, B)")
+    elif pad_mode == "before":
+        pad = lut[:, 0].cpu()
+    else:
+        pad = torch.zeros(3)
     pad_arr = (ctypes.c_float * 3)(*[float(x) for x in pad])
     planar = torch.empty((F, 3, H, W), dtype=dtype, device=dev) if want_planar else None
     rgbx = torch.empty((F, H, W, 4), dtype=dtype, device=dev) if want_rgbx else None

@@ -353,7 +353,7 @@ def main():
         return {"ms_per_step": ms, "frames_per_s": B * NT / (ms * 1e-3),
                 "path_algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "path_frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
 
-    smooth = smooth_res = bf16 = None
+    smooth = smooth_res = bf16 = layouts = None
     if rank == 0 and not args.no_variants:
         gen = torch.Generator(device=dev).manual_seed(7)
 
@@ -382,7 +382,22 @@ def main():
                 return a, ssm_b200.fuse_from_flow(img_h, flow_h, out5_h, t, packed=r)
         bf16 = variant(timed(step_bf16), (pack_bytes + fuse_bytes) // 2)
         bf16["note"] = "bf16 storage of every tensor, fp32 arithmetic; not the headline (the reference is fp32)"
-        del img_h, flow_h, out5_h
+        del img_h, flow_h
+        # the layouts either side of a channels-last stage-2 U-Net under bf16 autocast:
+        # compute_inputs writes B x N x H x W x 16 bf16, compute_output_image reads a bf16 U-Net output;
+        # frames, flows and the fused frames stay fp32
+        nhwc_buf = torch.empty((B, NT, H, W, 16), dtype=torch.bfloat16, device=dev).permute(0, 1, 4, 2, 3)
+
+        def step_layouts():
+            with torch.no_grad():
+                r = ssm_b200.pack_frames(img6, out=rgbx_buf)
+                a = ssm_b200.flow_pack_channels_last(img6, flow4, t, n_timesteps=NT, dtype=torch.bfloat16, packed=r,
+                                                     out=nhwc_buf)
+                return a, ssm_b200.fuse_from_flow(img6, flow4, out5_h, t, packed=r, out=frames_buf)
+        layouts = variant(timed(step_layouts), ((10 * 4 + 16 * 2 * NT) + (10 * 4 + (5 * 2 + 3 * 4) * NT)) * NPX * B)
+        layouts["note"] = ("compute_inputs written channels-last bf16 (what conv1a consumes under channels-last bf16 "
+                           "autocast), bf16 U-Net output read directly; fp32 frames/flows/result; not the headline")
+        del out5_h, nhwc_buf
 
     # ---- training backward of the same kernels (flow / U-Net-output gradients; frames are data) ----
     train = None
@@ -415,9 +430,11 @@ def main():
     # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
     e2e = None
     if not args.no_e2e:
-        h_img, h_flow, h_out5 = img6.cpu().pin_memory(), flow4.cpu().pin_memory(), out5.cpu().pin_memory()
-        h_t = t.cpu()
-        h_out = torch.empty((B, NT, 3, H, W), dtype=torch.float32, pin_memory=True)
+        # pinned buffers on the NUMA node the GPU hangs off (each rank binds to its own GPU's node)
+        with sharding.numa_local_to_gpu(local_rank) as placement:
+            h_img, h_flow, h_out5 = img6.cpu().pin_memory(), flow4.cpu().pin_memory(), out5.cpu().pin_memory()
+            h_t = t.cpu()
+            h_out = torch.empty((B, NT, 3, H, W), dtype=torch.float32, pin_memory=True)
         scratch = torch.empty(ssm_b200.synthesize_host_scratch_bytes(B, NT, H, W), dtype=torch.uint8, device=dev)
         ssm_b200.synthesize_host(h_img, h_flow, h_out5, h_t, out=h_out, scratch=scratch)          # warm-up
         barrier()
@@ -434,7 +451,8 @@ def main():
         d2h = res.numel() * 4
         e2e = {"value": frames_per_step * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "ssm_synthesize_host (pinned host buffers, 3-slot copy/compute pipeline)"}
+               "api": "ssm_synthesize_host (pinned host buffers, 3-slot copy/compute pipeline)",
+               "host_placement": placement.info}
         del h_img, h_flow, h_out5, res, h_out, scratch
 
     # ---- CPU baseline: the reference's torch-op path on the host cores, rank 0, N=1 only ------
@@ -457,7 +475,8 @@ def main():
                        "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
                        "parallelism": "pairs sharded over %d rank(s), no collective" % world},
             "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth,
-            "smooth_flow_and_unet_output_variant": smooth_res, "bf16_storage_variant": bf16, "cpu_baseline": cpu_baseline,
+            "smooth_flow_and_unet_output_variant": smooth_res, "bf16_storage_variant": bf16, "unet_layouts_variant": layouts,
+            "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 3
+#define SSM_ABI_VERSION 4
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -154,6 +154,23 @@ int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const voi
                       const ssm_tensor* grad_flow4, const ssm_tensor* grad_img6,
                       int B, int N, int H, int W, int dtype, int coord_mode,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the layouts either side of the stage-2 U-Net ---------------
+ * ssm_flow_pack_fwd_nhwc: a2 as ssm_flow_pack_fwd, but the stage-2 input is written channels-last,
+ * out16_nhwc = B x N x H x W x 16 elements of out_dtype (16-byte aligned), which is the layout -- and with
+ * out_dtype = SSM_DTYPE_BF16 the dtype -- conv1a of the stage-2 U-Net [flow_interpolation.py:36-38]
+ * consumes when the U-Net runs channels-last under bf16 autocast: no conversion pass runs between a2
+ * and the U-Net.  Values are those of ssm_flow_pack_fwd rounded once (RN) to out_dtype.  Inputs of
+ * dtype fp32 give out_dtype fp32 or bf16; bf16 inputs give bf16.
+ * ssm_fuse_flow_fwd_mixed: a3+a4 as ssm_fuse_flow_fwd with out5 stored in out5_dtype (bf16 straight
+ * from final_conv [flow_interpolation.py:149-157] under autocast) while frames, flows and the result
+ * stay in `dtype` (fp32): the result equals ssm_fuse_flow_fwd on out5 converted to fp32. */
+int ssm_flow_pack_fwd_nhwc(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const float* t,
+                           void* out16_nhwc, int B, int N, int H, int W,
+                           int dtype, int out_dtype, int coord_mode, void* stream);
+int ssm_fuse_flow_fwd_mixed(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4,
+                            const ssm_tensor* out5, int out5_dtype, const float* t, const ssm_tensor* out3,
+                            int B, int N, int H, int W, int dtype, int coord_mode, void* stream);
 
 /* ---- a4 + a9: compute_output_image fused with the loss front-end of SSMLosses
  *      [reference scripts/models/losses.py:104-170, 213-233; SURVEY.md section 8(f) rank 1].

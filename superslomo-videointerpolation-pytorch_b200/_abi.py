@@ -19,8 +19,8 @@ COORD_DIV, COORD_RCP = 0, 1
 EXPORTS = (
     "ssm_version", "ssm_last_error",
     "ssm_warp_fwd", "ssm_warp_bwd",
-    "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
-    "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd",
+    "ssm_flow_pack_fwd", "ssm_flow_pack_bwd", "ssm_flow_pack_fwd_nhwc",
+    "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_flow_fwd_mixed",
     "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd", "ssm_fuse_loss_workspace_bytes",
     "ssm_frames_from_u8", "ssm_frames_to_u8",
     "ssm_warp_bwd_workspace_bytes", "ssm_flow_pack_bwd_workspace_bytes", "ssm_fuse_bwd_workspace_bytes",
@@ -58,11 +58,13 @@ def lib():
     L.ssm_selftest_division.restype = I
     L.ssm_pack_frames.argtypes = [P, V, I, I, I, I, V]
     L.ssm_flow_pack_fwd.argtypes = [P, V, P, V, P, I, I, I, I, I, I, V]
+    L.ssm_flow_pack_fwd_nhwc.argtypes = [P, V, P, V, V, I, I, I, I, I, I, I, V]
     L.ssm_flow_pack_bwd.argtypes = [P, P, V, P, V, P, P, I, I, I, I, I, I, V, Z, V]
     L.ssm_fuse_fwd.argtypes = [P, V, P, P, V, P, I, I, I, I, I, I, V]
     L.ssm_fuse_bwd.argtypes = [P, P, V, P, P, V, P, P, P, I, I, I, I, I, I, V, Z, V]
     L.ssm_fuse_flow_fwd.argtypes = L.ssm_fuse_fwd.argtypes
     L.ssm_fuse_flow_bwd.argtypes = L.ssm_fuse_bwd.argtypes
+    L.ssm_fuse_flow_fwd_mixed.argtypes = [P, V, P, P, I, V, P, I, I, I, I, I, I, V]
     L.ssm_fuse_loss_fwd.argtypes = [P, V, P, P, P, V, P, V, I, I, I, I, I, I, I, I, V, Z, V]
     L.ssm_fuse_loss_bwd.argtypes = [P, V, P, V, P, P, P, P, V, P, P, I, I, I, I, I, I, I, I, V]
     F3, LL = ctypes.POINTER(ctypes.c_float), ctypes.c_longlong
@@ -74,6 +76,7 @@ def lib():
         getattr(L, n).restype = Z
     L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I, V, Z]
     for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
+              "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed",
               "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
               "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host"):
         getattr(L, n).restype = I

@@ -189,6 +189,25 @@ struct PackFwd {
     }
 };
 
+struct PackFwdNhwc {
+    const ssm_tensor* img6; const void* packed; const ssm_tensor* flow4; const float* t; void* out; int out_dtype;
+    int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        if (out_dtype == SSM_DTYPE_BF16) return go<T, MODE, PACKED, __nv_bfloat16>();
+        if constexpr (sizeof(T) == 4) return go<T, MODE, PACKED, float>();
+        return fail(SSM_ERR_UNSUPPORTED, "ssm_flow_pack_fwd_nhwc: bf16 inputs with fp32 output is not built");
+    }
+    template <typename T, int MODE, bool PACKED, typename TO> int go() {
+        const long long npx = (long long)H * W;
+        View<TO> o;
+        o.p = (TO*)out; o.sb = (long long)N * 16 * npx; o.sn = 16 * npx; o.sc = 1;
+        flow_pack_fwd_kernel<T, MODE, PACKED, TO, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<T>(img6), (const T*)packed, cview<T>(flow4), t, o, N, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_flow_pack_fwd_nhwc");
+        return SSM_OK;
+    }
+};
+
 struct PackBwd {
     const ssm_tensor *g16, *img6; const void* packed; const ssm_tensor* flow4; const float* t;
     const ssm_tensor *gflow4, *gimg6; int B, N, H, W; void* ws; cudaStream_t s;
@@ -231,6 +250,19 @@ struct FuseFwd {
         fuse_fwd_kernel<T, MODE, PACKED, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
             cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(out3), N, make_geom(H, W));
         SSM_LAUNCH_CHECK("ssm_fuse_fwd");
+        return SSM_OK;
+    }
+};
+
+// fp32 frames and flows with the U-Net output stored in bf16 (ssm_fuse_flow_fwd_mixed)
+struct FuseFlowFwdMixed {
+    const ssm_tensor* img6; const void* packed; const ssm_tensor *flow4, *out5; const float* t;
+    const ssm_tensor* out3; int B, N, H, W; cudaStream_t s;
+    template <typename T, int MODE, bool PACKED> int run() {
+        fuse_fwd_kernel<float, MODE, PACKED, true, __nv_bfloat16><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+            cview<float>(img6), (const float*)packed, cview<float>(flow4), cview<__nv_bfloat16>(out5), t,
+            mview<float>(out3), N, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_fuse_flow_fwd_mixed");
         return SSM_OK;
     }
 };
@@ -408,6 +440,21 @@ int ssm_flow_pack_fwd(const ssm_tensor* img6, const void* packed, const ssm_tens
     return dispatch3(dtype, coord_mode, packed != nullptr, PackFwd{img6, packed, flow4, t, out16, B, N, H, W, (cudaStream_t)stream});
 }
 
+int ssm_flow_pack_fwd_nhwc(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4, const float* t,
+                           void* out16_nhwc, int B, int N, int H, int W,
+                           int dtype, int out_dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_packed(packed));
+    SSM_TRY(check_common(B, N, 16, H, W, dtype, coord_mode));
+    if (out_dtype != SSM_DTYPE_F32 && out_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out_dtype %d", out_dtype);
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    if (!out16_nhwc) return fail(SSM_ERR_NULL, "out16_nhwc is NULL");
+    if (((uintptr_t)out16_nhwc) % 16 != 0) return fail(SSM_ERR_ALIGN, "out16_nhwc must be 16-byte aligned");
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     PackFwdNhwc{img6, packed, flow4, t, out16_nhwc, out_dtype, B, N, H, W, (cudaStream_t)stream});
+}
+
 int ssm_flow_pack_bwd(const ssm_tensor* grad16, const ssm_tensor* img6, const void* packed,
                       const ssm_tensor* flow4, const float* t, const ssm_tensor* grad_flow4,
                       const ssm_tensor* grad_img6, int B, int N, int H, int W, int dtype, int coord_mode,
@@ -489,6 +536,25 @@ int ssm_fuse_flow_fwd(const ssm_tensor* img6, const void* packed, const ssm_tens
                       const float* t, const ssm_tensor* out3, int B, int N, int H, int W,
                       int dtype, int coord_mode, void* stream) {
     return fuse_fwd_impl(img6, packed, flow4, out5, t, out3, B, N, H, W, dtype, coord_mode, stream, true);
+}
+
+int ssm_fuse_flow_fwd_mixed(const ssm_tensor* img6, const void* packed, const ssm_tensor* flow4,
+                            const ssm_tensor* out5, int out5_dtype, const float* t, const ssm_tensor* out3,
+                            int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
+    if (out5_dtype == dtype)
+        return fuse_fwd_impl(img6, packed, flow4, out5, t, out3, B, N, H, W, dtype, coord_mode, stream, true);
+    if (dtype != SSM_DTYPE_F32 || out5_dtype != SSM_DTYPE_BF16)
+        return fail(SSM_ERR_UNSUPPORTED, "ssm_fuse_flow_fwd_mixed: only fp32 frames/flows with a bf16 out5 (got dtype %d, out5_dtype %d)",
+                    dtype, out5_dtype);
+    SSM_TRY(check_packed(packed));
+    SSM_TRY(check_common(B, N, 5, H, W, dtype, coord_mode));
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_tensor(out5, "out5", out5_dtype, true));
+    SSM_TRY(check_tensor(out3, "out3", dtype, true));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    return dispatch3(dtype, coord_mode, packed != nullptr,
+                     FuseFlowFwdMixed{img6, packed, flow4, out5, t, out3, B, N, H, W, (cudaStream_t)stream});
 }
 
 int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const void* packed,

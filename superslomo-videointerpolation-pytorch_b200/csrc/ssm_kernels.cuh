@@ -149,10 +149,34 @@ warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, 
 #ifndef SSM_PACK_MIN_BLOCKS
 #define SSM_PACK_MIN_BLOCKS 4
 #endif
-template <typename T, int MODE, bool PACKED>
+// NHWC: the 16 channels of a pixel are written next to each other
+// (B x N x H x W x 16, i.e. torch.channels_last per (pair, timestep)) in the storage type TO, which may
+// differ from the input type -- with TO = bf16 this is the tensor conv1a of the stage-2 U-Net consumes
+// under channels-last bf16 autocast (flow_interpolation.py:36-38), so no layout or dtype conversion pass
+// runs between compute_inputs and the U-Net; a thread then writes 32 (bf16) or 64 (fp32) contiguous
+// bytes per timestep as 2 or 4 16-byte stores instead of 16 4-byte ones.
+template <typename TO> __device__ __forceinline__ void store16_nhwc(TO* o, const float (&v)[16]);
+template <> __device__ __forceinline__ void store16_nhwc<float>(float* o, const float (&v)[16]) {
+    float4* q = reinterpret_cast<float4*>(o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(q + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+}
+template <> __device__ __forceinline__ void store16_nhwc<__nv_bfloat16>(__nv_bfloat16* o, const float (&v)[16]) {
+    unsigned w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);   // .x = low half = even channel
+        w[k] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    uint4* q = reinterpret_cast<uint4*>(o);
+    __stcs(q, make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(q + 1, make_uint4(w[4], w[5], w[6], w[7]));
+}
+
+template <typename T, int MODE, bool PACKED, typename TO = T, bool NHWC = false>
 __global__ void __launch_bounds__(TILE_THREADS, SSM_PACK_MIN_BLOCKS)
 flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flow4,
-                     const float* __restrict__ tv, View<T> out16, int N, Geom g) {
+                     const float* __restrict__ tv, View<TO> out16, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
@@ -173,7 +197,7 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
         }
     }
     const float* tp = tv + ti.b * N;
-    T* __restrict__ O = out16.p + ti.b * out16.sb + p;
+    TO* __restrict__ O = out16.p + ti.b * out16.sb + (NHWC ? (long long)p * 16 : (long long)p);
     const int osc = (int)out16.sc;   // fits 32 bits (checked on the host): one IMAD.WIDE per address
     for (int n = 0; n < N; ++n, O += out16.sn) {
         const Coef k = make_coef(__ldg(tp + n));
@@ -184,6 +208,16 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
         Quad q1[3], q0[3];
         gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
         gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
+        if (NHWC) {                                                             // :364-367, channels-last
+            float o[16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                o[c] = c1[c]; o[3 + c] = bilerp(q1[c], t1); o[10 + c] = bilerp(q0[c], t0); o[13 + c] = c0[c];
+            }
+            o[6] = e1x; o[7] = e1y; o[8] = e0x; o[9] = e0y;
+            store16_nhwc<TO>(O, o);
+            continue;
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {                                           // :364-367
             sts_(O + (0 + c) * osc, c1[c]);
@@ -322,9 +356,12 @@ __device__ __forceinline__ void est_flows(float tt, const float (&f)[4], float (
     xs[2] = storage_round<T>(est_t0(k, f[0], f[2])); xs[3] = storage_round<T>(est_t0(k, f[1], f[3]));
 }
 
-template <typename T, int MODE, bool PACKED, bool RECOMP>
+// TY: storage type of the U-Net output (out5).  It may differ from T: under bf16 autocast final_conv
+// (flow_interpolation.py:149-157) produces bf16 while frames and flows stay fp32; reading it as it is
+// gives exactly the values of out5.float() without that conversion pass.
+template <typename T, int MODE, bool PACKED, bool RECOMP, typename TY = T>
 __global__ void __launch_bounds__(TILE_THREADS, SSM_FUSE_MIN_BLOCKS)
-fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const T> out5,
+fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> flows4, View<const TY> out5,
                 const float* __restrict__ tv, View<T> out3, int N, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
     if (!ti.valid) return;
@@ -333,7 +370,7 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
     const Frames<T, PACKED> fr(img6, packed, ti.b, npx);
     const float* tp = tv + ti.b * N;
     const T* __restrict__ X = flows4.p + ti.b * flows4.sb + p;
-    const T* __restrict__ Y = out5.p + ti.b * out5.sb + p;
+    const TY* __restrict__ Y = out5.p + ti.b * out5.sb + p;
     T* __restrict__ O = out3.p + ti.b * out3.sb + p;
     // channel strides fit 32 bits (checked on the host): one IMAD.WIDE per address
     const int xsc = (int)flows4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;

@@ -249,6 +249,46 @@ def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None, packed=None, out=N
     return _FlowPack.apply(img6, flow4, tvec, int(n_timesteps), _resolve_mode(coord_mode), packed)
 
 
+def flow_pack_channels_last(img6, flow4, t, n_timesteps=1, dtype=None, coord_mode=None, packed=None, out=None):
+    """compute_inputs for N timesteps, written in the layout (and dtype) the stage-2 U-Net consumes when it
+    runs channels-last, optionally under bf16 autocast (ssm_flow_pack_fwd_nhwc).
+
+    Returns a B x N x 16 x H x W tensor whose memory is B x N x H x W x 16 (`x.view(B*N, 16, H, W)` is a
+    torch.channels_last tensor: conv1a takes it without a layout or dtype conversion pass).  dtype: None
+    (= the frames' dtype) or torch.bfloat16; the values are those of flow_pack rounded once to dtype.
+    Inference only (the training loop uses flow_pack, whose backward exists).  out: optional caller-owned
+    result buffer with exactly that shape and strides."""
+    _same(img6, flow4)
+    if torch.is_grad_enabled() and (img6.requires_grad or flow4.requires_grad):
+        raise RuntimeError("flow_pack_channels_last is inference-only; use flow_pack for a differentiable result")
+    img6, flow4 = _abi.dense_planes(img6.detach()), _abi.dense_planes(flow4.detach())
+    B, C6, H, W = img6.shape
+    N = int(n_timesteps)
+    if C6 != 6 or flow4.shape != (B, 4, H, W):
+        raise RuntimeError("compute_inputs: expected img B x 6 x H x W and flow B x 4 x H x W, got %s and %s"
+                           % (tuple(img6.shape), tuple(flow4.shape)))
+    dtype = img6.dtype if dtype is None else dtype
+    if dtype not in (torch.float32, torch.bfloat16) or (img6.dtype == torch.bfloat16 and dtype != torch.bfloat16):
+        raise TypeError("flow_pack_channels_last: %s frames cannot be written as %s" % (img6.dtype, dtype))
+    tvec = _t_vector(t, B * N, img6.device)
+    if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+        packed = pack_frames(img6)
+    if out is None:
+        out = torch.empty((B, N, H, W, 16), dtype=dtype, device=img6.device).permute(0, 1, 4, 2, 3)
+    elif tuple(out.shape) != (B, N, 16, H, W) or out.dtype != dtype or out.device != img6.device \
+            or out.stride() != (N * 16 * H * W, 16 * H * W, 1, 16 * W, 16):
+        raise RuntimeError("flow_pack_channels_last: out= must be a %s %s tensor stored as B x N x H x W x 16"
+                           % ((B, N, 16, H, W), dtype))
+    with torch.cuda.device(img6.device):
+        rc = _abi.lib().ssm_flow_pack_fwd_nhwc(
+            _abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6), _abi.ref(_abi.desc(flow4, False)),
+            ctypes.c_void_p(tvec.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, N, H, W, _abi.dtype_code(img6),
+            _abi.DTYPE_BF16 if dtype == torch.bfloat16 else _abi.DTYPE_F32, _resolve_mode(coord_mode),
+            _abi.stream_ptr(img6.device))
+    _abi.check(rc, "ssm_flow_pack_fwd_nhwc")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 class _Fuse(torch.autograd.Function):
     """extract_outputs + compute_output_image for N timesteps -- flow_interpolation.py:374-429"""
@@ -381,12 +421,42 @@ class _FuseFlow(torch.autograd.Function):
         return gi, gf, gy, None, None, None
 
 
+def _fuse_from_flow_mixed(img6, flow4, out5, tvec, mode, packed, out):
+    """fp32 frames and flows with the U-Net output as bf16 autocast leaves it (ssm_fuse_flow_fwd_mixed):
+    equals fuse_from_flow(img6, flow4, out5.float(), t) without materialising out5.float().  Inference only."""
+    _same(img6, flow4)
+    if torch.is_grad_enabled() and (img6.requires_grad or flow4.requires_grad or out5.requires_grad):
+        raise RuntimeError("fuse_from_flow: a bf16 out5 with fp32 frames is inference-only; pass out5.float() "
+                           "for a differentiable result")
+    if out5.device != img6.device:
+        raise RuntimeError("ssm_b200: all tensors of a call must share a device")
+    img6, flow4, out5 = _abi.dense_planes(img6.detach()), _abi.dense_planes(flow4.detach()), _abi.dense_planes(out5.detach())
+    B, C6, H, W = img6.shape
+    if out5.dim() != 5 or C6 != 6 or flow4.shape != (B, 4, H, W) or out5.shape[0] != B or out5.shape[2:] != (5, H, W):
+        raise RuntimeError("fuse_from_flow: expected img B x 6, flow B x 4, output B x N x 5 (x H x W), "
+                           "got %s, %s, %s" % (tuple(img6.shape), tuple(flow4.shape), tuple(out5.shape)))
+    N = out5.shape[1]
+    if packed is None and N >= _AUTO_PACK_MIN_TIMESTEPS:
+        packed = pack_frames(img6)
+    out = _out_buffer(out, (B, N, 3, H, W), img6, "fuse_from_flow")
+    with torch.cuda.device(img6.device):
+        rc = _abi.lib().ssm_fuse_flow_fwd_mixed(
+            _abi.ref(_abi.desc(img6, False)), _packed_ptr(packed, img6), _abi.ref(_abi.desc(flow4, False)),
+            _abi.ref(_abi.desc(out5, True)), _abi.DTYPE_BF16, ctypes.c_void_p(tvec.data_ptr()),
+            _abi.ref(_abi.desc(out, True)), B, N, H, W, _abi.DTYPE_F32, mode, _abi.stream_ptr(img6.device))
+    _abi.check(rc, "ssm_fuse_flow_fwd_mixed")
+    return out
+
+
 def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None, out=None):
     """Fused frames for every (pair, timestep) from the stage-1 flows: img6 B x 6, flow4 B x 4,
     out5 B x N x 5 -> B x N x 3.  Equals fuse(img6, flow_pack(img6, flow4, t), out5, t) without reading
-    the 16-channel tensor back; gradients go to flow4 directly."""
+    the 16-channel tensor back; gradients go to flow4 directly.  A bf16 out5 (the U-Net output under bf16
+    autocast) next to fp32 frames and flows is read as it is (inference only)."""
     B, N = out5.shape[0], out5.shape[1]
     tvec = _t_vector(t, B * N, img6.device)
+    if out5.dtype == torch.bfloat16 and img6.dtype == torch.float32:
+        return _fuse_from_flow_mixed(img6, flow4, out5, tvec, _resolve_mode(coord_mode), packed, out)
     if out is not None:
         _no_grad_for_out(out, "fuse_from_flow", img6, flow4, out5)
         with torch.no_grad():

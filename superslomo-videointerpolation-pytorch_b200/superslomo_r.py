@@ -48,6 +48,9 @@ class FullModel(nn.Module, SynthesisMixin):
             w2, 16, 5, self.cross_skip, stage=2, cfg=cfg)
         self.freeze_weights()
         self.loss = loss if loss is not None else SSMLosses(cfg)
+        # interpolate(): write compute_inputs in the layout/dtype a channels-last stage-2 U-Net consumes and read
+        # its bf16 output directly; False = planar fp32 either side (generic)
+        self.unet_layouts = True
 
     def freeze_weights(self):
         """superslomo_r.py:73-88"""
@@ -129,19 +132,36 @@ class FullModel(nn.Module, SynthesisMixin):
         t_bn = t_values.view(1, N).expand(B, N).contiguous()
         step = N if unet_chunk is None else max(1, int(unet_chunk))
         rgbx = [F_ssm.pack_frames(pairs[:, w]) for w in range(Wn)]
+        # A channels-last stage-2 U-Net gets its input in that layout straight from compute_inputs -- and in
+        # bf16 when it runs under bf16 autocast -- so no conversion pass runs in front of conv1a
+        # (SURVEY.md section 8(f) rank 2).  One window only: several windows are stacked, which copies anyway.
+        nhwc_dtype = None
+        if self.unet_layouts and Wn == 1 and getattr(self.stage2_model, "channels_last", False):
+            nhwc_dtype = pairs.dtype
+            if torch.is_autocast_enabled("cuda"):
+                nhwc_dtype = torch.bfloat16 if torch.get_autocast_dtype("cuda") == torch.bfloat16 else None
         frames = []
         for n0 in range(0, N, step):
             tn = t_bn[:, n0:n0 + step].contiguous()
             n = tn.shape[1]
             # B x W x n x 16: every window at every time of the chunk
-            in16 = torch.stack([F_ssm.flow_pack(pairs[:, w], flows[:, w], tn, n_timesteps=n, packed=rgbx[w])
-                                for w in range(Wn)], dim=1) if Wn > 1 else \
-                F_ssm.flow_pack(pairs[:, 0], flows[:, 0], tn, n_timesteps=n, packed=rgbx[0]).unsqueeze(1)
+            if nhwc_dtype is not None:
+                in16 = F_ssm.flow_pack_channels_last(pairs[:, 0], flows[:, 0], tn, n_timesteps=n, dtype=nhwc_dtype,
+                                                     packed=rgbx[0]).unsqueeze(1)
+            elif Wn > 1:
+                in16 = torch.stack([F_ssm.flow_pack(pairs[:, w], flows[:, w], tn, n_timesteps=n, packed=rgbx[w])
+                                    for w in range(Wn)], dim=1)
+            else:
+                in16 = F_ssm.flow_pack(pairs[:, 0], flows[:, 0], tn, n_timesteps=n, packed=rgbx[0]).unsqueeze(1)
             # stage 2 sees (B*n) samples of W windows each
             x = in16.permute(0, 2, 1, 3, 4, 5).reshape(B * n, Wn, 16, *in16.shape[-2:])
             e = None
             if encs[0] is not None:
                 e = [enc.repeat_interleave(n, dim=0) for enc in encs]
-            out5 = self.stage2_model(x, e)[mid].to(pairs.dtype).view(B, n, 5, *in16.shape[-2:])
+            out5 = self.stage2_model(x, e)[mid]
+            # a bf16 U-Net output (autocast) next to fp32 frames is read as it is by the fusion kernel
+            if not (out5.dtype == torch.bfloat16 and pairs.dtype == torch.float32):
+                out5 = out5.to(pairs.dtype)
+            out5 = out5.view(B, n, 5, *in16.shape[-2:])
             frames.append(F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5, tn, packed=rgbx[mid]))
         return torch.cat(frames, dim=1)

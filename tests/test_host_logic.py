@@ -176,3 +176,31 @@ def test_checkpoint_layout_round_trip(tmp_path):
     assert formats.load_checkpoint(b, p) == 12
     for x, y in zip(a.stage2_model.parameters(), b.stage2_model.parameters()):
         assert torch.equal(x, y)
+
+
+def test_numa_placement_helper(tmp_path, monkeypatch):
+    """numa_local_to_gpu: binds to the GPU-local CPUs that the process may use, restores on exit, and is a
+    no-op without topology information."""
+    import os
+    from ssm_b200 import sharding
+    assert sharding._parse_cpulist("0-2,5,7-8\n") == {0, 1, 2, 5, 7, 8}
+    before = os.sched_getaffinity(0)
+    d = tmp_path / "0000:1b:00.0"
+    d.mkdir()
+    some = sorted(before)[: max(1, len(before) // 2)]
+    (d / "numa_node").write_text("0\n")
+    (d / "local_cpulist").write_text(",".join(str(c) for c in some) + "\n")
+    ctx = sharding.numa_local_to_gpu(0)
+    monkeypatch.setattr(ctx, "_pci_dir", lambda: str(d))
+    with ctx as placement:
+        assert placement.info["numa_node"] == 0
+        assert placement.info["cpus_bound"] == len(some)
+        assert os.sched_getaffinity(0) == set(some)
+    assert os.sched_getaffinity(0) == before
+    # no topology (e.g. a VM without NUMA information): nothing happens
+    (d / "numa_node").write_text("-1\n")
+    ctx = sharding.numa_local_to_gpu(0)
+    monkeypatch.setattr(ctx, "_pci_dir", lambda: str(d))
+    with ctx as placement:
+        assert placement.info == {"numa_node": None, "cpus_bound": 0, "mempolicy": False}
+        assert os.sched_getaffinity(0) == before

@@ -41,6 +41,9 @@ def main():
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the U-Nets (the path stays fp32)")
     ap.add_argument("--channels-last", action="store_true")
     ap.add_argument("--graph", action="store_true", help="capture the device part of the step into a CUDA graph")
+    ap.add_argument("--generic-plumbing", action="store_true",
+                    help="planar fp32 tensors either side of the stage-2 U-Net even when it runs channels-last / autocast "
+                         "(default: compute_inputs writes the channels-last [bf16] tensor conv1a consumes)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -51,6 +54,7 @@ def main():
     if a.channels_last:
         model.stage1_model.set_channels_last()
         model.stage2_model.set_channels_last()
+    model.unet_layouts = not a.generic_plumbing
     # device-resident t: a host list would be copied from pageable memory inside the captured region
     t_values = torch.tensor([(k + 1) / (N + 1) for k in range(N)], dtype=torch.float32, device=dev)
 
@@ -113,7 +117,8 @@ def main():
 
     # share of the step in this repo's kernels: events around every C-ABI call, eager pass
     spans, lib = [], ssm_b200._abi.lib()
-    names = ["ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_fuse_flow_fwd"]
+    names = ["ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_fuse_flow_fwd",
+             "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed"]
     originals = {n: getattr(lib, n) for n in names}
 
     def timed(n, fn):
@@ -143,6 +148,7 @@ def main():
         "what": "end-to-end inference step with the U-Nets (uint8 host frames -> uint8 host frames), not the bench headline",
         "pairs": B, "timesteps": N, "height": h_in, "width": w_in, "unet_chunk": a.unet_chunk,
         "amp_bf16_unets": a.amp, "channels_last_unets": a.channels_last, "cuda_graph": a.graph,
+        "unet_layouts": bool(model.unet_layouts and a.channels_last),
         "ms_per_step": ms, "frames_per_s": B * N / (ms * 1e-3), "checksum": checksum,
         "h2d_bytes_per_step": h_u8.numel(), "d2h_bytes_per_step": h_out.numel(),
         "path_kernels_ms": path_ms, "path_ms_total": sum(path_ms.values()),

@@ -395,9 +395,24 @@ def main():
                                                      out=nhwc_buf)
                 return a, ssm_b200.fuse_from_flow(img6, flow4, out5_h, t, packed=r, out=frames_buf)
         layouts = variant(timed(step_layouts), ((10 * 4 + 16 * 2 * NT) + (10 * 4 + (5 * 2 + 3 * 4) * NT)) * NPX * B)
+
+        # what the generic plumbing does for the same U-Net: planar fp32 compute_inputs, one torch pass that
+        # converts it to channels-last bf16, one that widens the bf16 U-Net output to fp32
+        out5_f = torch.empty_like(out5)
+
+        def step_generic():
+            with torch.no_grad():
+                r = ssm_b200.pack_frames(img6, out=rgbx_buf)
+                a = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT, packed=r, out=in16_buf)
+                nhwc_buf.copy_(a)
+                out5_f.copy_(out5_h)
+                return ssm_b200.fuse_from_flow(img6, flow4, out5_f, t, packed=r, out=frames_buf)
+        layouts["generic_ms_per_step"] = timed(step_generic)
         layouts["note"] = ("compute_inputs written channels-last bf16 (what conv1a consumes under channels-last bf16 "
-                           "autocast), bf16 U-Net output read directly; fp32 frames/flows/result; not the headline")
-        del out5_h, nhwc_buf
+                           "autocast) and the bf16 U-Net output read directly; generic_ms_per_step = the planar fp32 "
+                           "kernels plus the two torch conversion passes they need for the same U-Net; fp32 "
+                           "frames/flows/result; not the headline")
+        del out5_h, nhwc_buf, out5_f
 
     # ---- training backward of the same kernels (flow / U-Net-output gradients; frames are data) ----
     train = None

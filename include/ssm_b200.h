@@ -157,7 +157,7 @@ int ssm_fuse_flow_bwd(const ssm_tensor* grad3, const ssm_tensor* img6, const voi
 
 /* ---- the layouts either side of the stage-2 U-Net ---------------
  * ssm_flow_pack_fwd_nhwc: a2 as ssm_flow_pack_fwd, but the stage-2 input is written channels-last,
- * out16_nhwc = B x N x H x W x 16 elements of out_dtype (16-byte aligned), which is the layout -- and with
+ * out16_nhwc = B x N x H x W x 16 elements of out_dtype (32-byte aligned), which is the layout -- and with
  * out_dtype = SSM_DTYPE_BF16 the dtype -- conv1a of the stage-2 U-Net [flow_interpolation.py:36-38]
  * consumes when the U-Net runs channels-last under bf16 autocast: no conversion pass runs between a2
  * and the U-Net.  Values are those of ssm_flow_pack_fwd rounded once (RN) to out_dtype.  Inputs of

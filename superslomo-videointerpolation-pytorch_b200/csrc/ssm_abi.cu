@@ -449,7 +449,7 @@ int ssm_flow_pack_fwd_nhwc(const ssm_tensor* img6, const void* packed, const ssm
     SSM_TRY(check_tensor(img6, "img6", dtype, true));
     SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
     if (!out16_nhwc) return fail(SSM_ERR_NULL, "out16_nhwc is NULL");
-    if (((uintptr_t)out16_nhwc) % 16 != 0) return fail(SSM_ERR_ALIGN, "out16_nhwc must be 16-byte aligned");
+    if (((uintptr_t)out16_nhwc) % 32 != 0) return fail(SSM_ERR_ALIGN, "out16_nhwc must be 32-byte aligned");
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
     return dispatch3(dtype, coord_mode, packed != nullptr,
                      PackFwdNhwc{img6, packed, flow4, t, out16_nhwc, out_dtype, B, N, H, W, (cudaStream_t)stream});

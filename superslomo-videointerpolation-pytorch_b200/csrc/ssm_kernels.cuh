@@ -154,12 +154,22 @@ warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, 
 // differ from the input type -- with TO = bf16 this is the tensor conv1a of the stage-2 U-Net consumes
 // under channels-last bf16 autocast (flow_interpolation.py:36-38), so no layout or dtype conversion pass
 // runs between compute_inputs and the U-Net; a thread then writes 32 (bf16) or 64 (fp32) contiguous
-// bytes per timestep as 2 or 4 16-byte stores instead of 16 4-byte ones.
+// bytes per timestep as one or two 32-byte stores instead of 16 4-byte ones.
+// One 256-bit streaming store (sm_100: STG.256): a thread writes whole 32-byte sectors, so the two
+// halves of a sector never travel as separate byte-masked writes.  p must be 32-byte aligned.
+__device__ __forceinline__ void stcs256(void* p, const unsigned (&w)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
 template <typename TO> __device__ __forceinline__ void store16_nhwc(TO* o, const float (&v)[16]);
 template <> __device__ __forceinline__ void store16_nhwc<float>(float* o, const float (&v)[16]) {
-    float4* q = reinterpret_cast<float4*>(o);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) __stcs(q + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    for (int h = 0; h < 2; ++h) {
+        unsigned w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(v[8 * h + k]);
+        stcs256(o + 8 * h, w);
+    }
 }
 template <> __device__ __forceinline__ void store16_nhwc<__nv_bfloat16>(__nv_bfloat16* o, const float (&v)[16]) {
     unsigned w[8];
@@ -168,9 +178,7 @@ template <> __device__ __forceinline__ void store16_nhwc<__nv_bfloat16>(__nv_bfl
         const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);   // .x = low half = even channel
         w[k] = *reinterpret_cast<const unsigned*>(&h);
     }
-    uint4* q = reinterpret_cast<uint4*>(o);
-    __stcs(q, make_uint4(w[0], w[1], w[2], w[3]));
-    __stcs(q + 1, make_uint4(w[4], w[5], w[6], w[7]));
+    stcs256(o, w);
 }
 
 template <typename T, int MODE, bool PACKED, typename TO = T, bool NHWC = false>

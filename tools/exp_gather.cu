@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
+#include <string.h>
 #include <vector>
 #include <algorithm>
 
@@ -310,9 +311,83 @@ __global__ void __launch_bounds__(256, 4) k_like_lp(const float4* __restrict__ i
     }
 }
 
+// Which model describes the L1 data stage?  MODE 0: the 8 lanes of a quarter-warp read the same column of 8 different
+// rows (8 lines, one 16-byte bank group).  MODE 1: 8 different rows AND 8 different columns mod 8 (8 lines, 8 bank
+// groups).  MODE 2: 8 consecutive texels of one row (1 line).  A "one wavefront per line" model predicts 8/8/1
+// wavefronts per quarter-warp, a banked-SRAM model 8/1/1.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_bank(const float4* __restrict__ img, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int n = 0; n < 14; ++n) {
+        int yy = (y + 37 * n) % (H - 40), xx = x - lane;
+        int row = MODE == 2 ? yy : yy + lane, col = MODE == 0 ? xx + (lane >> 3) : xx + lane;
+        const float4* q = img + (long long)b * 2 * NPX + (long long)row * W + col;
+        float4 a = __ldg(q), c = __ldg(q + 2 * W), d = __ldg(q + 4 * W), e = __ldg(q + 6 * W);
+        acc += a.x + c.y + d.z + e.x;
+    }
+    out[(long long)b * NPX + (long long)y * W + x] = acc;
+}
+// rgbx16 with the taps read around L1 (ld.global.cg): does a miss path cost the same data-stage wavefronts?
+__global__ void __launch_bounds__(256) k_rgbx16cg(const float4* __restrict__ img, const float* __restrict__ fl, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            Smp s = sample_pos(fl, b, x, y, n, f);
+            const float4* q = img + ((long long)b * 2 + f) * NPX + (long long)s.y0 * W + s.x0;
+            float4 a = __ldcg(q), bb = __ldcg(q + 1), c = __ldcg(q + W), d = __ldcg(q + W + 1);
+            acc += lerp4(a.x, bb.x, c.x, d.x, s.wx, s.wy) + lerp4(a.y, bb.y, c.y, d.y, s.wx, s.wy) + lerp4(a.z, bb.z, c.z, d.z, s.wx, s.wy);
+        }
+    out[(long long)b * NPX + (long long)y * W + x] = acc;
+}
+
+// per-THREAD mix of the two load paths over the caller's own RGBx buffer: the first NT of the 8 taps of a timestep
+// (2 frames x 4 corners) go through the texture unit as point fetches from a LINEAR-memory texture object
+// (tex1Dfetch<float4>, no cudaArray, no upload), the others through the LSU (LDG.128).
+template <int NT, int NSTORE, bool JITTER>
+__global__ void __launch_bounds__(256, 4) k_like_mixlin(cudaTextureObject_t lin, const float4* __restrict__ img, const float* __restrict__ fl,
+                                                        const float* __restrict__ y5, float* __restrict__ out) {
+    int b, x, y; pixel_of_thread<0>(b, x, y);
+    const long long p = (long long)y * W + x;
+    for (int n = 0; n < N; ++n) {
+        float jx0 = 0, jy0 = 0, jx1 = 0, jy1 = 0, lg = 0;
+        if (JITTER) {
+            const float* Y = y5 + ((long long)(b * N + n) * 5) * NPX + p;
+            lg = __ldcs(Y); jx1 = __ldcs(Y + NPX); jy1 = __ldcs(Y + 2 * NPX); jx0 = __ldcs(Y + 3 * NPX); jy0 = __ldcs(Y + 4 * NPX);
+        }
+        float acc[3] = {lg, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            Smp s = sample_pos(fl, b, x, y, n, f);
+            if (JITTER) {
+                float ix = fminf(fmaxf(s.x0 + s.wx + (f ? jx1 : jx0), 0.f), W - 1.001f), iy = fminf(fmaxf(s.y0 + s.wy + (f ? jy1 : jy0), 0.f), H - 1.001f);
+                s.x0 = (int)ix; s.y0 = (int)iy; s.wx = ix - s.x0; s.wy = iy - s.y0;
+            }
+            const int base = (b * 2 + f) * (int)NPX + s.y0 * W + s.x0;
+            const int off[4] = {0, 1, W, W + 1};
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (f * 4 + k < NT) v[k] = tex1Dfetch<float4>(lin, base + off[k]);
+                else v[k] = __ldg(img + base + off[k]);
+            }
+            acc[0] += lerp4(v[0].x, v[1].x, v[2].x, v[3].x, s.wx, s.wy); acc[1] += lerp4(v[0].y, v[1].y, v[2].y, v[3].y, s.wx, s.wy);
+            acc[2] += lerp4(v[0].z, v[1].z, v[2].z, v[3].z, s.wx, s.wy);
+        }
+        float* O = out + ((long long)(b * N + n) * NSTORE) * NPX + p;
+#pragma unroll
+        for (int k = 0; k < NSTORE; ++k) __stcs(O + (long long)k * NPX, acc[k % 3] + k);
+    }
+}
+
+static bool g_once = false;   // `exp_gather once`: one launch per variant, rough flow only (for ncu counters)
 template <typename F> float time_ms(F&& launch, int reps = 10) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    for (int i = 0; i < 3; ++i) launch();
+    if (g_once) reps = 1;
+    for (int i = 0; i < (g_once ? 0 : 3); ++i) launch();
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(a));
     for (int i = 0; i < reps; ++i) launch();
@@ -328,7 +403,8 @@ static double checksum(const float* d_out) {
     return s / NPX;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    g_once = argc > 1 && !strcmp(argv[1], "once");
     float *img, *flow, *out; float4 *p16, *p32;
     CK(cudaMalloc(&img, B * 6 * NPX * 4)); CK(cudaMalloc(&flow, B * 4 * NPX * 4)); CK(cudaMalloc(&out, B * NPX * 4));
     CK(cudaMalloc(&p16, B * 2 * NPX * 16)); CK(cudaMalloc(&p32, B * 2 * NPX * 32));
@@ -354,6 +430,13 @@ int main() {
     rd.res.array.array = arr1; CK(cudaCreateTextureObject(&tex1, &rd, &td, nullptr));
     rd.res.array.array = arr4; CK(cudaCreateTextureObject(&tex4, &rd, &td, nullptr));
 
+    cudaTextureObject_t texlin;
+    {
+        cudaResourceDesc rl = {}; rl.resType = cudaResourceTypeLinear; rl.res.linear.devPtr = p16; rl.res.linear.desc = d4;
+        rl.res.linear.sizeInBytes = (size_t)B * 2 * NPX * 16;
+        cudaTextureDesc tl = {}; tl.addressMode[0] = cudaAddressModeClamp; tl.filterMode = cudaFilterModePoint; tl.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&texlin, &rl, &tl, nullptr));
+    }
     // time the array upload paths too (what a pack pre-pass into an array would cost at best)
     float up1 = time_ms([&] { for (int l = 0; l < B * 6; ++l) CK(cudaMemcpy2DToArrayAsync(arr1, (l & 3) * W * 4, (l >> 2) * H, img + l * NPX, W * 4, W * 4, H, cudaMemcpyDeviceToDevice)); }, 3), up4 = time_ms([&] { CK(cudaMemcpy3DAsync(&cq)); }, 3);
     printf("{\"upload_r32f_layers_ms\": %.3f, \"upload_rgba32f_layers_ms\": %.3f}\n", up1, up4);
@@ -366,7 +449,7 @@ int main() {
     CK(cudaDeviceSynchronize());
     const double samples = (double)B * NPX * N * 2;
     const int grids[2] = {8, 64};
-    for (int gi = 0; gi < 2; ++gi) {
+    for (int gi = 0; gi < (g_once ? 1 : 2); ++gi) {
         make_flow<<<(B * 4 * NPX + T - 1) / T, T>>>(flow, grids[gi], 20.0f, 12345u);
         CK(cudaDeviceSynchronize());
         struct R { const char* name; float ms; double sum; };
@@ -375,6 +458,10 @@ int main() {
         run("nogather", [&] { k_nogather<0><<<grid, 256>>>(flow, out); });
         run("planar4", [&] { k_planar4<0><<<grid, 256>>>(img, flow, out); });
         run("rgbx16", [&] { k_rgbx16<0><<<grid, 256>>>(p16, flow, out); });
+        run("bank_samecol", [&] { k_bank<0><<<grid, 256>>>(p16, out); });
+        run("bank_diag", [&] { k_bank<1><<<grid, 256>>>(p16, out); });
+        run("bank_row", [&] { k_bank<2><<<grid, 256>>>(p16, out); });
+        run("rgbx16cg", [&] { k_rgbx16cg<<<grid, 256>>>(p16, flow, out); });
         run("lanepair", [&] { k_lanepair<<<grid, 256>>>(p16, flow, out); });
         run("pair32", [&] { k_pair32<0><<<grid, 256>>>(p32, flow, out); });
         run("planar4_b84", [&] { k_planar4<1><<<grid, 256>>>(img, flow, out); });
@@ -391,6 +478,10 @@ int main() {
         run("k1like_texw" #TW, [&] { k_like<TW, 16, false><<<grid, 256>>>(tex1, p16, flow, y5, big); });
         run("k2like_lanepair", [&] { k_like_lp<3, true><<<grid, 256>>>(p16, flow, y5, big); });
         run("k1like_lanepair", [&] { k_like_lp<16, false><<<grid, 256>>>(p16, flow, y5, big); });
+#define MIXLIN(NT) \
+        run("k2like_mixlin" #NT, [&] { k_like_mixlin<NT, 3, true><<<grid, 256>>>(texlin, p16, flow, y5, big); }); \
+        run("k1like_mixlin" #NT, [&] { k_like_mixlin<NT, 16, false><<<grid, 256>>>(texlin, p16, flow, y5, big); });
+        MIXLIN(0) MIXLIN(1) MIXLIN(2) MIXLIN(3) MIXLIN(4) MIXLIN(8)
         LIKE(0) LIKE(2) LIKE(3) LIKE(4) LIKE(5) LIKE(6) LIKE(8)
         for (auto& r : rs)
             printf("{\"flow_grid\": \"1/%d\", \"variant\": \"%s\", \"ms\": %.3f, \"ns_per_warp_sample\": %.2f, \"cyc_per_warp_sample_per_sm\": %.1f, \"checksum\": %.6f}\n",

@@ -8,18 +8,19 @@ reference tree is absent.  Layer names and shapes follow the reference so that i
   stage 1  scripts/models/flow_computation.py:27-153   6 -> 4 channels (F01, F10)
   stage 2  scripts/models/flow_interpolation.py:27-157 16 -> 5 channels; conv7a takes 1024 channels
            when the stage-1 bottleneck is concatenated in (cross-stage skip, :98-101, :224-228)
-Only the CONV bottleneck is built here; the ConvLSTM / ConvGRU bottlenecks of the recurrent
-configuration are the reference's CLSTM submodule (out of scope) and can be passed in as `conv6`.
+The bottleneck is CONV (superslomo_original.ini) or the bidirectional ConvLSTM / ConvGRU of the recurrent
+configuration (superslomo_recurrent.ini:97,105; recurrent.py).
 
-Unlike the reference, which loops over the T windows in Python (flow_computation.py:303-325), a CONV
-bottleneck has no coupling between windows, so the T axis is folded into the batch and each layer
-runs once.
+Unlike the reference, which loops over the T windows in Python (flow_computation.py:303-325), encoder and
+decoder have no coupling between windows, so the T axis is folded into the batch and each layer runs once;
+only a recurrent bottleneck sees the windows of a sample as a sequence (B x T x 512 x H/32 x W/32).
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .layers import avg_pool, conv
+from .recurrent import BiConvRecurrent
 
 # (name, in, out, kernel) of the encoder / decoder convolutions
 _ENCODER = [("conv1a", None, 32, 7), ("conv1b", 32, 32, 7), ("conv2a", 32, 64, 5), ("conv2b", 64, 64, 5),
@@ -39,17 +40,23 @@ class FlowUNet(nn.Module):
     returns a list of T (encoding-or-None, output) tuples for stage 1 and a list of T outputs for
     stage 2, like the reference models."""
 
-    def __init__(self, in_channels, out_channels, stage, cross_skip=False, conv6=None):
+    def __init__(self, in_channels, out_channels, stage, cross_skip=False, conv6=None, bottleneck="CONV"):
         super().__init__()
         assert stage in (1, 2)
+        assert bottleneck in ("CONV", "CLSTM", "CGRU"), "BOTTLENECK must be CONV, CLSTM or CGRU"
         self.stage = stage
+        self.bottleneck_type = bottleneck
         self.cross_skip_connect = bool(cross_skip)
         for name, cin, cout, k in _ENCODER:
             setattr(self, name, conv(in_channels if cin is None else cin, cout, kernel_size=k, padding=k // 2))
         for i in range(2, 7):
             setattr(self, "pool%d" % i, avg_pool(kernel_size=2))
-        self.conv6 = conv6 if conv6 is not None else nn.Sequential(conv(512, 512, kernel_size=3),
-                                                                   conv(512, 512, kernel_size=3))
+        if conv6 is not None:
+            self.conv6 = conv6
+        elif bottleneck == "CONV":
+            self.conv6 = nn.Sequential(conv(512, 512, kernel_size=3), conv(512, 512, kernel_size=3))
+        else:                                              # flow_computation.py:73-88, flow_interpolation.py:73-88
+            self.conv6 = BiConvRecurrent("lstm" if bottleneck == "CLSTM" else "gru", 512, 512, (3, 3), num_layers=2)
         for name, cin, cout, k in _DECODER:
             if cin is None:
                 cin = 1024 if (stage == 2 and self.cross_skip_connect) else 512
@@ -88,15 +95,21 @@ class FlowUNet(nn.Module):
         x = self.fuse_conv(torch.cat([x, skips[0]], dim=1))
         return self.final_conv(x)
 
-    def forward_flat(self, x, enc_stage1=None):
-        """x: M x C x H x W (windows/timesteps already folded into M) -> (bottleneck M x 512 x H/32 x W/32,
-        output M x C_out x H x W)."""
+    def forward_flat(self, x, enc_stage1=None, windows=1):
+        """x: M x C x H x W (windows/timesteps already folded into M, windows fastest) -> (bottleneck
+        M x 512 x H/32 x W/32, output M x C_out x H x W).  `windows` = T: a recurrent bottleneck runs over the
+        M/T sequences of T windows."""
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
             if enc_stage1 is not None:
                 enc_stage1 = enc_stage1.contiguous(memory_format=torch.channels_last)
         skips, pooled = self._encode(x)
-        h = self.conv6(pooled)
+        if isinstance(self.conv6, BiConvRecurrent):
+            h = self.conv6(pooled.view(-1, windows, *pooled.shape[1:])).reshape(pooled.shape[0], -1, *pooled.shape[2:])
+            if self.channels_last:
+                h = h.contiguous(memory_format=torch.channels_last)
+        else:
+            h = self.conv6(pooled)
         out = self._decode(h, skips, enc_stage1)
         # the synthesis kernels read planar NCHW: hand the (4- or 5-channel) result back in that layout
         return h, (out.contiguous() if self.channels_last else out)
@@ -107,7 +120,7 @@ class FlowUNet(nn.Module):
         enc = None
         if self.stage == 2 and self.cross_skip_connect:
             enc = torch.stack(list(stage1_encoder_output), dim=1).reshape(B * T, *stage1_encoder_output[0].shape[1:])
-        h, out = self.forward_flat(x, enc)
+        h, out = self.forward_flat(x, enc, windows=T)
         out = out.view(B, T, *out.shape[1:])
         if self.stage == 2:
             return [out[:, w] for w in range(T)]
@@ -118,10 +131,10 @@ class FlowUNet(nn.Module):
 def get_model(path, in_channels, out_channels, cross_skip, verbose=False, stage=1, cfg=None):
     """Factory with the reference's signature (scripts/models/unetflow.py:11-32)."""
     section = "STAGE%d" % stage
-    if cfg is not None and cfg.has_option(section, "BOTTLENECK") and cfg.get(section, "BOTTLENECK") != "CONV":
-        raise NotImplementedError("only the CONV bottleneck is built here; pass the reference's ConvBLSTM/ConvBGRU "
-                                  "module as FlowUNet(conv6=...) for the recurrent configuration")
-    model = FlowUNet(in_channels, out_channels, stage, cross_skip)
+    bottleneck = "CONV"
+    if cfg is not None and cfg.has_option(section, "BOTTLENECK"):
+        bottleneck = cfg.get(section, "BOTTLENECK")
+    model = FlowUNet(in_channels, out_channels, stage, cross_skip, bottleneck=bottleneck)
     if path is not None:
         data = torch.load(path, map_location="cpu")
         key = "stage%s_state_dict" % stage

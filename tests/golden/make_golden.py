@@ -125,8 +125,12 @@ if __name__ == "__main__":
 
 
 # ---- the model loop (rows a6-a8): the reference's FullModel run on CPU ---------------------------
-def run_loop_case(name, n_frames, seed):
-    """Runs scripts/models/superslomo_r.py::FullModel (CONV bottleneck, random-init U-Nets from a
+BOTTLENECK_CODE = {"CONV": 0, "CLSTM": 1, "CGRU": 2}
+
+
+def run_loop_case(name, n_frames, seed, ini="superslomo_original.ini", bottleneck=None):
+    """Runs scripts/models/superslomo_r.py::FullModel (bottleneck from the .ini -- CONV for
+    superslomo_original.ini, CLSTM for superslomo_recurrent.ini -- or overridden; random-init U-Nets from a
     fixed seed, LAMBDA_P = 0 because the VGG weights cannot be downloaded) in inference and training
     mode on CPU.  The reference hard-codes .cuda() (superslomo_r.py:211); Tensor.cuda is patched to
     the identity for this run only.  U-Net weights are NOT stored (155 MB): tests rebuild them from
@@ -136,10 +140,12 @@ def run_loop_case(name, n_frames, seed):
     from models import superslomo_r as ref_model
 
     cfg = configparser.RawConfigParser()
-    cfg.read("/root/reference/configs/superslomo_original.ini")
+    cfg.read("/root/reference/configs/" + ini)
     for sec in ("STAGE1", "STAGE2"):
         cfg.set(sec, "LOADPREV", "FALSE")
         cfg.set(sec, "FREEZE", "FALSE")
+        if bottleneck is not None:
+            cfg.set(sec, "BOTTLENECK", bottleneck)
     cfg.set("TRAIN", "LAMBDA_P", "0")
     cfg.set("TRAIN", "N_FRAMES", str(n_frames))
     real_vgg, real_cuda = torchvision.models.vgg16, torch.Tensor.cuda
@@ -162,7 +168,7 @@ def run_loop_case(name, n_frames, seed):
         torchvision.models.vgg16, torch.Tensor.cuda = real_vgg, real_cuda
     rec = {"frames": frames, "targets": targets, "t": t.reshape(B, n_frames - 1), "est": est,
            "losses": losses.detach(), "est_train": est_tr.detach(), "grad_stage1_final": g1, "grad_stage2_final": g2,
-           "seed": torch.tensor(seed)}
+           "seed": torch.tensor(seed), "bottleneck": torch.tensor(BOTTLENECK_CODE[cfg.get("STAGE1", "BOTTLENECK")])}
     for i, e in enumerate(extras):
         rec["extra%d" % i] = e
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.detach().numpy() for k, v in rec.items()})
@@ -172,3 +178,31 @@ def run_loop_case(name, n_frames, seed):
 if __name__ == "__main__":
     run_loop_case("loop_frames2", 2, seed=4242)
     run_loop_case("loop_frames4", 4, seed=4343)
+    # the recurrent configuration (C4): bidirectional ConvLSTM bottleneck over the 3 windows of 4 frames, and the
+    # ConvGRU alternative the reference also builds (flow_computation.py:81-88)
+    run_loop_case("loop_ssmr4_clstm", 4, seed=4444, ini="superslomo_recurrent.ini")
+    run_loop_case("loop_ssmr3_cgru", 3, seed=4545, ini="superslomo_recurrent.ini", bottleneck="CGRU")
+
+
+# ---- checkpoint layout: state_dict keys and shapes of the reference U-Nets, per bottleneck -------------------
+def dump_state_dict_layout():
+    """tests/golden/state_dict_layout.json: {bottleneck: {stage: [[key, shape], ...]}} of the reference's
+    FlowComputationModel / FlowInterpolationModel (scripts/models/unetflow.py:11-32), so that the in-tree
+    U-Nets can be checked to load the author's checkpoints key for key."""
+    import configparser
+    import json
+    from models import unetflow
+
+    out = {}
+    for bottleneck in ("CONV", "CLSTM", "CGRU"):
+        cfg = configparser.RawConfigParser()
+        cfg.read("/root/reference/configs/superslomo_recurrent.ini")
+        for sec in ("STAGE1", "STAGE2"):
+            cfg.set(sec, "BOTTLENECK", bottleneck)
+        out[bottleneck] = {}
+        for stage, (cin, cout) in ((1, (6, 4)), (2, (16, 5))):
+            model = unetflow.get_model(None, cin, cout, True, stage=stage, cfg=cfg)
+            out[bottleneck]["stage%d" % stage] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    with open(os.path.join(HERE, "state_dict_layout.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("state_dict_layout.json:", {b: {s: len(v) for s, v in d.items()} for b, d in out.items()})

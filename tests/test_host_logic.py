@@ -178,6 +178,37 @@ def test_checkpoint_layout_round_trip(tmp_path):
         assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("bottleneck", ["CONV", "CLSTM", "CGRU"])
+def test_state_dict_layout_matches_reference(bottleneck):
+    """The in-tree U-Nets carry the reference's parameter names and shapes key for key, for every bottleneck the
+    reference builds (tests/golden/state_dict_layout.json, dumped from the reference's own models by
+    tests/golden/make_golden.py::dump_state_dict_layout): the author's checkpoints load unchanged."""
+    import json
+    import os
+    from ssm_b200 import unets
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "state_dict_layout.json")) as f:
+        want = json.load(f)[bottleneck]
+    with torch.device("meta"):
+        models = {"stage1": unets.FlowUNet(6, 4, 1, True, bottleneck=bottleneck),
+                  "stage2": unets.FlowUNet(16, 5, 2, True, bottleneck=bottleneck)}
+    for stage, m in models.items():
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == want[stage], stage
+
+
+def test_get_model_reads_bottleneck_from_cfg():
+    import configparser
+    from ssm_b200 import recurrent, unets
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("[STAGE1]\nBOTTLENECK=CGRU\n[STAGE2]\nBOTTLENECK=CONV\n")
+    with torch.device("meta"):
+        assert isinstance(unets.get_model(None, 6, 4, True, stage=1, cfg=cfg).conv6, recurrent.BiConvRecurrent)
+        assert not isinstance(unets.get_model(None, 16, 5, True, stage=2, cfg=cfg).conv6, recurrent.BiConvRecurrent)
+        cfg.set("STAGE2", "BOTTLENECK", "TRANSFORMER")
+        with pytest.raises(AssertionError):
+            unets.get_model(None, 16, 5, True, stage=2, cfg=cfg)
+
+
 def test_numa_placement_helper(tmp_path, monkeypatch):
     """numa_local_to_gpu: binds to the GPU-local CPUs that the process may use, restores on exit, and is a
     no-op without topology information."""

@@ -30,8 +30,8 @@ def _exact_convs():
     ssm_b200.set_coord_mode("cpu")
 
 
-def _model(seed):
-    s1, s2 = seeded_unets(seed, DEV)
+def _model(seed, bottleneck="CONV"):
+    s1, s2 = seeded_unets(seed, DEV, bottleneck=bottleneck)
     return FullModel(cfg=None, stage1_model=s1, stage2_model=s2,
                      loss=ssm_b200.losses.SSMLosses(lambda_r=60.0, lambda_p=0.0, lambda_w=10.0))
 
@@ -43,7 +43,7 @@ def test_fullmodel_vs_reference_golden(name):
     comparison is at 1e-4, not at the hot path's 1e-5."""
     d = load_golden(name)
     ssm_b200.set_coord_mode("cpu")
-    m = _model(d["seed"].item())
+    m = _model(d["seed"].item(), d.get("bottleneck", 0))
     frames, t = d["frames"].to(DEV), d["t"].to(DEV)
     t5 = t.view(*t.shape, 1, 1, 1)
     with torch.no_grad():
@@ -94,13 +94,16 @@ def test_fullmodel_vs_reference_loop_on_device(n_frames):
         assert max_err(p1.grad, p2.grad) <= 1e-3 * scale, "stage-2 grad %s" % n1
 
 
-@pytest.mark.parametrize("n_frames,n_t,chunk", [(2, 7, None), (2, 7, 3), (4, 3, None)])
-def test_interpolate_vs_per_timestep_reference_loop(n_frames, n_t, chunk):
+@pytest.mark.parametrize("n_frames,n_t,chunk,bottleneck", [(2, 7, None, "CONV"), (2, 7, 3, "CONV"), (4, 3, None, "CONV"),
+                                                           (4, 7, None, "CLSTM"), (4, 3, 2, "CGRU")])
+def test_interpolate_vs_per_timestep_reference_loop(n_frames, n_t, chunk, bottleneck):
     """interpolate(): stage 1 once, all N times per launch, vs the reference's loop that calls the
-    whole model once per intermediate time (evaluate_interpolation_results.py:234-242)."""
+    whole model once per intermediate time (evaluate_interpolation_results.py:234-242).  CLSTM / CGRU: the
+    recurrent configuration (C4, superslomo_recurrent.ini) -- the bottleneck couples the 3 windows of a sample, the
+    N times are folded into the batch next to them."""
     B, H, W = 2, 64, 96
     ssm_b200.set_coord_mode("cuda")
-    m = _model(99)
+    m = _model(99, bottleneck)
     frames = synthetic.frames(B, H, W, n_frames=n_frames, seed=15).view(B, n_frames, 3, H, W).to(DEV)
     torch.backends.cudnn.enabled = False
     tv = torch.arange(1, n_t + 1, dtype=torch.float32) / (n_t + 1)

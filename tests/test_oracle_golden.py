@@ -99,7 +99,10 @@ def test_loop_oracle_matches_reference_fullmodel(name):
     against the reference's own FullModel run on CPU (tests/golden/make_golden.py::run_loop_case).
     Also pins that the in-tree U-Nets rebuild the reference's weights from the seed."""
     d = load_golden(name)
-    s1, s2 = seeded_unets(d["seed"].item())
+    s1, s2 = seeded_unets(d["seed"].item(), bottleneck=d.get("bottleneck", 0))
+    for m in (s1, s2):              # recurrent bottleneck: the reference's joint gate convolution, for its rounding
+        if hasattr(m.conv6, "split_input"):
+            m.conv6.split_input = False
     t = d["t"].view(*d["t"].shape, 1, 1, 1)
     with torch.no_grad():
         est, extras = torch_oracle.model_forward(s1, s2, d["frames"], t)
@@ -113,6 +116,22 @@ def test_loop_oracle_matches_reference_fullmodel(name):
     losses.mean(dim=0)[0].backward()
     assert_close_fp32(s1.final_conv.weight.grad, d["grad_stage1_final"], "stage-1 final_conv grad", tol=1e-5)
     assert_close_fp32(s2.final_conv.weight.grad, d["grad_stage2_final"], "stage-2 final_conv grad", tol=1e-5)
+
+
+@pytest.mark.parametrize("name", [n for n in loop_cases() if "ssmr" in n])
+def test_recurrent_bottleneck_split_gate_convolution(name):
+    """The batched-input form of the ConvLSTM / ConvGRU bottleneck (recurrent.py: input half of every gate
+    convolution run once over all windows) against the reference's FullModel: same weights, same result up to
+    the summation order inside the convolutions."""
+    d = load_golden(name)
+    s1, s2 = seeded_unets(d["seed"].item(), bottleneck=d["bottleneck"])
+    assert s1.conv6.split_input and s2.conv6.split_input
+    t = d["t"].view(*d["t"].shape, 1, 1, 1)
+    with torch.no_grad():
+        est, extras = torch_oracle.model_forward(s1, s2, d["frames"], t)
+    assert_close_fp32(est, d["est"], "inference frame", tol=1e-4)
+    for i, e in enumerate(extras):
+        assert_close_fp32(e, d["extra%d" % i], "inference extra %d" % i, tol=1e-4)
 
 
 # ---- pre/post frame steps (SURVEY 8(f) rank 3): restatements pinned to the reference's own methods --------

@@ -27,13 +27,18 @@ def loop_cases():
                   if n.startswith("loop_"))
 
 
-def seeded_unets(seed, device="cpu"):
+BOTTLENECKS = ("CONV", "CLSTM", "CGRU")     # tests/golden/make_golden.py::BOTTLENECK_CODE
+
+
+def seeded_unets(seed, device="cpu", bottleneck="CONV"):
     """The two U-Nets with the weights the golden generator's reference FullModel had: same seed,
     same construction order (stage 1 then stage 2), same state_dict keys."""
     from ssm_b200 import unets
     torch.manual_seed(int(seed))
-    s1 = unets.FlowUNet(6, 4, 1, cross_skip=True)
-    s2 = unets.FlowUNet(16, 5, 2, cross_skip=True)
+    if not isinstance(bottleneck, str):                      # the code stored in a loop fixture (absent = CONV)
+        bottleneck = BOTTLENECKS[int(bottleneck)]
+    s1 = unets.FlowUNet(6, 4, 1, cross_skip=True, bottleneck=bottleneck)
+    s2 = unets.FlowUNet(16, 5, 2, cross_skip=True, bottleneck=bottleneck)
     return s1.to(device), s2.to(device)
 
 

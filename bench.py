@@ -211,6 +211,26 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def whole_model_step(timeout_s=300):
+    """tools/pipeline_step.py in a child process: uint8 host frames -> both U-Nets (stock torch/cuDNN, random init,
+    channels-last + bf16 autocast; out of scope) + the path -> uint8 host frames, 2 pairs x 7 timesteps at 1080p.
+    Reported next to the headline so that the share of the path in a whole step is visible; never the headline."""
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "pipeline_step.py")
+    try:
+        out = subprocess.run([sys.executable, tool, "--amp", "--channels-last", "--steps", "3", "--warmup", "2"],
+                             capture_output=True, text=True, timeout=timeout_s)
+        d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        keep = ("pairs", "timesteps", "height", "width", "amp_bf16_unets", "channels_last_unets", "ms_per_step",
+                "frames_per_s", "h2d_bytes_per_step", "d2h_bytes_per_step", "path_kernels_ms", "path_ms_total",
+                "path_share_of_step")
+        res = {k: d[k] for k in keep if k in d}
+        res["note"] = ("whole inference step incl. both U-Nets (stock torch/cuDNN, random init, out of scope): uint8 host "
+                       "frames in, uint8 host frames out; context for the headline, not a bench value")
+        return res
+    except Exception as e:       # context only: never fail the bench line over it
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,6 +500,11 @@ def main():
                                   "(oracle/torch_oracle.py == the reference's op sequence)" % (NT, H, W),
                         "ms_per_frame": 1e3 * best / frames_c}
 
+    # ---- context, not the headline: where the path sits in a whole inference step with the two U-Nets ------------
+    whole_model = None
+    if rank == 0 and world == 1 and not args.no_variants:
+        whole_model = whole_model_step()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
@@ -491,7 +516,7 @@ def main():
                        "parallelism": "pairs sharded over %d rank(s), no collective" % world},
             "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth,
             "smooth_flow_and_unet_output_variant": smooth_res, "bf16_storage_variant": bf16, "unet_layouts_variant": layouts,
-            "cpu_baseline": cpu_baseline,
+            "whole_model_context": whole_model, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line))

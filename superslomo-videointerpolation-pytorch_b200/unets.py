@@ -32,6 +32,13 @@ _DECODER = [("conv7a", None, 512, 3), ("conv7b", 512, 512, 3), ("conv8a", 1024, 
 
 
 def _up2(x):
+    """2x bilinear upsampling (flow_computation.py:92-94).  CUDA autocast lists upsample_bilinear2d as an fp32 op:
+    left alone it casts a bf16 activation up, interpolates and writes fp32 -- 38 % of a whole 1080p inference step
+    (profiles/r01s_pipeline_profile.txt) -- and the next convolution casts the result down again.  The activation
+    stays in the dtype the convolutions produced (ATen accumulates the four taps in fp32 either way)."""
+    if x.is_cuda and x.dtype != torch.float32 and torch.is_autocast_enabled("cuda"):
+        with torch.autocast("cuda", enabled=False):
+            return F.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear", align_corners=False)
     return F.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear", align_corners=False)
 
 

@@ -44,7 +44,10 @@ def main():
     ap.add_argument("--generic-plumbing", action="store_true",
                     help="planar fp32 tensors either side of the stage-2 U-Net even when it runs channels-last / autocast "
                          "(default: compute_inputs writes the channels-last [bf16] tensor conv1a consumes)")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN time its algorithms per shape")
+    ap.add_argument("--profile", default=None, help="write the kernel table of one step (torch.profiler) to this file")
     a = ap.parse_args()
+    torch.backends.cudnn.benchmark = a.cudnn_benchmark
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N, h_in, w_in = a.pairs, a.timesteps, a.height, a.width
@@ -144,10 +147,18 @@ def main():
     for n, s, e in spans:
         path_ms[n] = path_ms.get(n, 0.0) + s.elapsed_time(e)
 
+    if a.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof, torch.no_grad():
+            device_part()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
+
     print(json.dumps({
         "what": "end-to-end inference step with the U-Nets (uint8 host frames -> uint8 host frames), not the bench headline",
         "pairs": B, "timesteps": N, "height": h_in, "width": w_in, "unet_chunk": a.unet_chunk,
-        "amp_bf16_unets": a.amp, "channels_last_unets": a.channels_last, "cuda_graph": a.graph,
+        "amp_bf16_unets": a.amp, "channels_last_unets": a.channels_last, "cuda_graph": a.graph, "cudnn_benchmark": a.cudnn_benchmark,
         "unet_layouts": bool(model.unet_layouts and a.channels_last),
         "ms_per_step": ms, "frames_per_s": B * N / (ms * 1e-3), "checksum": checksum,
         "h2d_bytes_per_step": h_u8.numel(), "d2h_bytes_per_step": h_out.numel(),

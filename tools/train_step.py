@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--n-frames", type=int, default=2, help="2 = SuperSloMo original (one window), 4 = SSMR windows")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the U-Nets (the path stays fp32)")
     ap.add_argument("--channels-last", action="store_true", help="NHWC U-Nets (cuDNN tensor-core kernels)")
+    ap.add_argument("--bottleneck", default="CONV", choices=["CONV", "CLSTM", "CGRU"],
+                    help="U-Net bottleneck: CONV = superslomo_original.ini, CLSTM = superslomo_recurrent.ini (use --n-frames 4)")
     a = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,7 +51,10 @@ def main():
     B, S, T = a.global_batch // world, a.size, a.n_frames
 
     torch.manual_seed(42)                       # same initial weights on every rank (configs/*.ini [SEED])
-    model = FullModel(cfg=None, loss=ssm_b200.losses.SSMLosses(lambda_r=60.0, lambda_p=0.0, lambda_w=10.0)).to(dev)
+    import configparser
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("[STAGE1]\nBOTTLENECK=%s\n[STAGE2]\nBOTTLENECK=%s\nCROSS_SKIP=TRUE\n" % (a.bottleneck, a.bottleneck))
+    model = FullModel(cfg=cfg, loss=ssm_b200.losses.SSMLosses(lambda_r=60.0, lambda_p=0.0, lambda_w=10.0)).to(dev)
     if a.channels_last:
         model.stage1_model.set_channels_last()
         model.stage2_model.set_channels_last()
@@ -121,7 +126,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "what": "data-parallel training step (synthetic crops, random-init U-Nets)", "n_gpus": world,
-            "global_batch": a.global_batch, "per_gpu_batch": B, "crop": S, "n_frames": T, "amp_bf16_unets": a.amp, "channels_last_unets": a.channels_last,
+            "global_batch": a.global_batch, "per_gpu_batch": B, "crop": S, "n_frames": T, "bottleneck": a.bottleneck, "amp_bf16_unets": a.amp, "channels_last_unets": a.channels_last,
             "ms_per_step": ms, "samples_per_s": a.global_batch / (ms * 1e-3), "loss": float(loss.detach()),
             "unet_parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
             "path_kernels_ms": path_ms, "path_ms_total": sum(path_ms.values()),

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 4
+#define SSM_ABI_VERSION 5
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -220,6 +220,21 @@ int ssm_frames_from_u8(const unsigned char* src, long long src_frame_stride, int
 int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int left, int H_out, int W_out,
                      const float* mean3, const float* std3, float scale, int bgr, int saturate,
                      unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int dtype, void* stream);
+
+/* ---- element-wise steps between the U-Nets' cuDNN convolutions -------
+ * Channels-last activations (M x H x W x C, C a multiple of 8, 16-byte aligned), bf16 or fp32 storage, fp32
+ * arithmetic in ATen's operation order; forward only (inference).  The convolutions stay on cuDNN.
+ * ssm_upsample2x_nhwc: F.interpolate(x, size=(2H, 2W), mode="bilinear", align_corners=False), the upsampleN
+ *   lambdas of [scripts/models/flow_computation.py:92-94, 102-104, 112-114, 122-124, 132-134] and
+ *   [flow_interpolation.py:92-139].  `out` may be a channel slice of a wider tensor (out_pixel_stride >= C
+ *   elements between pixels), which absorbs the torch.cat in front of the upsampling.
+ * ssm_bias_leaky_nhwc: y <- LeakyReLU(y + bias[c], slope) in place, the bias add and activation of
+ *   layers.conv [scripts/models/layers.py:21-33]; bias: DEVICE float[C]; pixels = M*H*W.
+ * ssm_avgpool2_nhwc: AvgPool2d(2) [scripts/models/layers.py:60-63]: in M x 2H_out x 2W_out x C. */
+int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, long long out_pixel_stride,
+                        int dtype, void* stream);
+int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream);
+int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, int C, int dtype, void* stream);
 
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
  * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */

@@ -6,6 +6,7 @@
 
 #include "ssm_frames.cuh"
 #include "ssm_scatter.cuh"
+#include "ssm_unet_glue.cuh"
 
 namespace {
 
@@ -666,6 +667,61 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
         frames_to_u8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(cview<__nv_bfloat16>(planar), H, W, top, left, H_out, W_out, mean3[0], mean3[1], mean3[2],
             std3[0], std3[1], std3[2], scale, bgr != 0, saturate != 0, dst, dst_frame_stride, dst_row_stride, total);
     SSM_LAUNCH_CHECK("ssm_frames_to_u8");
+    return SSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Element-wise steps between the U-Nets' cuDNN convolutions (channels-last activations, inference)
+static int check_glue(const char* who, const void* a, const void* b, long long count, int C, int dtype) {
+    if (!a || !b) return fail(SSM_ERR_NULL, "%s: NULL pointer", who);
+    if (count <= 0 || C <= 0) return fail(SSM_ERR_SHAPE, "%s: sizes must be positive", who);
+    if (C % 8 != 0) return fail(SSM_ERR_SHAPE, "%s: C must be a multiple of 8 (got %d)", who, C);
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
+    if (((uintptr_t)a | (uintptr_t)b) % 16 != 0) return fail(SSM_ERR_ALIGN, "%s: pointers must be 16-byte aligned", who);
+    if ((count * (C / 8) + 255) / 256 > 2147483647ll) return fail(SSM_ERR_SHAPE, "%s: too large for one launch", who);
+    return SSM_OK;
+}
+
+int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, long long out_pixel_stride, int dtype, void* stream) {
+    if (M <= 0 || H <= 0 || W <= 0) return fail(SSM_ERR_SHAPE, "ssm_upsample2x_nhwc: M, H, W must be positive");
+    SSM_TRY(check_glue("ssm_upsample2x_nhwc", in, out, (long long)M * H * W, C, dtype));
+    if (out_pixel_stride < C || out_pixel_stride % 8 != 0)
+        return fail(SSM_ERR_SHAPE, "ssm_upsample2x_nhwc: out_pixel_stride must be a multiple of 8 and >= C");
+    const long long total = (long long)M * H * W * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        upsample2x_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, H, W, C / 8, out_pixel_stride, total);
+    else
+        upsample2x_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, H, W, C / 8, out_pixel_stride, total);
+    SSM_LAUNCH_CHECK("ssm_upsample2x_nhwc");
+    return SSM_OK;
+}
+
+int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream) {
+    SSM_TRY(check_glue("ssm_bias_leaky_nhwc", y, bias, pixels, C, dtype));
+    const long long total = pixels * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        bias_leaky_nhwc_kernel<float><<<grid, 256, 0, s>>>((float*)y, bias, C / 8, slope, total);
+    else
+        bias_leaky_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)y, bias, C / 8, slope, total);
+    SSM_LAUNCH_CHECK("ssm_bias_leaky_nhwc");
+    return SSM_OK;
+}
+
+int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, int C, int dtype, void* stream) {
+    if (M <= 0 || H_out <= 0 || W_out <= 0) return fail(SSM_ERR_SHAPE, "ssm_avgpool2_nhwc: M, H_out, W_out must be positive");
+    SSM_TRY(check_glue("ssm_avgpool2_nhwc", in, out, (long long)M * H_out * W_out, C, dtype));
+    const long long total = (long long)M * H_out * W_out * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        avgpool2_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, H_out, W_out, C / 8, total);
+    else
+        avgpool2_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, H_out, W_out, C / 8, total);
+    SSM_LAUNCH_CHECK("ssm_avgpool2_nhwc");
     return SSM_OK;
 }
 

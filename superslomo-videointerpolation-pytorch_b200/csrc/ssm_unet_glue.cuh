@@ -1,0 +1,148 @@
+// ssm_unet_glue.cuh -- element-wise steps BETWEEN the cuDNN convolutions of the two flow U-Nets, for
+// channels-last (N x H x W x C) activations in bf16 or fp32 (sm_100a).  Inference only.
+//
+// The convolutions themselves stay on PyTorch / cuDNN (the one dense contraction of the system).  A whole
+// 1080p inference step, however, spends only 26 % of its time in them (profiles/r01s_pipeline_profile.txt):
+// ATen's channels-last bilinear upsampling kernel takes 38 % (1.7 ms per call, ~10x off its bandwidth
+// bound), the separate bias add after every convolution 12 %, LeakyReLU 3 %, average pooling 6 %.  These
+// three kernels do the same arithmetic as the ATen ops they replace, in the same order, at HBM speed:
+//
+//   upsample2x_nhwc_kernel   F.interpolate(x, size=(2H, 2W), mode="bilinear", align_corners=False)
+//                            reference: the lambda upsampleN of scripts/models/flow_computation.py:92-94, 102-104, ...
+//   bias_leaky_nhwc_kernel   conv bias add + LeakyReLU(0.1)      reference: layers.conv, scripts/models/layers.py:21-33
+//   avgpool2_nhwc_kernel     AvgPool2d(2)                        reference: layers.avg_pool, scripts/models/layers.py:60-63
+//
+// One thread owns 8 consecutive channels (16 B in bf16, 32 B in fp32) of one pixel, so a warp moves 512 /
+// 1024 contiguous bytes per access; all arithmetic is fp32 (ATen's accscalar_t), rounded once on store.
+#pragma once
+#include "ssm_device.cuh"
+
+namespace ssm {
+
+struct Vec8 { float v[8]; };
+
+template <typename T> __device__ __forceinline__ Vec8 ld8(const T* p);
+template <> __device__ __forceinline__ Vec8 ld8<float>(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    Vec8 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <> __device__ __forceinline__ Vec8 ld8<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    Vec8 r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r.v[2 * k] = __uint_as_float(w[k] << 16); r.v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+    return r;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const Vec8& r);
+template <> __device__ __forceinline__ void st8<float>(float* p, const Vec8& r) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(r.v[4], r.v[5], r.v[6], r.v[7]));
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const Vec8& r) {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * k], r.v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+}
+
+// in: M x H x W x C   out: M x 2H x 2W x CO (channels 0..C-1 of each pixel).  One thread = 8 channels of one INPUT pixel (y, x): it reads the 3x3
+// neighbourhood rows {max(y-1,0), y, min(y+1,H-1)} x columns {max(x-1,0), x, min(x+1,W-1)} and writes the 2x2
+// output block (2y..2y+1, 2x..2x+1).  ATen (UpSampleBilinear2d.cu) takes, per output index o, the source index
+// s = max(0.5*(o + 0.5) - 0.5, 0), the taps i1 = int(s) and i1 + (i1 < size-1), and the weights (1 - l, l) with
+// l = s - i1:   o = 2i, i >= 1: taps (i-1, i), weights (0.25, 0.75);   o = 0: taps (0, min(1, size-1)), weights (1, 0);
+//               o = 2i+1:      taps (i, min(i+1, size-1)), weights (0.75, 0.25);
+// and sums  h0*(w0*a + w1*b) + h1*(w0*c + w1*d)  in fp32 -- the same expression, in the same order, here.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C8, long long CO, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const long long m = r / H;
+    const int C = C8 * 8;
+    const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
+    const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
+    const T* base = in + (m * H * (long long)W) * C + c8 * 8;
+    Vec8 A[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) A[a][b] = ld8<T>(base + ((long long)ys[a] * W + xs[b]) * C);
+    const bool x0 = x == 0, y0 = y == 0;
+    const float we0 = x0 ? 1.0f : 0.25f, we1 = x0 ? 0.0f : 0.75f;     // even output column
+    const float he0 = y0 ? 1.0f : 0.25f, he1 = y0 ? 0.0f : 0.75f;     // even output row
+    Vec8 o00, o01, o10, o11;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float He[3], Ho[3];                                            // horizontal sums of the three rows
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float right_e = x0 ? A[a][2].v[k] : A[a][1].v[k];    // even column: taps (x-1, x), at x = 0: (0, 1)
+            He[a] = we0 * A[a][0].v[k] + we1 * right_e;
+            Ho[a] = 0.75f * A[a][1].v[k] + 0.25f * A[a][2].v[k];       // odd column: taps (x, x+1)
+        }
+        const float bot_e = y0 ? He[2] : He[1], bot_o = y0 ? Ho[2] : Ho[1];   // even row: rows (y-1, y), at y = 0: (0, 1)
+        o00.v[k] = he0 * He[0] + he1 * bot_e;
+        o01.v[k] = he0 * Ho[0] + he1 * bot_o;
+        o10.v[k] = 0.75f * He[1] + 0.25f * He[2];                      // odd row: rows (y, y+1)
+        o11.v[k] = 0.75f * Ho[1] + 0.25f * Ho[2];
+    }
+    // CO = pixel stride of `out` in elements (>= C): the result may be a channel slice of a wider tensor, so that the
+    // torch.cat in front of the upsampling (flow_computation.py:250-251, ...) needs no pass of its own
+    const int W2 = 2 * W;
+    T* ob = out + ((m * 2 * H + 2 * y) * (long long)W2 + 2 * x) * CO + c8 * 8;
+    st8<T>(ob, o00);
+    st8<T>(ob + CO, o01);
+    st8<T>(ob + (long long)W2 * CO, o10);
+    st8<T>(ob + (long long)W2 * CO + CO, o11);
+}
+
+// y <- leaky_relu(y + bias[c], slope), in place.  bias: fp32, C values.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_leaky_nhwc_kernel(T* __restrict__ y, const float* __restrict__ bias, int C8, float slope, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    T* p = y + i * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8) + 1);
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    Vec8 r = ld8<T>(p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // the two-step form rounds the sum to the storage type before the activation (aten::add_ then leaky_relu_)
+        const float s = storage_round<T>(r.v[k] + b[k]);
+        r.v[k] = s > 0.0f ? s : s * slope;
+    }
+    st8<T>(p, r);
+}
+
+// in: M x H x W x C (H, W even)   out: M x H/2 x W/2 x C, mean of the 2x2 window, summed in ATen's order
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool2_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int Ho, int Wo, int C8, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const long long m = r / Ho;
+    const int C = C8 * 8, W = 2 * Wo;
+    const T* p = in + ((m * 2 * Ho + 2 * y) * (long long)W + 2 * x) * C + c8 * 8;
+    const Vec8 a = ld8<T>(p), b = ld8<T>(p + C), c = ld8<T>(p + (long long)W * C), d = ld8<T>(p + (long long)W * C + C);
+    Vec8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = (((a.v[k] + b.v[k]) + c.v[k]) + d.v[k]) / 4.0f;
+    st8<T>(out + i * 8, o);
+}
+
+}  // namespace ssm

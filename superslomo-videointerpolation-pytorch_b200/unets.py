@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import unet_glue
 from .layers import avg_pool, conv
 from .recurrent import BiConvRecurrent
 
@@ -72,6 +73,10 @@ class FlowUNet(nn.Module):
         self.final_conv = nn.Conv2d(32, out_channels, kernel_size=3, stride=1, padding=1, bias=True)
 
     channels_last = False     # set_channels_last(): NHWC activations/weights for cuDNN's tensor-core kernels
+    # In inference on channels-last CUDA activations the element-wise ops BETWEEN the convolutions (bias add +
+    # LeakyReLU, 2x2 average pooling, cat + bilinear upsampling) run as this repo's kernels (unet_glue.py); the
+    # convolutions stay on cuDNN.  False = stock torch ops everywhere.
+    fast_glue = True
 
     def set_channels_last(self, on=True):
         """SURVEY.md section 8(f) rank 2 (plumbing around the path): run the convolutions in channels-last
@@ -79,27 +84,73 @@ class FlowUNet(nn.Module):
         4/5-channel output is converted back to the planar layout the synthesis kernels read."""
         self.channels_last = bool(on)
         self.to(memory_format=torch.channels_last if on else torch.contiguous_format)
+        self._param_cache = {}
         return self
+
+    # ---- inference fast path: cuDNN convolution without bias + fused bias/LeakyReLU -------------------------------
+    def _glue_on(self, x):
+        return self.fast_glue and self.channels_last and x.is_cuda and not torch.is_grad_enabled()
+
+    def _params(self, conv_layer, dtype):
+        """(weight in the compute dtype, bias as fp32 rounded to the compute dtype -- what autocast hands cuDNN and
+        aten::add_), cast once instead of on every call; re-made when the parameters change."""
+        cache = self.__dict__.setdefault("_param_cache", {})
+        w, b = conv_layer.weight, conv_layer.bias
+        key = (id(conv_layer), dtype)
+        stamp = (w._version, b._version, w.data_ptr(), b.data_ptr())
+        hit = cache.get(key)
+        if hit is None or hit[0] != stamp:
+            wd = w.detach() if w.dtype == dtype else w.detach().to(dtype)
+            hit = (stamp, wd.contiguous(memory_format=torch.channels_last), b.detach().to(dtype).float().contiguous())
+            cache[key] = hit
+        return hit[1], hit[2]
+
+    def _block(self, seq, x):
+        """conv + LeakyReLU(0.1) block (layers.conv)."""
+        if not self._glue_on(x):
+            return seq(x)
+        dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            return seq(x)
+        layer = seq[0]
+        w, b = self._params(layer, dtype)
+        y = F.conv2d(x if x.dtype == dtype else x.to(dtype), w, None, layer.stride, layer.padding, layer.dilation, layer.groups)
+        if not unet_glue.usable(y):
+            return F.leaky_relu_(y.add_(b.to(dtype).view(1, -1, 1, 1)), 0.1)
+        return unet_glue.bias_leaky_(y, b, 0.1)
+
+    def _pool(self, pool, x):
+        if self._glue_on(x) and unet_glue.usable(x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            return unet_glue.avgpool2(x)
+        return pool(x)
+
+    def _up2_cat(self, parts):
+        """upsample(cat(parts)): flow_computation.py:236-251 upsamples the concatenation of the decoder state and
+        the encoder skip; the fast path upsamples each part into its channel slice of the result."""
+        if self._glue_on(parts[0]):
+            parts = [p if p.dtype == parts[0].dtype else p.to(parts[0].dtype) for p in parts]
+            if all(unet_glue.usable(p) for p in parts):
+                return unet_glue.upsample2x_cat(parts)
+        return _up2(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
     def _encode(self, x):
         skips = []
         for level in range(1, 6):
             if level > 1:
-                x = getattr(self, "pool%d" % level)(x)
-            x = getattr(self, "conv%da" % level)(x)
-            x = getattr(self, "conv%db" % level)(x)
+                x = self._pool(getattr(self, "pool%d" % level), x)
+            x = self._block(getattr(self, "conv%da" % level), x)
+            x = self._block(getattr(self, "conv%db" % level), x)
             skips.append(x)
-        return skips, self.pool6(x)
+        return skips, self._pool(self.pool6, x)
 
     def _decode(self, h, skips, enc_stage1):
-        if self.stage == 2 and self.cross_skip_connect:
-            h = torch.cat([h, enc_stage1], dim=1)
-        x = self.conv7b(self.conv7a(_up2(h)))
+        parts = [h, enc_stage1] if (self.stage == 2 and self.cross_skip_connect) else [h]
+        x = self._block(self.conv7b, self._block(self.conv7a, self._up2_cat(parts)))
         for level, skip in zip((8, 9, 10, 11), (skips[4], skips[3], skips[2], skips[1])):
-            x = _up2(torch.cat([x, skip], dim=1))
-            x = getattr(self, "conv%da" % level)(x)
-            x = getattr(self, "conv%db" % level)(x)
-        x = self.fuse_conv(torch.cat([x, skips[0]], dim=1))
+            x = self._up2_cat([x, skip])
+            x = self._block(getattr(self, "conv%da" % level), x)
+            x = self._block(getattr(self, "conv%db" % level), x)
+        x = self._block(self.fuse_conv, torch.cat([x, skips[0]], dim=1))
         return self.final_conv(x)
 
     def forward_flat(self, x, enc_stage1=None, windows=1):
@@ -115,6 +166,8 @@ class FlowUNet(nn.Module):
             h = self.conv6(pooled.view(-1, windows, *pooled.shape[1:])).reshape(pooled.shape[0], -1, *pooled.shape[2:])
             if self.channels_last:
                 h = h.contiguous(memory_format=torch.channels_last)
+        elif isinstance(self.conv6, nn.Sequential) and len(self.conv6) == 2 and all(isinstance(b, nn.Sequential) for b in self.conv6):
+            h = self._block(self.conv6[1], self._block(self.conv6[0], pooled))
         else:
             h = self.conv6(pooled)
         out = self._decode(h, skips, enc_stage1)

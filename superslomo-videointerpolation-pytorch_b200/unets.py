@@ -43,6 +43,10 @@ def _up2(x):
     return F.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear", align_corners=False)
 
 
+def _has_hooks(m):
+    return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks)
+
+
 class FlowUNet(nn.Module):
     """U-Net with five 2x average-pool levels.  forward(unet_in B x T x C x H x W[, stage-1 encodings])
     returns a list of T (encoding-or-None, output) tuples for stage 1 and a list of T outputs for
@@ -107,8 +111,8 @@ class FlowUNet(nn.Module):
 
     def _block(self, seq, x):
         """conv + LeakyReLU(0.1) block (layers.conv)."""
-        if not self._glue_on(x):
-            return seq(x)
+        if not self._glue_on(x) or _has_hooks(seq) or _has_hooks(seq[0]) or _has_hooks(seq[1]):
+            return seq(x)             # hooks observe the stock modules: honour them
         dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             return seq(x)

@@ -103,11 +103,17 @@ def test_interpolate_uses_the_unet_layouts(monkeypatch):
 
     monkeypatch.setattr(F_ssm, "flow_pack_channels_last", spy_nhwc)
     monkeypatch.setattr(F_ssm, "_fuse_from_flow_mixed", spy_mixed)
-    hook = m.stage2_model.conv1a.register_forward_pre_hook(
-        lambda mod, args: seen["conv_in"].append((args[0].dtype, args[0].is_contiguous(memory_format=torch.channels_last))))
+    real_block = m.stage2_model._block
+
+    def spy_block(seq, x):                     # what the first convolution block of stage 2 is handed
+        if seq is m.stage2_model.conv1a:
+            seen["conv_in"].append((x.dtype, x.is_contiguous(memory_format=torch.channels_last)))
+        return real_block(seq, x)
+
+    monkeypatch.setattr(m.stage2_model, "_block", spy_block)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         fast = m.interpolate(frames, tv)
-    hook.remove()
+    monkeypatch.setattr(m.stage2_model, "_block", real_block)
     assert seen["nhwc"] == 1 and seen["mixed"] == 1
     assert seen["conv_in"] == [(torch.bfloat16, True)]
     # generic plumbing: planar fp32 compute_inputs, converted by the U-Net wrapper and autocast

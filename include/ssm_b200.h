@@ -223,7 +223,9 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
 
 /* ---- element-wise steps between the U-Nets' cuDNN convolutions -------
  * Channels-last activations (M x H x W x C, C a multiple of 8, 16-byte aligned), bf16 or fp32 storage, fp32
- * arithmetic in ATen's operation order; forward only (inference).  The convolutions stay on cuDNN.
+ * arithmetic in ATen's operation order.  The convolutions stay on cuDNN.  The *_bwd entry points are the
+ * vector-Jacobian products autograd derives for the same torch ops (gathers: deterministic, no atomics);
+ * the bias gradient (a per-channel sum of grad_x) is left to the caller.
  * ssm_upsample2x_nhwc: F.interpolate(x, size=(2H, 2W), mode="bilinear", align_corners=False), the upsampleN
  *   lambdas of [scripts/models/flow_computation.py:92-94, 102-104, 112-114, 122-124, 132-134] and
  *   [flow_interpolation.py:92-139].  `out` may be a channel slice of a wider tensor (out_pixel_stride >= C
@@ -235,6 +237,11 @@ int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, l
                         int dtype, void* stream);
 int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream);
 int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, int C, int dtype, void* stream);
+int ssm_upsample2x_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H, int W, int C,
+                            long long grad_out_pixel_stride, int dtype, void* stream);   /* grad_in: M x H x W x C */
+int ssm_leaky_bwd_nhwc(const void* grad_y, const void* y, void* grad_x, long long pixels, int C, float slope,
+                       int dtype, void* stream);       /* y = the activation output; grad_x may alias grad_y */
+int ssm_avgpool2_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H_out, int W_out, int C, int dtype, void* stream);
 
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
  * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */

@@ -725,6 +725,52 @@ int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, in
     return SSM_OK;
 }
 
+int ssm_upsample2x_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H, int W, int C, long long grad_out_pixel_stride,
+                            int dtype, void* stream) {
+    if (M <= 0 || H <= 0 || W <= 0) return fail(SSM_ERR_SHAPE, "ssm_upsample2x_bwd_nhwc: M, H, W must be positive");
+    SSM_TRY(check_glue("ssm_upsample2x_bwd_nhwc", grad_out, grad_in, (long long)M * H * W, C, dtype));
+    if (grad_out_pixel_stride < C || grad_out_pixel_stride % 8 != 0)
+        return fail(SSM_ERR_SHAPE, "ssm_upsample2x_bwd_nhwc: grad_out_pixel_stride must be a multiple of 8 and >= C");
+    const long long total = (long long)M * H * W * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        upsample2x_bwd_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)grad_out, (float*)grad_in, H, W, C / 8, grad_out_pixel_stride, total);
+    else
+        upsample2x_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)grad_out, (__nv_bfloat16*)grad_in, H, W, C / 8,
+                                                                      grad_out_pixel_stride, total);
+    SSM_LAUNCH_CHECK("ssm_upsample2x_bwd_nhwc");
+    return SSM_OK;
+}
+
+int ssm_leaky_bwd_nhwc(const void* grad_y, const void* y, void* grad_x, long long pixels, int C, float slope, int dtype, void* stream) {
+    SSM_TRY(check_glue("ssm_leaky_bwd_nhwc", grad_y, y, pixels, C, dtype));
+    SSM_TRY(check_glue("ssm_leaky_bwd_nhwc", grad_x, y, pixels, C, dtype));
+    const long long total = pixels * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        leaky_bwd_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)grad_y, (const float*)y, (float*)grad_x, slope, total);
+    else
+        leaky_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)grad_y, (const __nv_bfloat16*)y, (__nv_bfloat16*)grad_x, slope, total);
+    SSM_LAUNCH_CHECK("ssm_leaky_bwd_nhwc");
+    return SSM_OK;
+}
+
+int ssm_avgpool2_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H_out, int W_out, int C, int dtype, void* stream) {
+    if (M <= 0 || H_out <= 0 || W_out <= 0) return fail(SSM_ERR_SHAPE, "ssm_avgpool2_bwd_nhwc: M, H_out, W_out must be positive");
+    SSM_TRY(check_glue("ssm_avgpool2_bwd_nhwc", grad_out, grad_in, (long long)M * H_out * W_out, C, dtype));
+    const long long total = (long long)M * H_out * W_out * (C / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        avgpool2_bwd_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)grad_out, (float*)grad_in, H_out, W_out, C / 8, total);
+    else
+        avgpool2_bwd_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)grad_out, (__nv_bfloat16*)grad_in, H_out, W_out, C / 8, total);
+    SSM_LAUNCH_CHECK("ssm_avgpool2_bwd_nhwc");
+    return SSM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-buffer entry point: pair-sized chunks, three slots of caller-owned device scratch on three
 // streams, so the H2D copy of pair b+1, the kernels of pair b and the D2H copy of pair b-1 overlap.

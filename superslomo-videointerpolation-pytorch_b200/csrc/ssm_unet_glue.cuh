@@ -1,5 +1,5 @@
 // ssm_unet_glue.cuh -- element-wise steps BETWEEN the cuDNN convolutions of the two flow U-Nets, for
-// channels-last (N x H x W x C) activations in bf16 or fp32 (sm_100a).  Inference only.
+// channels-last (N x H x W x C) activations in bf16 or fp32 (sm_100a), forward and backward.
 //
 // The convolutions themselves stay on PyTorch / cuDNN (the one dense contraction of the system).  A whole
 // 1080p inference step, however, spends only 26 % of its time in them (profiles/r01s_pipeline_profile.txt):
@@ -143,6 +143,82 @@ avgpool2_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int Ho, int 
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = (((a.v[k] + b.v[k]) + c.v[k]) + d.v[k]) / 4.0f;
     st8<T>(out + i * 8, o);
+}
+
+// ---- backward of the three steps (training).  All are gathers: deterministic, no atomics. ------------------------
+// d/d(in) of upsample2x: input pixel (y, x) is a tap of output rows 2y-1 .. 2y+2 with weights 0.25, 0.75, 0.75, 0.25
+// (see the forward), except at the borders: row 0 takes output row 0 with weight 1 and has no row -1; row H-1 takes
+// output row 2H-1 with weight 1 (both of its taps clamp to H-1) and has no row 2H.  Columns alike.
+// g: M x 2H x 2W x CO (channel slice starting at `g`), gin: M x H x W x C dense.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_nhwc_kernel(const T* __restrict__ g, T* __restrict__ gin, int H, int W, int C8, long long CO, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const long long m = r / H;
+    float wr[4] = {0.25f, 0.75f, 0.75f, 0.25f}, wc[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    if (y == 0) { wr[0] = 0.0f; wr[1] = 1.0f; }
+    if (y == H - 1) { wr[3] = 0.0f; wr[2] = 1.0f; }
+    if (x == 0) { wc[0] = 0.0f; wc[1] = 1.0f; }
+    if (x == W - 1) { wc[3] = 0.0f; wc[2] = 1.0f; }
+    const int W2 = 2 * W;
+    const T* gb = g + (m * 2 * H * (long long)W2) * CO + c8 * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int oy = 2 * y - 1 + a;
+        if (wr[a] == 0.0f) continue;
+        float row[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (wc[b] == 0.0f) continue;
+            const Vec8 v = ld8<T>(gb + ((long long)oy * W2 + (2 * x - 1 + b)) * CO);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) row[k] = fmaf(wc[b], v.v[k], row[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wr[a], row[k], acc[k]);
+    }
+    Vec8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+    st8<T>(gin + i * 8, o);
+}
+
+// gx = gy * (y > 0 ? 1 : slope), y = the activation OUTPUT (same sign as the pre-activation for slope > 0)
+template <typename T>
+__global__ void __launch_bounds__(256)
+leaky_bwd_nhwc_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gx, float slope, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const Vec8 g = ld8<T>(gy + i * 8), v = ld8<T>(y + i * 8);
+    Vec8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = v.v[k] > 0.0f ? g.v[k] : g.v[k] * slope;
+    st8<T>(gx + i * 8, o);
+}
+
+// gin[2y+a, 2x+b] = gout[y, x] / 4
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool2_bwd_nhwc_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Ho, int Wo, int C8, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const long long m = r / Ho;
+    const int C = C8 * 8, W = 2 * Wo;
+    Vec8 v = ld8<T>(gout + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = v.v[k] / 4.0f;
+    T* p = gin + ((m * 2 * Ho + 2 * y) * (long long)W + 2 * x) * C + c8 * 8;
+    st8<T>(p, v); st8<T>(p + C, v); st8<T>(p + (long long)W * C, v); st8<T>(p + (long long)W * C + C, v);
 }
 
 }  // namespace ssm

@@ -5,8 +5,9 @@ The convolutions stay on PyTorch / cuDNN.  What these replace are the ATen eleme
 take 60 % of a whole 1080p inference step (profiles/r01s_pipeline_profile.txt): the channels-last bilinear
 upsampling (the `upsampleN` lambdas of scripts/models/flow_computation.py:92-134), the bias add + LeakyReLU(0.1)
 of layers.conv (scripts/models/layers.py:21-33) and AvgPool2d(2) (layers.py:60-63).  Same arithmetic, same
-operation order as the ATen ops; forward only -- `usable(x)` is False whenever autograd is recording, and the
-callers in unets.py then use the stock torch ops.
+operation order as the ATen ops in the forward; the backward kernels are the vector-Jacobian products autograd
+derives for those ops, written as gathers (deterministic, no atomics).  `usable(x)` says whether a tensor can take
+this path; the callers in unets.py use the stock torch ops otherwise.
 """
 import ctypes
 
@@ -16,53 +17,146 @@ from . import _abi
 
 
 def usable(x):
-    """CUDA, channels-last dense, bf16/fp32, C a multiple of 8, and no autograd graph to extend."""
+    """CUDA, channels-last dense, bf16/fp32, C a multiple of 8."""
     return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and x.shape[1] % 8 == 0
-            and not (torch.is_grad_enabled() and x.requires_grad)
             and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _ptr(t, elem_offset=0):
+    return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
+
+
+def _nhwc(t):
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
 
 
 def _nhwc_empty(M, C, H, W, like):
     return torch.empty((M, C, H, W), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
 
 
-def upsample2x_cat(parts):
-    """F.interpolate(torch.cat(parts, dim=1), size=(2H, 2W), mode="bilinear", align_corners=False) without the
-    concatenated intermediate: every part is upsampled straight into its channel slice of the result."""
+def _upsample2x_cat_fwd(parts):
     x0 = parts[0]
     M, _, H, W = x0.shape
     C = sum(p.shape[1] for p in parts)
     out = _nhwc_empty(M, C, 2 * H, 2 * W, x0)
     L = _abi.lib()
-    esz = out.element_size()
     off = 0
     with torch.cuda.device_of(x0):
         for p in parts:
             if p.shape[0] != M or p.shape[2:] != x0.shape[2:] or p.dtype != x0.dtype:
                 raise RuntimeError("upsample2x_cat: parts must share batch, size and dtype")
-            _abi.check(L.ssm_upsample2x_nhwc(ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(out.data_ptr() + off * esz),
-                                             M, H, W, p.shape[1], C, _abi.dtype_code(p), _abi.stream_ptr(p.device)),
-                       "ssm_upsample2x_nhwc")
+            _abi.check(L.ssm_upsample2x_nhwc(_ptr(p), _ptr(out, off), M, H, W, p.shape[1], C, _abi.dtype_code(p),
+                                             _abi.stream_ptr(p.device)), "ssm_upsample2x_nhwc")
             off += p.shape[1]
     return out
 
 
-def bias_leaky_(y, bias_f32, slope=0.1):
-    """y <- leaky_relu(y + bias, slope) in place; bias_f32: fp32 CUDA tensor of C values."""
+class _Upsample2xCat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *parts):
+        ctx.channels = [p.shape[1] for p in parts]
+        ctx.size = (parts[0].shape[0], parts[0].shape[2], parts[0].shape[3])
+        return _upsample2x_cat_fwd(parts)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _nhwc(g)
+        M, H, W = ctx.size
+        C = sum(ctx.channels)
+        L = _abi.lib()
+        grads, off = [], 0
+        with torch.cuda.device_of(g):
+            for i, c in enumerate(ctx.channels):
+                if ctx.needs_input_grad[i]:
+                    gi = _nhwc_empty(M, c, H, W, g)
+                    _abi.check(L.ssm_upsample2x_bwd_nhwc(_ptr(g, off), _ptr(gi), M, H, W, c, C, _abi.dtype_code(g),
+                                                         _abi.stream_ptr(g.device)), "ssm_upsample2x_bwd_nhwc")
+                    grads.append(gi)
+                else:
+                    grads.append(None)
+                off += c
+        return tuple(grads)
+
+
+def upsample2x_cat(parts):
+    """F.interpolate(torch.cat(parts, dim=1), size=(2H, 2W), mode="bilinear", align_corners=False) without the
+    concatenated intermediate: every part is upsampled straight into its channel slice of the result (and the
+    gradient of every part is gathered straight from its slice of the result's gradient)."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in parts):
+        return _Upsample2xCat.apply(*parts)
+    return _upsample2x_cat_fwd(parts)
+
+
+def _bias_leaky_fwd(y, bias_f32, slope):
     M, C, H, W = y.shape
     with torch.cuda.device_of(y):
-        _abi.check(_abi.lib().ssm_bias_leaky_nhwc(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(bias_f32.data_ptr()),
-                                                  M * H * W, C, float(slope), _abi.dtype_code(y), _abi.stream_ptr(y.device)),
-                   "ssm_bias_leaky_nhwc")
+        _abi.check(_abi.lib().ssm_bias_leaky_nhwc(_ptr(y), _ptr(bias_f32), M * H * W, C, float(slope), _abi.dtype_code(y),
+                                                  _abi.stream_ptr(y.device)), "ssm_bias_leaky_nhwc")
     return y
+
+
+class _BiasLeaky(torch.autograd.Function):
+    """y <- leaky_relu(y + bias) in place on a convolution output (which the convolution's own backward does not
+    need); saves the OUTPUT, whose sign is the pre-activation's."""
+
+    @staticmethod
+    def forward(ctx, y, bias, slope):
+        # the bias joins in the activation's dtype, as autocast hands it to aten::add_
+        _bias_leaky_fwd(y, bias.detach().to(y.dtype).float().contiguous(), slope)
+        ctx.mark_dirty(y)
+        ctx.save_for_backward(y)
+        ctx.slope, ctx.bias_dtype = slope, bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = _nhwc(gy)
+        M, C, H, W = y.shape
+        gx = torch.empty_like(y, memory_format=torch.channels_last)
+        with torch.cuda.device_of(y):
+            _abi.check(_abi.lib().ssm_leaky_bwd_nhwc(_ptr(gy), _ptr(y), _ptr(gx), M * H * W, C, float(ctx.slope),
+                                                     _abi.dtype_code(y), _abi.stream_ptr(y.device)), "ssm_leaky_bwd_nhwc")
+        gb = gx.sum(dim=(0, 2, 3), dtype=torch.float32).to(ctx.bias_dtype) if ctx.needs_input_grad[1] else None
+        return gx, gb, None
+
+
+def bias_leaky_(y, bias, slope=0.1):
+    """y <- leaky_relu(y + bias, slope) in place.  Inference: `bias` is an fp32 CUDA tensor of C values already rounded
+    to the activation dtype.  With autograd recording: `bias` is the convolution's bias parameter."""
+    if torch.is_grad_enabled() and (y.requires_grad or bias.requires_grad):
+        return _BiasLeaky.apply(y, bias, slope)
+    return _bias_leaky_fwd(y, bias, slope)
+
+
+def _avgpool2_fwd(x):
+    M, C, H, W = x.shape
+    out = _nhwc_empty(M, C, H // 2, W // 2, x)
+    with torch.cuda.device_of(x):
+        _abi.check(_abi.lib().ssm_avgpool2_nhwc(_ptr(x), _ptr(out), M, H // 2, W // 2, C, _abi.dtype_code(x),
+                                                _abi.stream_ptr(x.device)), "ssm_avgpool2_nhwc")
+    return out
+
+
+class _AvgPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return _avgpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _nhwc(g)
+        M, C, H, W = ctx.shape
+        gin = _nhwc_empty(M, C, H, W, g)
+        with torch.cuda.device_of(g):
+            _abi.check(_abi.lib().ssm_avgpool2_bwd_nhwc(_ptr(g), _ptr(gin), M, H // 2, W // 2, C, _abi.dtype_code(g),
+                                                        _abi.stream_ptr(g.device)), "ssm_avgpool2_bwd_nhwc")
+        return gin
 
 
 def avgpool2(x):
     """AvgPool2d(2) of a channels-last tensor with even H and W."""
-    M, C, H, W = x.shape
-    out = _nhwc_empty(M, C, H // 2, W // 2, x)
-    with torch.cuda.device_of(x):
-        _abi.check(_abi.lib().ssm_avgpool2_nhwc(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                                M, H // 2, W // 2, C, _abi.dtype_code(x), _abi.stream_ptr(x.device)),
-                   "ssm_avgpool2_nhwc")
-    return out
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _AvgPool2.apply(x)
+    return _avgpool2_fwd(x)

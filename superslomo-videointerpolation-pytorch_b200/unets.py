@@ -77,9 +77,9 @@ class FlowUNet(nn.Module):
         self.final_conv = nn.Conv2d(32, out_channels, kernel_size=3, stride=1, padding=1, bias=True)
 
     channels_last = False     # set_channels_last(): NHWC activations/weights for cuDNN's tensor-core kernels
-    # In inference on channels-last CUDA activations the element-wise ops BETWEEN the convolutions (bias add +
-    # LeakyReLU, 2x2 average pooling, cat + bilinear upsampling) run as this repo's kernels (unet_glue.py); the
-    # convolutions stay on cuDNN.  False = stock torch ops everywhere.
+    # On channels-last CUDA activations the element-wise ops BETWEEN the convolutions (bias add + LeakyReLU, 2x2
+    # average pooling, cat + bilinear upsampling) run as this repo's kernels, forward and backward (unet_glue.py);
+    # the convolutions stay on cuDNN.  False = stock torch ops everywhere.
     fast_glue = True
 
     def set_channels_last(self, on=True):
@@ -91,9 +91,9 @@ class FlowUNet(nn.Module):
         self._param_cache = {}
         return self
 
-    # ---- inference fast path: cuDNN convolution without bias + fused bias/LeakyReLU -------------------------------
+    # ---- fast path: cuDNN convolution without bias + fused bias/LeakyReLU ------------------------------------------
     def _glue_on(self, x):
-        return self.fast_glue and self.channels_last and x.is_cuda and not torch.is_grad_enabled()
+        return self.fast_glue and self.channels_last and x.is_cuda
 
     def _params(self, conv_layer, dtype):
         """(weight in the compute dtype, bias as fp32 rounded to the compute dtype -- what autocast hands cuDNN and
@@ -117,6 +117,13 @@ class FlowUNet(nn.Module):
         if dtype not in (torch.float32, torch.bfloat16):
             return seq(x)
         layer = seq[0]
+        recording = torch.is_grad_enabled() and (x.requires_grad or layer.weight.requires_grad or layer.bias.requires_grad)
+        if recording:
+            # autograd: the parameters themselves enter the graph (autocast casts the weight, the cast is differentiable)
+            y = F.conv2d(x, layer.weight, None, layer.stride, layer.padding, layer.dilation, layer.groups)
+            if not unet_glue.usable(y):
+                return F.leaky_relu_(y + layer.bias.to(y.dtype).view(1, -1, 1, 1), 0.1)
+            return unet_glue.bias_leaky_(y, layer.bias, 0.1)
         w, b = self._params(layer, dtype)
         y = F.conv2d(x if x.dtype == dtype else x.to(dtype), w, None, layer.stride, layer.padding, layer.dilation, layer.groups)
         if not unet_glue.usable(y):

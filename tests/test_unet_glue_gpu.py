@@ -87,8 +87,6 @@ def test_glue_rejects_what_it_cannot_do():
     assert not unet_glue.usable(_nhwc(1, 12, 4, 4, torch.float32, 9))        # C % 8
     assert not unet_glue.usable(x.half())
     assert not unet_glue.usable(x.cpu())
-    with torch.enable_grad():
-        assert not unet_glue.usable(x.clone().requires_grad_())
     L = ssm_b200._abi.lib()
     import ctypes
     rc = L.ssm_upsample2x_nhwc(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(x.data_ptr()), 1, 4, 4, 12, 12, 0, None)
@@ -124,10 +122,64 @@ def test_unet_fast_path_matches_stock_modules(amp, bottleneck):
         torch.backends.cudnn.allow_tf32 = prev
 
 
-def test_fast_path_is_off_when_autograd_records():
-    s1, _ = seeded_unets(32, DEV)
-    s1.set_channels_last()
-    x = torch.randn((1, 1, 6, 32, 32), device=DEV)
-    out = s1(x)[0][1]
-    out.sum().backward()                      # stock modules: a graph exists
-    assert s1.conv1a[0].weight.grad is not None
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_backward_kernels_match_autograd_of_the_aten_ops(dtype):
+    """upsample(cat), avg-pool and bias + LeakyReLU: gradients from the gather kernels vs autograd through the ATen ops."""
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    a, b = _nhwc(2, 16, 7, 9, dtype, 21).requires_grad_(), _nhwc(2, 8, 7, 9, dtype, 22).requires_grad_()
+    g = _nhwc(2, 24, 14, 18, dtype, 23)
+    ref = F.interpolate(torch.cat([a, b], dim=1), size=(14, 18), mode="bilinear", align_corners=False)
+    ra, rb = torch.autograd.grad(ref, (a, b), g)
+    ga, gb = torch.autograd.grad(unet_glue.upsample2x_cat([a, b]), (a, b), g)
+    for got, want in ((ga, ra), (gb, rb)):
+        assert (got.float() - want.float()).abs().max().item() <= tol * max(1.0, want.float().abs().max().item())
+    for shape in ((1, 8, 1, 1), (1, 8, 1, 5), (2, 8, 6, 1)):          # degenerate sizes: every border rule at once
+        x = _nhwc(*shape, dtype, 24).requires_grad_()
+        gg = _nhwc(shape[0], shape[1], 2 * shape[2], 2 * shape[3], dtype, 25)
+        (want,) = torch.autograd.grad(F.interpolate(x, size=(2 * shape[2], 2 * shape[3]), mode="bilinear", align_corners=False), x, gg)
+        (got,) = torch.autograd.grad(unet_glue.upsample2x_cat([x]), x, gg)
+        assert (got.float() - want.float()).abs().max().item() <= tol * max(1.0, want.float().abs().max().item()), shape
+    x = _nhwc(2, 32, 10, 12, dtype, 26).requires_grad_()
+    gp = _nhwc(2, 32, 5, 6, dtype, 27)
+    (want,) = torch.autograd.grad(F.avg_pool2d(x, 2), x, gp)
+    (got,) = torch.autograd.grad(unet_glue.avgpool2(x), x, gp)
+    assert (got.float() - want.float()).abs().max().item() <= tol * max(1.0, want.float().abs().max().item())
+    y0 = _nhwc(2, 32, 9, 11, dtype, 28)
+    bias = torch.randn(32, device=DEV, requires_grad=True)
+    gy = _nhwc(2, 32, 9, 11, dtype, 29)
+    ya = y0.clone(memory_format=torch.preserve_format).requires_grad_()
+    ref = F.leaky_relu(ya + bias.to(dtype).view(1, -1, 1, 1), 0.1)
+    wy, wb = torch.autograd.grad(ref, (ya, bias), gy)
+    yb = y0.clone(memory_format=torch.preserve_format).requires_grad_()
+    out = unet_glue.bias_leaky_(yb * 1.0, bias, 0.1)                    # * 1.0: a non-leaf, as a convolution output is
+    qy, qb = torch.autograd.grad(out, (yb, bias), gy)
+    assert (qy.float() - wy.float()).abs().max().item() <= tol * max(1.0, wy.float().abs().max().item())
+    assert (qb.float() - wb.float()).abs().max().item() <= (1e-3 if dtype == torch.float32 else 5e-2) * max(1.0, wb.abs().max().item())
+
+
+@pytest.mark.parametrize("bottleneck", ["CONV", "CLSTM"])
+def test_unet_training_fast_path_matches_stock_modules(bottleneck):
+    """fp32, channels-last, autograd recording: outputs and every parameter gradient, fast vs stock element-wise ops."""
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        s1, s2 = seeded_unets(33, DEV, bottleneck=bottleneck)
+        s1.set_channels_last(); s2.set_channels_last()
+        g = torch.Generator(device=DEV).manual_seed(12)
+        pairs = torch.randn((2, 2, 6, 64, 64), generator=g, device=DEV)
+        in16 = torch.randn((2, 2, 16, 64, 64), generator=g, device=DEV)
+        res = {}
+        for fast in (False, True):
+            s1.fast_glue = s2.fast_glue = fast
+            s1.zero_grad(); s2.zero_grad()
+            o1 = s1(pairs)
+            o2 = s2(in16, [e for e, _ in o1])
+            loss = sum(f.square().mean() for _, f in o1) + sum(o.square().mean() for o in o2)
+            loss.backward()
+            res[fast] = (loss.item(), {n: p.grad.clone() for m in (s1, s2) for n, p in m.named_parameters()})
+        assert abs(res[True][0] - res[False][0]) <= 1e-4 * max(1.0, abs(res[False][0]))
+        for n, want in res[False][1].items():
+            got = res[True][1][n]
+            assert (got - want).abs().max().item() <= 2e-3 * max(want.abs().max().item(), 1e-6), n
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--channels-last", action="store_true", help="NHWC U-Nets (cuDNN tensor-core kernels)")
     ap.add_argument("--bottleneck", default="CONV", choices=["CONV", "CLSTM", "CGRU"],
                     help="U-Net bottleneck: CONV = superslomo_original.ini, CLSTM = superslomo_recurrent.ini (use --n-frames 4)")
+    ap.add_argument("--profile", default=None, help="write the kernel table of one step (torch.profiler) to this file")
     a = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,6 +120,13 @@ def main():
     step()
     torch.cuda.synchronize()
     ssm_b200._abi._lib = lib
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=50, max_name_column_width=90))
     path_ms = {}
     for n, s, e in spans:
         path_ms[n] = path_ms.get(n, 0.0) + s.elapsed_time(e)

@@ -227,8 +227,8 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
  * vector-Jacobian products autograd derives for the same torch ops (gathers: deterministic, no atomics);
  * the bias gradient (a per-channel sum of grad_x) is left to the caller.
  * ssm_upsample2x_nhwc: F.interpolate(x, size=(2H, 2W), mode="bilinear", align_corners=False), the upsampleN
- *   lambdas of [scripts/models/flow_computation.py:92-94, 102-104, 112-114, 122-124, 132-134] and
- *   [flow_interpolation.py:92-139].  `out` may be a channel slice of a wider tensor (out_pixel_stride >= C
+ *   lambdas of [scripts/models/flow_computation.py:92-94, 103-105, 113-115, 124-126, 135-137; applied at :236-272] and
+ *   [flow_interpolation.py:92-141; applied at :228-267].  `out` may be a channel slice of a wider tensor (out_pixel_stride >= C
  *   elements between pixels), which absorbs the torch.cat in front of the upsampling.
  * ssm_bias_leaky_nhwc: y <- LeakyReLU(y + bias[c], slope) in place, the bias add and activation of
  *   layers.conv [scripts/models/layers.py:21-33]; bias: DEVICE float[C]; pixels = M*H*W.

@@ -8,7 +8,7 @@
 // three kernels do the same arithmetic as the ATen ops they replace, in the same order, at HBM speed:
 //
 //   upsample2x_nhwc_kernel   F.interpolate(x, size=(2H, 2W), mode="bilinear", align_corners=False)
-//                            reference: the lambda upsampleN of scripts/models/flow_computation.py:92-94, 102-104, ...
+//                            reference: the lambda upsampleN of scripts/models/flow_computation.py:92-94, 103-105, ... (applied at :236-272)
 //   bias_leaky_nhwc_kernel   conv bias add + LeakyReLU(0.1)      reference: layers.conv, scripts/models/layers.py:21-33
 //   avgpool2_nhwc_kernel     AvgPool2d(2)                        reference: layers.avg_pool, scripts/models/layers.py:60-63
 //
@@ -96,7 +96,7 @@ upsample2x_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int
         o11.v[k] = 0.75f * Ho[1] + 0.25f * Ho[2];
     }
     // CO = pixel stride of `out` in elements (>= C): the result may be a channel slice of a wider tensor, so that the
-    // torch.cat in front of the upsampling (flow_computation.py:250-251, ...) needs no pass of its own
+    // torch.cat in front of the upsampling (flow_computation.py:244-245, 253-254, ...) needs no pass of its own
     const int W2 = 2 * W;
     T* ob = out + ((m * 2 * H + 2 * y) * (long long)W2 + 2 * x) * CO + c8 * 8;
     st8<T>(ob, o00);

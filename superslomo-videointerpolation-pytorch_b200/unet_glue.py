@@ -3,7 +3,7 @@ ssm_avgpool2_nhwc of include/ssm_b200.h), for channels-last activations in infer
 
 The convolutions stay on PyTorch / cuDNN.  What these replace are the ATen element-wise ops around them, which
 take 60 % of a whole 1080p inference step (profiles/r01s_pipeline_profile.txt): the channels-last bilinear
-upsampling (the `upsampleN` lambdas of scripts/models/flow_computation.py:92-134), the bias add + LeakyReLU(0.1)
+upsampling (the `upsampleN` lambdas of scripts/models/flow_computation.py:92-137, applied at :236-272), the bias add + LeakyReLU(0.1)
 of layers.conv (scripts/models/layers.py:21-33) and AvgPool2d(2) (layers.py:60-63).  Same arithmetic, same
 operation order as the ATen ops in the forward; the backward kernels are the vector-Jacobian products autograd
 derives for those ops, written as gathers (deterministic, no atomics).  `usable(x)` says whether a tensor can take

@@ -136,7 +136,7 @@ class FlowUNet(nn.Module):
         return pool(x)
 
     def _up2_cat(self, parts):
-        """upsample(cat(parts)): flow_computation.py:236-251 upsamples the concatenation of the decoder state and
+        """upsample(cat(parts)): flow_computation.py:244-245, 253-254, 262-263, 271-272 upsamples the concatenation of the decoder state and
         the encoder skip; the fast path upsamples each part into its channel slice of the result."""
         if self._glue_on(parts[0]):
             parts = [p if p.dtype == parts[0].dtype else p.to(parts[0].dtype) for p in parts]

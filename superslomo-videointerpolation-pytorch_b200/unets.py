@@ -98,14 +98,24 @@ class FlowUNet(nn.Module):
     def _params(self, conv_layer, dtype):
         """(weight in the compute dtype, bias as fp32 rounded to the compute dtype -- what autocast hands cuDNN and
         aten::add_), cast once instead of on every call; re-made when the parameters change."""
-        cache = self.__dict__.setdefault("_param_cache", {})
         w, b = conv_layer.weight, conv_layer.bias
+
+        def make():
+            wd = w.detach() if w.dtype == dtype else w.detach().to(dtype)
+            return wd.contiguous(memory_format=torch.channels_last), b.detach().to(dtype).float().contiguous()
+
+        if not isinstance(w, nn.Parameter):
+            # an nn.DataParallel replica: its "parameters" are per-forward broadcast copies -- nothing worth keeping,
+            # and a cache keyed on them would grow with every call
+            return make()
+        cache = self.__dict__.setdefault("_param_cache", {})
         key = (id(conv_layer), dtype)
         stamp = (w._version, b._version, w.data_ptr(), b.data_ptr())
         hit = cache.get(key)
         if hit is None or hit[0] != stamp:
-            wd = w.detach() if w.dtype == dtype else w.detach().to(dtype)
-            hit = (stamp, wd.contiguous(memory_format=torch.channels_last), b.detach().to(dtype).float().contiguous())
+            if len(cache) > 256:
+                cache.clear()
+            hit = (stamp,) + make()
             cache[key] = hit
         return hit[1], hit[2]
 

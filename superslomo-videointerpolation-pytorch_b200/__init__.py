@@ -7,14 +7,15 @@ from .functional import (flow_pack, flow_pack_channels_last, fuse, fuse_from_flo
                          synthesize_host_scratch_bytes)
 from .layers import avg_pool, conv, warp
 from .flow_interpolation import SynthesisMixin, patch_reference
-from . import formats, frames, losses, sharding, superslomo_r, synthetic, unets
+from . import formats, frames, losses, sharding, superslomo_r, synthetic, unet_glue, unets
+from .unet_glue import accelerate_unet
 from .frames import frames_from_u8, frames_to_u8, normalisation_lut
 from .superslomo_r import FullModel
 
 __all__ = ["warp", "conv", "avg_pool", "flow_pack", "flow_pack_channels_last", "fuse", "fuse_from_flow", "fuse_loss", "pack_frames", "synthesize_host",
            "synthesize_host_scratch_bytes", "SynthesisMixin", "FullModel", "patch_reference",
            "set_coord_mode", "get_coord_mode", "abi_version", "frames_from_u8", "frames_to_u8",
-           "normalisation_lut"]
+           "normalisation_lut", "accelerate_unet"]
 
 
 def abi_version():

@@ -160,3 +160,67 @@ def avgpool2(x):
     if torch.is_grad_enabled() and x.requires_grad:
         return _AvgPool2.apply(x)
     return _avgpool2_fwd(x)
+
+
+# ---- drop-in for the reference's own U-Net instances -------------------------------------------------------------
+class FusedConvLeaky(torch.nn.Sequential):
+    """nn.Sequential(Conv2d, LeakyReLU) -- what layers.conv builds (scripts/models/layers.py:21-33) -- with the same
+    children and therefore the same state_dict keys ("0.weight", "0.bias"), whose forward runs the convolution on
+    cuDNN WITHOUT its bias and adds bias + LeakyReLU in one in-place pass.  Falls back to the stock children whenever
+    the activation cannot take that pass (CPU, planar layout, other dtypes, C % 8 != 0, hooks installed)."""
+
+    def forward(self, x):
+        conv, act = self[0], self[1]
+        if (not x.is_cuda or conv.bias is None or conv._forward_hooks or conv._forward_pre_hooks
+                or act._forward_hooks or act._forward_pre_hooks):
+            return act(conv(x))
+        y = torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if not usable(y):
+            return act(y + conv.bias.to(y.dtype).view(1, -1, 1, 1))
+        if torch.is_grad_enabled() and (y.requires_grad or conv.bias.requires_grad):
+            return bias_leaky_(y, conv.bias, act.negative_slope)
+        return bias_leaky_(y, conv.bias.detach().to(y.dtype).float().contiguous(), act.negative_slope)
+
+
+class FastAvgPool2(torch.nn.AvgPool2d):
+    """AvgPool2d(2) (layers.avg_pool, scripts/models/layers.py:60-63) on the channels-last kernel when it applies."""
+
+    def forward(self, x):
+        if usable(x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and not (self._forward_hooks or self._forward_pre_hooks):
+            return avgpool2(x)
+        return super().forward(x)
+
+
+def _fast_upsample(x):
+    if usable(x):
+        return upsample2x_cat([x])
+    if x.is_cuda and x.dtype != torch.float32 and torch.is_autocast_enabled("cuda"):
+        with torch.autocast("cuda", enabled=False):      # autocast would interpolate in fp32 (see unets._up2)
+            return torch.nn.functional.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear", align_corners=False)
+    return torch.nn.functional.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear", align_corners=False)
+
+
+def accelerate_unet(model):
+    """Apply the element-wise kernels to an instance of the REFERENCE's FlowComputationModel / FlowInterpolationModel
+    (scripts/models/flow_computation.py, flow_interpolation.py) in place: parameters, state_dict keys and results
+    (up to rounding) are unchanged, every convolution stays an nn.Conv2d on cuDNN.
+      * every nn.Sequential(Conv2d, LeakyReLU) child becomes a FusedConvLeaky over the same two modules,
+      * every AvgPool2d(2) child becomes a FastAvgPool2,
+      * the `upsample7` .. `upsample11` lambdas (flow_computation.py:92-137) become the 2x bilinear kernel,
+      * weights are converted to channels-last, which makes cuDNN produce channels-last activations.
+    Returns the model."""
+    nn = torch.nn
+    for name, child in list(model.named_children()):
+        if (isinstance(child, nn.Sequential) and not isinstance(child, FusedConvLeaky) and len(child) == 2
+                and isinstance(child[0], nn.Conv2d) and isinstance(child[1], nn.LeakyReLU)):
+            setattr(model, name, FusedConvLeaky(child[0], child[1]))
+        elif isinstance(child, nn.Sequential):
+            accelerate_unet(child)                      # e.g. the CONV bottleneck: Sequential(conv(...), conv(...))
+        elif (isinstance(child, nn.AvgPool2d) and not isinstance(child, FastAvgPool2) and child.kernel_size in (2, (2, 2))
+              and child.stride in (2, (2, 2), None) and child.padding in (0, (0, 0)) and not child.ceil_mode):
+            setattr(model, name, FastAvgPool2(2))
+    for level in range(7, 12):
+        if hasattr(model, "upsample%d" % level) and not isinstance(getattr(model, "upsample%d" % level), nn.Module):
+            setattr(model, "upsample%d" % level, _fast_upsample)
+    model.to(memory_format=torch.channels_last)
+    return model

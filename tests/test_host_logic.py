@@ -235,3 +235,74 @@ def test_numa_placement_helper(tmp_path, monkeypatch):
     with ctx as placement:
         assert placement.info == {"numa_node": None, "cpus_bound": 0, "mempolicy": False}
         assert os.sched_getaffinity(0) == before
+
+
+class _RefStyleUNet(torch.nn.Module):
+    """Built the way the reference builds its U-Nets (flow_computation.py:36-153): layers.conv Sequentials,
+    layers.avg_pool, and the upsampleN lambdas stored as plain attributes."""
+
+    def __init__(self):
+        super().__init__()
+        import torch.nn.functional as F
+        self.conv1a, self.conv1b = ssm_b200.conv(6, 16, 7, padding=3), ssm_b200.conv(16, 16, 7, padding=3)
+        self.pool2 = ssm_b200.avg_pool(kernel_size=2)
+        self.conv2a = ssm_b200.conv(16, 32, 5, padding=2)
+        self.conv6 = torch.nn.Sequential(ssm_b200.conv(32, 32), ssm_b200.conv(32, 32))
+        self.upsample7 = lambda x: F.interpolate(x, size=(2 * x.shape[2], 2 * x.shape[3]), mode="bilinear")
+        self.conv7a = ssm_b200.conv(48, 16)
+        self.final_conv = torch.nn.Conv2d(16, 4, 3, padding=1)
+
+    def forward(self, x):
+        s1 = self.conv1b(self.conv1a(x))
+        h = self.conv6(self.conv2a(self.pool2(s1)))
+        return self.final_conv(self.conv7a(torch.cat([self.upsample7(h), s1], dim=1)))
+
+
+def test_accelerate_unet_keeps_parameters_keys_and_cpu_results():
+    from ssm_b200 import unet_glue
+    torch.manual_seed(5)
+    m = _RefStyleUNet()
+    x = torch.randn(2, 6, 16, 24)
+    want = m(x)
+    keys = list(m.state_dict().keys())
+    params = [id(p) for p in m.parameters()]
+    assert ssm_b200.accelerate_unet(m) is m
+    assert list(m.state_dict().keys()) == keys and [id(p) for p in m.parameters()] == params
+    assert isinstance(m.conv1a, unet_glue.FusedConvLeaky) and isinstance(m.conv6[1], unet_glue.FusedConvLeaky)
+    assert isinstance(m.pool2, unet_glue.FastAvgPool2) and m.upsample7 is unet_glue._fast_upsample
+    assert isinstance(m.final_conv, torch.nn.Conv2d)
+    got = m(x)                                  # CPU tensors: every fused module falls back to its stock children
+    assert torch.allclose(got, want, atol=1e-6)
+    got.sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
+    ssm_b200.accelerate_unet(m)                 # idempotent
+    assert list(m.state_dict().keys()) == keys
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/scripts"), reason="needs the reference tree (build container only)")
+def test_accelerate_unet_on_the_reference_classes():
+    """The reference's own FlowComputationModel / FlowInterpolationModel: same keys, same CPU results after accelerate_unet."""
+    import configparser
+    sys.path.insert(0, "/root/reference/scripts")
+    try:
+        from models import unetflow
+        cfg = configparser.RawConfigParser()
+        cfg.read("/root/reference/configs/superslomo_original.ini")
+        torch.manual_seed(6)
+        s1 = unetflow.get_model(None, 6, 4, True, stage=1, cfg=cfg).eval()
+        s2 = unetflow.get_model(None, 16, 5, True, stage=2, cfg=cfg).eval()
+        x1, x2 = torch.randn(1, 1, 6, 64, 64), torch.randn(1, 1, 16, 64, 64)
+        with torch.no_grad():
+            o1 = s1(x1)
+            o2 = s2(x2, [e for e, _ in o1])
+        keys = (list(s1.state_dict()), list(s2.state_dict()))
+        ssm_b200.accelerate_unet(s1); ssm_b200.accelerate_unet(s2)
+        assert (list(s1.state_dict()), list(s2.state_dict())) == keys
+        with torch.no_grad():
+            p1 = s1(x1)
+            p2 = s2(x2, [e for e, _ in p1])
+        assert torch.allclose(p1[0][1], o1[0][1], atol=1e-5) and torch.allclose(p2[0], o2[0], atol=1e-5)
+    finally:
+        sys.path.remove("/root/reference/scripts")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]

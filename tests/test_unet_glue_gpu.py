@@ -183,3 +183,39 @@ def test_unet_training_fast_path_matches_stock_modules(bottleneck):
             assert (got - want).abs().max().item() <= 2e-3 * max(want.abs().max().item(), 1e-6), n
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_accelerate_unet_on_a_reference_style_module(amp):
+    """accelerate_unet on a U-Net built the way the reference builds its own (layers.conv Sequentials, avg_pool,
+    upsampleN lambdas): same results as the untouched module, and the element-wise kernels are what runs."""
+    import copy
+    from test_host_logic import _RefStyleUNet
+    torch.manual_seed(7)
+    stock = _RefStyleUNet().to(DEV).eval()
+    fast = ssm_b200.accelerate_unet(copy.deepcopy(stock))
+    x = torch.randn(2, 6, 32, 48, device=DEV)
+    calls = []
+    lib = ssm_b200._abi.lib()
+
+    class _Spy:
+        def __getattr__(self, n):
+            if n in ("ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc"):
+                calls.append(n)
+            return getattr(lib, n)
+
+    ssm_b200._abi._lib = _Spy()
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            want, got = stock(x).float(), fast(x).float()
+    finally:
+        ssm_b200._abi._lib = lib
+    assert calls.count("ssm_bias_leaky_nhwc") == 6 and calls.count("ssm_avgpool2_nhwc") == 1 and calls.count("ssm_upsample2x_nhwc") == 1
+    tol = 3e-2 if amp else 1e-4
+    assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    # training through the accelerated module: gradients agree with the stock one
+    stock.train(); fast.train()
+    ls, lf = stock(x).square().mean(), fast(x).square().mean()
+    ls.backward(); lf.backward()
+    for (n, a), (_, b) in zip(stock.named_parameters(), fast.named_parameters()):
+        assert (a.grad - b.grad).abs().max().item() <= 2e-3 * max(a.grad.abs().max().item(), 1e-6), n

@@ -236,6 +236,12 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
 int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, long long out_pixel_stride,
                         int dtype, void* stream);
 int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream);
+/* the same, written to out1 (pixel stride out1_pixel_stride elements; out1 == y, stride C = in place) and, if out2 is
+ * not NULL, also to out2: channel slices of wider tensors, so that the torch.cat that would copy the activation
+ * next [flow_computation.py:277] needs no pass of its own */
+int ssm_bias_leaky_nhwc_to(const void* y, const float* bias, long long pixels, int C, float slope,
+                           void* out1, long long out1_pixel_stride, void* out2, long long out2_pixel_stride,
+                           int dtype, void* stream);
 int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, int C, int dtype, void* stream);
 int ssm_upsample2x_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H, int W, int C,
                             long long grad_out_pixel_stride, int dtype, void* stream);   /* grad_in: M x H x W x C */

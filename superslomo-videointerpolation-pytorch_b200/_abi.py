@@ -27,7 +27,7 @@ EXPORTS = (
     "ssm_packed_frames_bytes", "ssm_pack_frames",
     "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
     "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
-    "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc",
+    "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to",
 )
 
 
@@ -80,6 +80,7 @@ def lib():
     L.ssm_upsample2x_nhwc.argtypes = [V, V, I, I, I, I, LL, I, V]
     L.ssm_bias_leaky_nhwc.argtypes = [V, V, LL, I, ctypes.c_float, I, V]
     L.ssm_avgpool2_nhwc.argtypes = [V, V, I, I, I, I, I, V]
+    L.ssm_bias_leaky_nhwc_to.argtypes = [V, V, LL, I, ctypes.c_float, V, LL, V, LL, I, V]
     L.ssm_upsample2x_bwd_nhwc.argtypes = [V, V, I, I, I, I, LL, I, V]
     L.ssm_leaky_bwd_nhwc.argtypes = [V, V, V, LL, I, ctypes.c_float, I, V]
     L.ssm_avgpool2_bwd_nhwc.argtypes = [V, V, I, I, I, I, I, V]
@@ -88,7 +89,7 @@ def lib():
               "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
               "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host",
               "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
-              "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc"):
+              "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to"):
         getattr(L, n).restype = I
     _lib = L
     return L

@@ -698,17 +698,28 @@ int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, l
     return SSM_OK;
 }
 
-int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream) {
+int ssm_bias_leaky_nhwc_to(const void* y, const float* bias, long long pixels, int C, float slope,
+                           void* out1, long long out1_pixel_stride, void* out2, long long out2_pixel_stride,
+                           int dtype, void* stream) {
     SSM_TRY(check_glue("ssm_bias_leaky_nhwc", y, bias, pixels, C, dtype));
+    SSM_TRY(check_glue("ssm_bias_leaky_nhwc", out1, out2 ? out2 : out1, pixels, C, dtype));
+    if (out1_pixel_stride < C || out1_pixel_stride % 8 != 0 || (out2 && (out2_pixel_stride < C || out2_pixel_stride % 8 != 0)))
+        return fail(SSM_ERR_SHAPE, "ssm_bias_leaky_nhwc: output pixel strides must be multiples of 8 and >= C");
     const long long total = pixels * (C / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == SSM_DTYPE_F32)
-        bias_leaky_nhwc_kernel<float><<<grid, 256, 0, s>>>((float*)y, bias, C / 8, slope, total);
+        bias_leaky_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)y, bias, C / 8, slope, total, (float*)out1, out1_pixel_stride,
+                                                           (float*)out2, out2_pixel_stride);
     else
-        bias_leaky_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)y, bias, C / 8, slope, total);
+        bias_leaky_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)y, bias, C / 8, slope, total, (__nv_bfloat16*)out1,
+                                                                   out1_pixel_stride, (__nv_bfloat16*)out2, out2_pixel_stride);
     SSM_LAUNCH_CHECK("ssm_bias_leaky_nhwc");
     return SSM_OK;
+}
+
+int ssm_bias_leaky_nhwc(void* y, const float* bias, long long pixels, int C, float slope, int dtype, void* stream) {
+    return ssm_bias_leaky_nhwc_to(y, bias, pixels, C, slope, y, C, nullptr, 0, dtype, stream);
 }
 
 int ssm_avgpool2_nhwc(const void* in, void* out, int M, int H_out, int W_out, int C, int dtype, void* stream) {

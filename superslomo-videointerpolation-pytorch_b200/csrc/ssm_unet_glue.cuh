@@ -105,24 +105,29 @@ upsample2x_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int
     st8<T>(ob + (long long)W2 * CO + CO, o11);
 }
 
-// y <- leaky_relu(y + bias[c], slope), in place.  bias: fp32, C values.
+// out1 <- leaky_relu(y + bias[c], slope); out1 == y with pixel stride C is the in-place form.  bias: fp32, C values.
+// out1 (pixel stride CO1 elements) and the optional second copy out2 (pixel stride CO2) may be channel slices of
+// wider tensors: the activation is then written where the next torch.cat would have copied it
+// (flow_computation.py:277 cat([conv11b_out, conv1b_out]) in front of fuse_conv), and that cat needs no pass.
 template <typename T>
 __global__ void __launch_bounds__(256)
-bias_leaky_nhwc_kernel(T* __restrict__ y, const float* __restrict__ bias, int C8, float slope, long long total) {
+bias_leaky_nhwc_kernel(const T* __restrict__ y, const float* __restrict__ bias, int C8, float slope, long long total,
+                       T* __restrict__ out1, long long CO1, T* __restrict__ out2, long long CO2) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c8 = (int)(i % C8);
-    T* p = y + i * 8;
+    const long long px = i / C8;
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8) + 1);
     const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    Vec8 r = ld8<T>(p);
+    Vec8 r = ld8<T>(y + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         // the two-step form rounds the sum to the storage type before the activation (aten::add_ then leaky_relu_)
         const float s = storage_round<T>(r.v[k] + b[k]);
         r.v[k] = s > 0.0f ? s : s * slope;
     }
-    st8<T>(p, r);
+    st8<T>(out1 + px * CO1 + c8 * 8, r);
+    if (out2) st8<T>(out2 + px * CO2 + c8 * 8, r);
 }
 
 // in: M x H x W x C (H, W even)   out: M x H/2 x W/2 x C, mean of the 2x2 window, summed in ATen's order

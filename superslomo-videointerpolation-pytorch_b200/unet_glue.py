@@ -95,6 +95,26 @@ def _bias_leaky_fwd(y, bias_f32, slope):
     return y
 
 
+def bias_leaky_into(y, bias_f32, slope, wide, channel_offset, keep_in_place):
+    """Inference only: leaky_relu(y + bias) written into channels [channel_offset, channel_offset + C) of the wider
+    channels-last tensor `wide` (the result of a torch.cat that then never has to run) -- instead of in place
+    (keep_in_place=False) or in addition to the in-place result (keep_in_place=True).  Returns y (valid only with
+    keep_in_place) ."""
+    M, C, H, W = y.shape
+    CW = wide.shape[1]
+    if (wide.shape[0], wide.shape[2], wide.shape[3]) != (M, H, W) or wide.dtype != y.dtype or not usable(wide) \
+            or channel_offset % 8 or channel_offset + C > CW:
+        raise RuntimeError("bias_leaky_into: `wide` must be a channels-last tensor of the same batch, size and dtype")
+    with torch.cuda.device_of(y):
+        if keep_in_place:
+            out1, s1, out2, s2 = _ptr(y), C, _ptr(wide, channel_offset), CW
+        else:
+            out1, s1, out2, s2 = _ptr(wide, channel_offset), CW, None, 0
+        _abi.check(_abi.lib().ssm_bias_leaky_nhwc_to(_ptr(y), _ptr(bias_f32), M * H * W, C, float(slope), out1, s1, out2, s2,
+                                                     _abi.dtype_code(y), _abi.stream_ptr(y.device)), "ssm_bias_leaky_nhwc_to")
+    return y
+
+
 class _BiasLeaky(torch.autograd.Function):
     """y <- leaky_relu(y + bias) in place on a convolution output (which the convolution's own backward does not
     need); saves the OUTPUT, whose sign is the pre-activation's."""

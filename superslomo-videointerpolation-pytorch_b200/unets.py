@@ -119,8 +119,18 @@ class FlowUNet(nn.Module):
             cache[key] = hit
         return hit[1], hit[2]
 
-    def _block(self, seq, x):
-        """conv + LeakyReLU(0.1) block (layers.conv)."""
+    def _block(self, seq, x, into=None):
+        """conv + LeakyReLU(0.1) block (layers.conv).  into = (wide, channel_offset, keep): in inference the activation
+        is (also) written into that channel slice of the pre-allocated result of a later torch.cat; returns None
+        instead of the activation when it was honoured and keep is False."""
+        y = self._block_impl(seq, x, into)
+        if into is not None and not (isinstance(y, tuple)):
+            wide, off, keep = into                     # the fast path did not apply: do what torch.cat would have done
+            wide[:, off:off + y.shape[1]] = y
+            return y if keep else None
+        return y[0] if isinstance(y, tuple) else y
+
+    def _block_impl(self, seq, x, into):
         if not self._glue_on(x) or _has_hooks(seq) or _has_hooks(seq[0]) or _has_hooks(seq[1]):
             return seq(x)             # hooks observe the stock modules: honour them
         dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
@@ -138,6 +148,10 @@ class FlowUNet(nn.Module):
         y = F.conv2d(x if x.dtype == dtype else x.to(dtype), w, None, layer.stride, layer.padding, layer.dilation, layer.groups)
         if not unet_glue.usable(y):
             return F.leaky_relu_(y.add_(b.to(dtype).view(1, -1, 1, 1)), 0.1)
+        if into is not None and into[0].dtype == y.dtype:
+            wide, off, keep = into
+            unet_glue.bias_leaky_into(y, b, 0.1, wide, off, keep)
+            return (y if keep else None,)              # tuple: `into` has been honoured
         return unet_glue.bias_leaky_(y, b, 0.1)
 
     def _pool(self, pool, x):
@@ -155,24 +169,37 @@ class FlowUNet(nn.Module):
         return _up2(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
     def _encode(self, x):
-        skips = []
+        """-> (skips, pooled bottleneck input, fuse_in).  fuse_in: in inference on the fast path, the pre-allocated input of
+        fuse_conv -- cat([conv11b_out, conv1b_out]), flow_computation.py:277 -- whose second half conv1b's activation
+        pass fills while it writes the skip; None otherwise (the decoder then calls torch.cat)."""
+        skips, fuse_in = [], None
         for level in range(1, 6):
             if level > 1:
                 x = self._pool(getattr(self, "pool%d" % level), x)
             x = self._block(getattr(self, "conv%da" % level), x)
-            x = self._block(getattr(self, "conv%db" % level), x)
+            if level == 1 and self._glue_on(x) and not torch.is_grad_enabled() and unet_glue.usable(x):
+                fuse_in = torch.empty((x.shape[0], 64, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                                      memory_format=torch.channels_last)
+                x = self._block(self.conv1b, x, into=(fuse_in, 32, True))
+            else:
+                x = self._block(getattr(self, "conv%db" % level), x)
             skips.append(x)
-        return skips, self._pool(self.pool6, x)
+        return skips, self._pool(self.pool6, x), fuse_in
 
-    def _decode(self, h, skips, enc_stage1):
+    def _decode(self, h, skips, enc_stage1, fuse_in=None):
         parts = [h, enc_stage1] if (self.stage == 2 and self.cross_skip_connect) else [h]
         x = self._block(self.conv7b, self._block(self.conv7a, self._up2_cat(parts)))
         for level, skip in zip((8, 9, 10, 11), (skips[4], skips[3], skips[2], skips[1])):
             x = self._up2_cat([x, skip])
             x = self._block(getattr(self, "conv%da" % level), x)
-            x = self._block(getattr(self, "conv%db" % level), x)
-        x = self._block(self.fuse_conv, torch.cat([x, skips[0]], dim=1))
-        return self.final_conv(x)
+            if level == 11 and fuse_in is not None and fuse_in.dtype == x.dtype:
+                self._block(self.conv11b, x, into=(fuse_in, 0, False))      # lands in fuse_in[:, 0:32]
+                x = None
+            else:
+                x = self._block(getattr(self, "conv%db" % level), x)
+        if x is not None:
+            fuse_in = torch.cat([x, skips[0]], dim=1)
+        return self.final_conv(self._block(self.fuse_conv, fuse_in))
 
     def forward_flat(self, x, enc_stage1=None, windows=1):
         """x: M x C x H x W (windows/timesteps already folded into M, windows fastest) -> (bottleneck
@@ -182,7 +209,7 @@ class FlowUNet(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
             if enc_stage1 is not None:
                 enc_stage1 = enc_stage1.contiguous(memory_format=torch.channels_last)
-        skips, pooled = self._encode(x)
+        skips, pooled, fuse_in = self._encode(x)
         if isinstance(self.conv6, BiConvRecurrent):
             h = self.conv6(pooled.view(-1, windows, *pooled.shape[1:])).reshape(pooled.shape[0], -1, *pooled.shape[2:])
             if self.channels_last:
@@ -191,7 +218,7 @@ class FlowUNet(nn.Module):
             h = self._block(self.conv6[1], self._block(self.conv6[0], pooled))
         else:
             h = self.conv6(pooled)
-        out = self._decode(h, skips, enc_stage1)
+        out = self._decode(h, skips, enc_stage1, fuse_in)
         # the synthesis kernels read planar NCHW: hand the (4- or 5-channel) result back in that layout
         return h, (out.contiguous() if self.channels_last else out)
 

@@ -105,10 +105,10 @@ def test_interpolate_uses_the_unet_layouts(monkeypatch):
     monkeypatch.setattr(F_ssm, "_fuse_from_flow_mixed", spy_mixed)
     real_block = m.stage2_model._block
 
-    def spy_block(seq, x):                     # what the first convolution block of stage 2 is handed
+    def spy_block(seq, x, **kw):               # what the first convolution block of stage 2 is handed
         if seq is m.stage2_model.conv1a:
             seen["conv_in"].append((x.dtype, x.is_contiguous(memory_format=torch.channels_last)))
-        return real_block(seq, x)
+        return real_block(seq, x, **kw)
 
     monkeypatch.setattr(m.stage2_model, "_block", spy_block)
     with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -2,7 +2,7 @@
 """Interpolate a directory of frames (what the reference's scripts/visualize_interpolation.py does):
 
     python tools/interpolate_dir.py --input-dir frames/ --output-dir out/ --upsample-rate 8 [--weights ckpt.pt]
-                                    [--n-frames 2] [--fps-240] [--save-flows] [--amp] [--channels-last]
+                                    [--n-frames 2] [--fps-240] [--save-flows] [--amp] [--channels-last] [--bottleneck CLSTM]
 
 uint8 images go to the GPU as they are; ssm_frames_from_u8 normalises and pads them, FullModel.interpolate
 runs stage 1 once per window and all intermediate times per launch, ssm_frames_to_u8 crops and converts
@@ -34,10 +34,15 @@ def main():
     ap.add_argument("--save-flows", action="store_true")
     ap.add_argument("--amp", action="store_true")
     ap.add_argument("--channels-last", action="store_true")
+    ap.add_argument("--bottleneck", default="CONV", choices=["CONV", "CLSTM", "CGRU"],
+                    help="CONV: superslomo_original.ini; CLSTM: superslomo_recurrent.ini (use --n-frames 4)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(42)
-    model = ssm_b200.FullModel(cfg=None).to(dev).eval()
+    import configparser
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("[STAGE1]\nBOTTLENECK=%s\n[STAGE2]\nBOTTLENECK=%s\nCROSS_SKIP=TRUE\n" % (a.bottleneck, a.bottleneck))
+    model = ssm_b200.FullModel(cfg=cfg).to(dev).eval()
     if a.weights:
         formats.load_checkpoint(model, a.weights)
     if a.channels_last:

@@ -25,12 +25,13 @@ class SSMLosses(nn.Module):
     def __init__(self, cfg=None, lambda_r=60.0, lambda_p=20.0, lambda_w=10.0, stage1_frozen=False,
                  stage2_frozen=False, perceptual_features=None):
         super().__init__()
-        if cfg is not None:
-            lambda_r = cfg.getfloat("TRAIN", "LAMBDA_R")      # losses.py:73-78
-            lambda_w = cfg.getfloat("TRAIN", "LAMBDA_W")
-            lambda_p = cfg.getfloat("TRAIN", "LAMBDA_P")
-            stage1_frozen = cfg.getboolean("STAGE1", "FREEZE")
-            stage2_frozen = cfg.getboolean("STAGE2", "FREEZE")
+        if cfg is not None:                                    # losses.py:73-78; a partial config keeps the defaults
+            get = lambda fn, sec, key, default: fn(sec, key) if cfg.has_option(sec, key) else default
+            lambda_r = get(cfg.getfloat, "TRAIN", "LAMBDA_R", lambda_r)
+            lambda_w = get(cfg.getfloat, "TRAIN", "LAMBDA_W", lambda_w)
+            lambda_p = get(cfg.getfloat, "TRAIN", "LAMBDA_P", lambda_p)
+            stage1_frozen = get(cfg.getboolean, "STAGE1", "FREEZE", stage1_frozen)
+            stage2_frozen = get(cfg.getboolean, "STAGE2", "FREEZE", stage2_frozen)
         self.loss_weights = (lambda_r, lambda_p, lambda_w)
         self.stage1_frozen, self.stage2_frozen = stage1_frozen, stage2_frozen
         self.perceptual_features = perceptual_features     # e.g. torchvision vgg16.features[:23]

@@ -306,3 +306,13 @@ def test_accelerate_unet_on_the_reference_classes():
         sys.path.remove("/root/reference/scripts")
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
+
+
+def test_fullmodel_accepts_a_partial_config():
+    """tools pass a config that only names the bottleneck: every other option keeps the reference's default."""
+    import configparser
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("[STAGE1]\nBOTTLENECK=CONV\n[STAGE2]\nBOTTLENECK=CONV\nCROSS_SKIP=TRUE\n")
+    with torch.device("meta"):
+        m = ssm_b200.FullModel(cfg=cfg)
+    assert m.loss.loss_weights == (60.0, 20.0, 10.0) and m.cross_skip

@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 import ssm_b200
-from ssm_b200 import unet_glue, unets
+from ssm_b200 import unet_glue
 from util import seeded_unets
 
 pytestmark = pytest.mark.gpu

@@ -25,7 +25,6 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ssm_b200  # noqa: E402
-from ssm_b200 import functional as F_ssm  # noqa: E402
 from ssm_b200.superslomo_r import FullModel  # noqa: E402
 
 

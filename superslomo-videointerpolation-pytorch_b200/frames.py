@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from .synthetic import PIXEL_MEAN, PIXEL_STD, pad32
+from .synthetic import PIXEL_MEAN, PIXEL_STD
 
 
 def normalisation_lut(mean=PIXEL_MEAN, std=PIXEL_STD, divisor=255.0, style="visualize", device="cuda"):

@@ -91,3 +91,26 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("SURVEY", ""), "%s mentions the oracle" % f
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/ssm_b200.h compiles as C99 (no C++ or torch types) and a C program links
+    against libssm_b200.so and reads the version without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "ssm_b200.h"\n'
+                   'int main(void) { printf("%d %d\\n", ssm_version(), SSM_ABI_VERSION);\n'
+                   '  return ssm_warp_fwd(0, 0, 0, 1, 3, 8, 8, SSM_DTYPE_F32, SSM_COORD_DIV, 0) < 0 ? 0 : 1; }\n')
+    libdir = os.path.dirname(ssm_b200._abi.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-l:libssm_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr                    # NULL tensors are an argument error (< 0), not a crash
+    a, b = out.stdout.split()
+    assert a == b == str(ssm_b200.abi_version())

@@ -153,3 +153,38 @@ def test_prepost_oracle_matches_reference():
     assert np.array_equal(torch_oracle.crop_denormalize_u8(torch.from_numpy(d["eval_in"]), h0, w0, h, w), d["eval_u8"])
     got = torch_oracle.reader_normalize_and_pad(d["reader_rgb_u8"], int(d["reader_pad"][0]))
     assert torch.equal(got, torch.from_numpy(d["reader_out"]))
+
+
+# ---- the C restatement against the torch restatement (== the reference's op sequence) on random small cases ------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(B=st.integers(1, 3), H=st.integers(1, 9), W=st.integers(1, 11), seed=st.integers(0, 2 ** 20),
+       flow_scale=st.sampled_from([0.0, 0.3, 2.0, 40.0]), k=st.integers(1, 7))
+def test_c_oracle_matches_torch_oracle_on_random_small_cases(B, H, W, seed, flow_scale, k):
+    """Degenerate sizes (H or W = 1: the normalisation divides by max(size-1, 1)), flows that leave the image on every
+    side, all timesteps k/8: forward values and the flow / logit / residual-flow gradients of the C oracle against
+    autograd through the reference's torch ops."""
+    g = torch.Generator().manual_seed(seed)
+    img6 = torch.randn((B, 6, H, W), generator=g)
+    flow4 = (torch.randn((B, 4, H, W), generator=g) * flow_scale).requires_grad_()
+    out5 = torch.randn((B, 5, H, W), generator=g).requires_grad_()
+    t = torch.full((B,), k / 8.0)
+    t4 = t.view(B, 1, 1, 1)
+    in16 = torch_oracle.compute_inputs(img6, flow4, t4)
+    frame = torch_oracle.compute_output_image(img6, in16, out5, t4)
+    c16 = c_oracle.compute_inputs(img6, flow4.detach(), t)
+    assert torch.equal(c16[:, 6:10], in16[:, 6:10].detach())
+    assert_close_fp32(c16, in16, "compute_inputs", tol=2e-6 * max(1.0, img6.abs().max().item()))
+    cfr = c_oracle.compute_output_image(img6, c16, out5.detach(), t)
+    # the final division amplifies rounding where the visibility-weighted denominator is small
+    assert_close_fp32(cfr, frame, "compute_output_image", tol=1e-5 * max(1.0, img6.abs().max().item()))
+    if flow_scale <= 2.0:       # gradients w.r.t. the flow are discontinuous at cell borders: compare where they are tame
+        g3 = torch.randn(frame.shape, generator=g)
+        gflow, gout = torch.autograd.grad(frame, (flow4, out5), g3)
+        _, gx, gy = c_oracle.compute_output_image_backward(g3, img6, c16, out5.detach(), t, need_img=False)
+        _, gf = c_oracle.compute_inputs_backward(gx, img6, flow4.detach(), t, need_img=False)
+        scale = max(1.0, gflow.abs().max().item(), gout.abs().max().item())
+        assert_close_fp32(gy, gout, "grad out5", tol=2e-5 * scale)
+        assert_close_fp32(gf, gflow, "grad flow", tol=2e-5 * scale)

@@ -73,6 +73,8 @@ def _inputs(B, N, H, W, seed, kind="smooth", smooth=True, flow_px=8.0):
     (2, 1, 33, 31, "border", True),      # narrower than one tile, samples cross every border
     (1, 2, 8, 1920, "integer", False),
     (1, 1, 1, 1, "zero", False),         # degenerate 1x1 frame: max(W-1,1) path
+    (2, 2, 1, 40, "border", False),      # a single row: the y normalisation divides by max(H-1, 1) = 1
+    (2, 2, 37, 1, "noise", False),       # a single column
     (3, 2, 352, 352, "smooth", True),    # training crop size
 ])
 def test_batched_kernels_vs_c_oracle(mode_name, mode, B, N, H, W, kind, smooth):

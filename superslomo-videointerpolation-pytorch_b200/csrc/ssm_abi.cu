@@ -687,13 +687,13 @@ int ssm_upsample2x_nhwc(const void* in, void* out, int M, int H, int W, int C, l
     SSM_TRY(check_glue("ssm_upsample2x_nhwc", in, out, (long long)M * H * W, C, dtype));
     if (out_pixel_stride < C || out_pixel_stride % 8 != 0)
         return fail(SSM_ERR_SHAPE, "ssm_upsample2x_nhwc: out_pixel_stride must be a multiple of 8 and >= C");
-    const long long total = (long long)M * H * W * (C / 8);
-    const unsigned grid = (unsigned)((total + 255) / 256);
+    const long long total = (long long)M * ((H + UPS_ROWS - 1) / UPS_ROWS) * W * (C / 8);     // one thread per row block
+    const unsigned grid = (unsigned)((total + UPS_BLOCK - 1) / UPS_BLOCK);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == SSM_DTYPE_F32)
-        upsample2x_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, H, W, C / 8, out_pixel_stride, total);
+        upsample2x_nhwc_kernel<float><<<grid, UPS_BLOCK, 0, s>>>((const float*)in, (float*)out, H, W, C / 8, out_pixel_stride, total);
     else
-        upsample2x_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, H, W, C / 8, out_pixel_stride, total);
+        upsample2x_nhwc_kernel<__nv_bfloat16><<<grid, UPS_BLOCK, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, H, W, C / 8, out_pixel_stride, total);
     SSM_LAUNCH_CHECK("ssm_upsample2x_nhwc");
     return SSM_OK;
 }

@@ -12,7 +12,14 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssm_b200.so")
 SOURCES = ["ssm_abi.cu"]
-HEADERS = ["ssm_device.cuh", "ssm_kernels.cuh", "ssm_scatter.cuh", "ssm_frames.cuh"]
+
+
+def _deps():
+    """every file the library is compiled from: csrc/*.cu, csrc/*.cuh (new headers are picked up without
+    editing a list) and the public header"""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) \
+        + [os.path.join(ROOT, "include", "ssm_b200.h")]
 
 
 def _nvcc():
@@ -26,8 +33,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "ssm_b200.h")]
-    return any(os.path.getmtime(d) > built for d in deps)
+    return any(os.path.getmtime(d) > built for d in _deps())
 
 
 def build(force=False, verbose=False):

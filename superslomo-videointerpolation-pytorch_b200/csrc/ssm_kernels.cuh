@@ -209,8 +209,10 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
     const int osc = (int)out16.sc;   // fits 32 bits (checked on the host): one IMAD.WIDE per address
     for (int n = 0; n < N; ++n, O += out16.sn) {
         const Coef k = make_coef(__ldg(tp + n));
-        const float e0x = est_t0(k, f01x, f10x), e0y = est_t0(k, f01y, f10y);   // F_t0  :353
-        const float e1x = est_t1(k, f01x, f10x), e1y = est_t1(k, f01y, f10y);   // F_t1  :356
+        // rounded to the storage type before they are used: the warped channels then correspond to the flows a
+        // consumer reads back from channels 6:10 (and to what fuse_fwd / est_flows recompute); a no-op in fp32
+        const float e0x = storage_round<T>(est_t0(k, f01x, f10x)), e0y = storage_round<T>(est_t0(k, f01y, f10y));   // F_t0  :353
+        const float e1x = storage_round<T>(est_t1(k, f01x, f10x)), e1y = storage_round<T>(est_t1(k, f01y, f10y));   // F_t1  :356
         const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);               // warp(img_1, F_t1) :361
         const Taps t0 = make_taps<MODE>(ti.x, ti.y, e0x, e0y, g);               // warp(img_0, F_t0) :362
         Quad q1[3], q0[3];
@@ -300,8 +302,8 @@ flow_pack_bwd_kernel(View<const T> g16, View<const T> img6, const T* __restrict_
                 }
             }
             if (!want_flow) continue;
-            const float e0x = est_t0(k, f01x, f10x), e0y = est_t0(k, f01y, f10y);
-            const float e1x = est_t1(k, f01x, f10x), e1y = est_t1(k, f01y, f10y);
+            const float e0x = storage_round<T>(est_t0(k, f01x, f10x)), e0y = storage_round<T>(est_t0(k, f01y, f10y));
+            const float e1x = storage_round<T>(est_t1(k, f01x, f10x)), e1y = storage_round<T>(est_t1(k, f01y, f10y));
             float g1x = 0, g1y = 0, g0x = 0, g0y = 0;
             {
                 const Taps t1 = make_taps<MODE>(ti.x, ti.y, e1x, e1y, g);

@@ -93,8 +93,8 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
     long long* a0 = acc + (long long)ti.b * 6 * npx;      // I0 planes 0-2, I1 planes 3-5
     for (int n = 0; n < N; ++n) {
         const Coef k = make_coef(__ldg(tv + ti.b * N + n));
-        const Taps t1 = make_taps<MODE>(ti.x, ti.y, est_t1(k, f01x, f10x), est_t1(k, f01y, f10y), g);
-        const Taps t0 = make_taps<MODE>(ti.x, ti.y, est_t0(k, f01x, f10x), est_t0(k, f01y, f10y), g);
+        const Taps t1 = make_taps<MODE>(ti.x, ti.y, storage_round<T>(est_t1(k, f01x, f10x)), storage_round<T>(est_t1(k, f01y, f10y)), g);
+        const Taps t0 = make_taps<MODE>(ti.x, ti.y, storage_round<T>(est_t0(k, f01x, f10x)), storage_round<T>(est_t0(k, f01y, f10y)), g);
         const T* G = g16.p + ti.b * g16.sb + n * g16.sn + p;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

@@ -3,18 +3,36 @@
 
 Only the warp-loss front-end is part of the rebuilt path: its four `warp` calls
 (losses.py:152-161) run through the sm_100a kernel and back-propagate through it.  The L1
-reconstruction term is a plain torch expression.  The VGG16 perceptual term needs the pretrained
-torchvision weights the reference downloads (losses.py:23), which are unavailable offline and out of
-scope; a feature extractor can be injected, otherwise that term is zero.
+reconstruction term is a plain torch expression.  The VGG16 perceptual term (losses.py:12-41, 213) is
+torchvision's pretrained VGG16 up to conv4_3, frozen, exactly as the reference builds it; when
+LAMBDA_P != 0 and those weights cannot be loaded (no network, no cache) construction FAILS unless the
+caller passes a feature extractor or opts out explicitly (`perceptual_features="zero"` or "random").
 
 forward() returns the reference's [B, 4] tensor: (total, reconstruction, warp, perceptual), each the
 per-sample mean (kept per sample because the reference gathers it across DataParallel replicas).
 """
+import warnings
+
 import torch
 import torch.nn as nn
 
 from . import functional as F_ssm
 from .layers import warp
+
+
+def vgg16_conv4_3(pretrained=True):
+    """torchvision VGG16 `features[:23]` (up to conv4_3 + ReLU), frozen and in eval mode: the feature extractor of
+    the reference's PerceptualLoss (losses.py:12-41).  pretrained=False gives the same architecture with random
+    weights (throughput measurements without a network)."""
+    import torchvision
+    try:
+        net = torchvision.models.vgg16(weights=torchvision.models.VGG16_Weights.IMAGENET1K_V1 if pretrained else None)
+    except TypeError:          # torchvision < 0.13
+        net = torchvision.models.vgg16(pretrained=pretrained)
+    feats = net.features[:23].eval()
+    for p in feats.parameters():
+        p.requires_grad = False
+    return feats
 
 
 def _sample_mean(x):
@@ -23,7 +41,10 @@ def _sample_mean(x):
 
 class SSMLosses(nn.Module):
     def __init__(self, cfg=None, lambda_r=60.0, lambda_p=20.0, lambda_w=10.0, stage1_frozen=False,
-                 stage2_frozen=False, perceptual_features=None):
+                 stage2_frozen=False, perceptual_features="auto"):
+        """perceptual_features: "auto" (default) = the reference's pretrained VGG16 conv4_3 whenever LAMBDA_P != 0,
+        raising if the weights are unavailable; a module = use it; "random" = random-init VGG16 conv4_3 (same
+        compute, for throughput runs); "zero" / None = explicit opt-out, the perceptual column is zero."""
         super().__init__()
         if cfg is not None:                                    # losses.py:73-78; a partial config keeps the defaults
             get = lambda fn, sec, key, default: fn(sec, key) if cfg.has_option(sec, key) else default
@@ -34,7 +55,28 @@ class SSMLosses(nn.Module):
             stage2_frozen = get(cfg.getboolean, "STAGE2", "FREEZE", stage2_frozen)
         self.loss_weights = (lambda_r, lambda_p, lambda_w)
         self.stage1_frozen, self.stage2_frozen = stage1_frozen, stage2_frozen
-        self.perceptual_features = perceptual_features     # e.g. torchvision vgg16.features[:23]
+        if isinstance(perceptual_features, str):
+            kind = perceptual_features.lower()
+            if kind not in ("auto", "random", "zero"):
+                raise ValueError("perceptual_features must be a module, None, 'auto', 'random' or 'zero'")
+            if kind == "zero" or lambda_p == 0:
+                perceptual_features = None
+            elif kind == "random":
+                perceptual_features = vgg16_conv4_3(pretrained=False)
+            else:
+                try:
+                    perceptual_features = vgg16_conv4_3(pretrained=True)
+                except Exception as e:      # offline: the reference itself fails here (losses.py:23)
+                    raise RuntimeError(
+                        "SSMLosses: LAMBDA_P = %g needs torchvision's pretrained VGG16 (reference losses.py:23) and it "
+                        "could not be loaded (%s: %s). Pass perceptual_features=<module>, or opt out explicitly with "
+                        "perceptual_features='zero' (perceptual term dropped) or 'random' (random-init VGG16)."
+                        % (lambda_p, type(e).__name__, str(e)[:120])) from e
+        elif perceptual_features is None and lambda_p != 0:
+            warnings.warn("SSMLosses: perceptual_features=None with LAMBDA_P = %g: the perceptual term of the reference "
+                          "(losses.py:213) is DROPPED and the total loss differs from the reference's" % lambda_p,
+                          RuntimeWarning, stacklevel=2)
+        self.perceptual_features = perceptual_features     # torchvision vgg16.features[:23], frozen
 
     def get_warp_loss(self, img_tensor, flowC_output, flowI_input, flowI_output, target_image):
         """losses.py:113-170: (total, stage-1 part, stage-2 part) as B x 3 x H x W L1 maps."""

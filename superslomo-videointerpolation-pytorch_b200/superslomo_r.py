@@ -47,7 +47,16 @@ class FullModel(nn.Module, SynthesisMixin):
         self.stage2_model = stage2_model if stage2_model is not None else unets.get_model(
             w2, 16, 5, self.cross_skip, stage=2, cfg=cfg)
         self.freeze_weights()
-        self.loss = loss if loss is not None else SSMLosses(cfg)
+        # The loss module is only needed by training forwards.  The reference builds it eagerly, pretrained VGG16
+        # included (losses.py:23); here a VGG16 that cannot be loaded (offline) fails the first TRAINING forward
+        # instead of every inference-only construction.
+        self._loss_error = None
+        if loss is None:
+            try:
+                loss = SSMLosses(cfg)
+            except RuntimeError as e:
+                self._loss_error = e
+        self.loss = loss
         # interpolate(): write compute_inputs in the layout/dtype a channels-last stage-2 U-Net consumes and read
         # its bf16 output directly; False = planar fp32 either side (generic)
         self.unet_layouts = True
@@ -80,6 +89,8 @@ class FullModel(nn.Module, SynthesisMixin):
         Training: (est_img_t of the middle window, losses [B, 4]); inference: (est_img_t,
         (flowC_01, flowC_10, est_flow_t1, est_flow_t0, refined_flow_t1, refined_flow_t0, v_0t))."""
         if not inference_mode:
+            if self.loss is None:
+                raise RuntimeError("FullModel: no loss module (%s)" % self._loss_error)
             assert target_images is not None, "No target found for loss."
             assert target_images.shape[1] == image_tensor.shape[1] - 1, "Insufficient number of targets."
         pairs = self.get_image_pairs(image_tensor)                    # B x W x 6 x H x W

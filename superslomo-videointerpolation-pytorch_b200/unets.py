@@ -88,8 +88,22 @@ class FlowUNet(nn.Module):
         4/5-channel output is converted back to the planar layout the synthesis kernels read."""
         self.channels_last = bool(on)
         self.to(memory_format=torch.channels_last if on else torch.contiguous_format)
-        self._param_cache = {}
+        self.invalidate_param_cache()
         return self
+
+    def invalidate_param_cache(self):
+        """Drop the cached casts of weights/biases (the bf16 copies the inference fast path keeps).  Called by
+        train()/eval(), load_state_dict() and set_channels_last(); call it yourself after writing parameters
+        through `.data` (EMA swaps, p.data.copy_()): such writes bump neither the version counter nor data_ptr."""
+        self.__dict__["_param_cache"] = {}
+
+    def train(self, mode=True):
+        self.invalidate_param_cache()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_param_cache()
+        return super().load_state_dict(*args, **kwargs)
 
     # ---- fast path: cuDNN convolution without bias + fused bias/LeakyReLU ------------------------------------------
     def _glue_on(self, x):
@@ -103,6 +117,11 @@ class FlowUNet(nn.Module):
         def make():
             wd = w.detach() if w.dtype == dtype else w.detach().to(dtype)
             return wd.contiguous(memory_format=torch.channels_last), b.detach().to(dtype).float().contiguous()
+
+        if w.dtype == dtype and b.dtype == torch.float32 and w.is_contiguous(memory_format=torch.channels_last):
+            # nothing to cast: use the live tensors, so in-place writes through `.data` (EMA swaps, p.data.copy_()),
+            # which bump neither the version counter nor data_ptr, are always seen
+            return w.detach(), (b.detach() if dtype == torch.float32 else b.detach().to(dtype).float())
 
         if not isinstance(w, nn.Parameter):
             # an nn.DataParallel replica: its "parameters" are per-forward broadcast copies -- nothing worth keeping,

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 5
+#define SSM_ABI_VERSION 6
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -221,6 +221,43 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
                      const float* mean3, const float* std3, float scale, int bgr, int saturate,
                      unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int dtype, void* stream);
 
+/* ---- frames that arrive as 8-bit images: a2 and a3+a4 gathering from 2x2 byte entries ---------------------
+ * The reference reads uint8 images and normalises them on the fly [scripts/visualize_interpolation.py:61-88
+ * load_batch, :257-262 normalize_tensor].  Because that normalisation is affine in the byte, v = a*b + c with
+ * a = 1/(divisor*std), c = -mean/std, it commutes with bilinear interpolation; the kernels below therefore gather
+ * raw bytes from an ENTRY TABLE -- entry(x0, y0) = the 2x2 neighbourhood {(x0,y0),(x0+1,y0),(x0,y0+1),(x0+1,y0+1)}
+ * x RGB as 12 bytes in a 16-byte slot, x0 in [-1, W-1], y0 in [-1, H-1], zero bytes outside the frame -- with ONE
+ * 16-byte request per bilinear sample instead of four (the fp32 gathers are bound by the L1 data stage), and apply
+ * a, c after interpolating: a * sum_k w_k b_k + c * sum_{k inside} w_k.  Results are within 1e-6 of ssm_flow_pack_fwd /
+ * ssm_fuse_flow_fwd on the normalised fp32 frames (zeros padding and align_corners=True as in layers.warp).
+ * One thread owns two adjacent pixels: W must be even, fp32 tensors 8-byte aligned with even strides.
+ * ssm_quads_from_u8: F uint8 images (layout and placement as ssm_frames_from_u8, padding pixels = byte 0, i.e. pad
+ *   BEFORE normalising as visualize_interpolation.py:76-87 does) -> F x (H+1) x (W+1) entries
+ *   (ssm_quads_bytes(F, H, W) bytes, 16-byte aligned).  A frame pair is two consecutive frames: quads of pair b
+ *   start at entry 2*b*(H+1)*(W+1).
+ * norm6: HOST float[6] = {a_R, a_G, a_B, c_R, c_G, c_B}.
+ * ssm_flow_pack_fwd_q8 [flow_interpolation.py:338-372]: img6 (B x 6 x H x W fp32, the normalised frames from
+ *   ssm_frames_from_u8) is only read for the six pass-through channels; out16 B x N x 16 x H x W fp32.
+ * ssm_flow_pack_fwd_q8_nhwc: the same written channels-last (B x N x H x W x 16, fp32 or bf16) as ssm_flow_pack_fwd_nhwc.
+ * ssm_fuse_flow_fwd_q8 [flow_interpolation.py:374-429]: as ssm_fuse_flow_fwd(_mixed); out5 in out5_dtype (fp32 or bf16).
+ * ssm_fuse_flow_fwd_q8_u8: the same with ssm_frames_to_u8 fused behind it: the fused frames are cropped,
+ *   de-normalised and written as B*N uint8 images H_out x W_out x 3 (frame index b*N + n)
+ *   [scripts/visualize_interpolation.py:221-232, 264-268]; no fp32 frame is materialised. */
+size_t ssm_quads_bytes(int F, int H, int W);
+int ssm_quads_from_u8(const unsigned char* src, long long src_frame_stride, int src_row_stride, int bgr,
+                      int F, int H_in, int W_in, int H, int W, int top, int left, void* quads, void* stream);
+int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                              void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
+                              int coord_mode, void* stream);
+int ssm_fuse_flow_fwd_q8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+int ssm_fuse_flow_fwd_q8_u8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                            unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int top, int left,
+                            int H_out, int W_out, const float* mean3, const float* std3, float scale, int bgr, int saturate,
+                            const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+
 /* ---- element-wise steps between the U-Nets' cuDNN convolutions -------
  * Channels-last activations (M x H x W x C, C a multiple of 8, 16-byte aligned), bf16 or fp32 storage, fp32
  * arithmetic in ATen's operation order.  The convolutions stay on cuDNN.  The *_bwd entry points are the
@@ -269,6 +306,21 @@ size_t ssm_synthesize_host_scratch_bytes(int B, int N, int H, int W);
 int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const float* out5_host,
                         const float* t_host, float* out3_host, float* in16_host,
                         int B, int N, int H, int W, int coord_mode, void* scratch, size_t scratch_bytes);
+
+/* ---- host-buffer entry point for 8-bit frames: uint8 images in, uint8 interpolated images out ----------------
+ * frames_host B x 2 x H_in x W_in x 3 uint8 (dense), placed at (top, left) of the padded H x W frame (pad = byte 0);
+ * flow4_host B x 4 x H x W fp32; out5_host B x N x 5 x H x W in out5_dtype (fp32 or bf16); t_host B*N floats;
+ * out_host B x N x H_in x W_in x 3 uint8 (clamped to [0, 255] if saturate, else numpy astype(uint8) wrap-around);
+ * lut_host float[3][256] (ssm_frames_from_u8's table: the pass-through channels of the stage-2 input are normalised
+ * with it); norm6 / mean3 / std3 host float arrays as above.  Per pair it runs ssm_frames_from_u8, ssm_quads_from_u8,
+ * ssm_flow_pack_fwd_q8 (the stage-2 input stays on the device, as with in16_host = NULL above) and
+ * ssm_fuse_flow_fwd_q8_u8 on three slots of caller-owned device scratch (256-byte aligned).  Synchronous. */
+size_t ssm_synthesize_host_u8_scratch_bytes(int B, int N, int H_in, int W_in, int H, int W, int out5_dtype);
+int ssm_synthesize_host_u8(const unsigned char* frames_host, int bgr, const float* flow4_host, const void* out5_host,
+                           int out5_dtype, const float* t_host, unsigned char* out_host, const float* lut_host,
+                           const float* norm6, const float* mean3, const float* std3, int saturate,
+                           int B, int N, int H_in, int W_in, int H, int W, int top, int left, int coord_mode,
+                           void* scratch, size_t scratch_bytes);
 
 #ifdef __cplusplus
 }

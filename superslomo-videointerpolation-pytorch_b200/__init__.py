@@ -7,7 +7,7 @@ from .functional import (flow_pack, flow_pack_channels_last, fuse, fuse_from_flo
                          synthesize_host_scratch_bytes)
 from .layers import avg_pool, conv, warp
 from .flow_interpolation import SynthesisMixin, patch_reference
-from . import formats, frames, losses, sharding, superslomo_r, synthetic, unet_glue, unets
+from . import formats, frames, losses, q8, sharding, superslomo_r, synthetic, unet_glue, unets
 from .unet_glue import accelerate_unet
 from .frames import frames_from_u8, frames_to_u8, normalisation_lut
 from .superslomo_r import FullModel

@@ -28,6 +28,8 @@ EXPORTS = (
     "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
     "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
     "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to",
+    "ssm_quads_bytes", "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8",
+    "ssm_fuse_flow_fwd_q8_u8", "ssm_synthesize_host_u8", "ssm_synthesize_host_u8_scratch_bytes",
 )
 
 
@@ -77,6 +79,16 @@ def lib():
         getattr(L, n).argtypes = [I, I, I, I]
         getattr(L, n).restype = Z
     L.ssm_synthesize_host.argtypes = [V, V, V, V, V, V, I, I, I, I, I, V, Z]
+    L.ssm_quads_bytes.argtypes = [I, I, I]
+    L.ssm_quads_bytes.restype = Z
+    L.ssm_quads_from_u8.argtypes = [V, LL, I, I, I, I, I, I, I, I, I, V, V]
+    L.ssm_flow_pack_fwd_q8.argtypes = [P, V, P, V, P, F3, I, I, I, I, I, V]
+    L.ssm_flow_pack_fwd_q8_nhwc.argtypes = [P, V, P, V, V, I, F3, I, I, I, I, I, V]
+    L.ssm_fuse_flow_fwd_q8.argtypes = [V, P, P, I, V, P, F3, I, I, I, I, I, V]
+    L.ssm_fuse_flow_fwd_q8_u8.argtypes = [V, P, P, I, V, V, LL, I, I, I, I, I, F3, F3, ctypes.c_float, I, I, F3, I, I, I, I, I, V]
+    L.ssm_synthesize_host_u8_scratch_bytes.argtypes = [I, I, I, I, I, I, I]
+    L.ssm_synthesize_host_u8_scratch_bytes.restype = Z
+    L.ssm_synthesize_host_u8.argtypes = [V, I, V, V, I, V, V, F3, F3, F3, F3, I, I, I, I, I, I, I, I, I, I, V, Z]
     L.ssm_upsample2x_nhwc.argtypes = [V, V, I, I, I, I, LL, I, V]
     L.ssm_bias_leaky_nhwc.argtypes = [V, V, LL, I, ctypes.c_float, I, V]
     L.ssm_avgpool2_nhwc.argtypes = [V, V, I, I, I, I, I, V]
@@ -89,7 +101,9 @@ def lib():
               "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
               "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host",
               "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
-              "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to"):
+              "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to",
+              "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8",
+              "ssm_fuse_flow_fwd_q8_u8", "ssm_synthesize_host_u8"):
         getattr(L, n).restype = I
     _lib = L
     return L

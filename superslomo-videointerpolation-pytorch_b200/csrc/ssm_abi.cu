@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "ssm_frames.cuh"
+#include "ssm_q8.cuh"
 #include "ssm_scatter.cuh"
 #include "ssm_unet_glue.cuh"
 
@@ -783,6 +784,173 @@ int ssm_avgpool2_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H_out,
 }
 
 // ---------------------------------------------------------------------------------------------
+// 8-bit frames: entry tables + the forward kernels that gather from them (ssm_q8.cuh)
+static int check_q8(const char* who, int B, int N, int H, int W, int coord_mode, const void* quads, const float* norm6) {
+    SSM_TRY(check_common(B, N, 16, H, W, SSM_DTYPE_F32, coord_mode));
+    if (W % 2 != 0) return fail(SSM_ERR_SHAPE, "%s: W must be even (got %d): two pixels per thread", who, W);
+    if (!quads || !norm6) return fail(SSM_ERR_NULL, "%s: quads or norm6 is NULL", who);
+    if (((uintptr_t)quads) % 16 != 0) return fail(SSM_ERR_ALIGN, "%s: quads must be 16-byte aligned", who);
+    const long long tiles = (long long)B * ((H + Q8_TILE_H - 1) / Q8_TILE_H) * ((W + Q8_TILE_W - 1) / Q8_TILE_W);
+    if (tiles > 2147483647ll) return fail(SSM_ERR_SHAPE, "%s: too many tiles for one launch", who);
+    if ((long long)(H + 1) * (W + 1) > MAX_PLANE) return fail(SSM_ERR_SHAPE, "%s: H*W too large", who);
+    return SSM_OK;
+}
+// 8-byte vector access: base and every stride a multiple of 2 elements (fp32) / the pair of bf16 values aligned to 4 bytes
+static int check_pairable(const ssm_tensor* t, const char* name, int dtype) {
+    const size_t esz = dtype == SSM_DTYPE_F32 ? 4 : 2;
+    if (((uintptr_t)t->data) % (2 * esz) != 0 || t->stride_b % 2 != 0 || t->stride_n % 2 != 0 || t->stride_c % 2 != 0)
+        return fail(SSM_ERR_ALIGN, "%s: base must be aligned to two elements and strides must be even (two pixels per access)", name);
+    return SSM_OK;
+}
+static Norm3 make_norm(const float* norm6) {
+    Norm3 n;
+    for (int k = 0; k < 3; ++k) { n.a[k] = norm6[k]; n.c[k] = norm6[3 + k]; }
+    return n;
+}
+static unsigned q8_grid(int B, int H, int W) {
+    return (unsigned)((long long)B * ((H + Q8_TILE_H - 1) / Q8_TILE_H) * ((W + Q8_TILE_W - 1) / Q8_TILE_W));
+}
+
+size_t ssm_quads_bytes(int F, int H, int W) {
+    if (F <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)F * (H + 1) * (W + 1) * 16;
+}
+
+int ssm_quads_from_u8(const unsigned char* src, long long src_frame_stride, int src_row_stride, int bgr,
+                      int F, int H_in, int W_in, int H, int W, int top, int left, void* quads, void* stream) {
+    if (F <= 0 || H_in <= 0 || W_in <= 0 || H <= 0 || W <= 0)
+        return fail(SSM_ERR_SHAPE, "ssm_quads_from_u8: F, H_in, W_in, H, W must be positive");
+    if (top < 0 || left < 0 || top + H_in > H || left + W_in > W)
+        return fail(SSM_ERR_SHAPE, "ssm_quads_from_u8: the %d x %d source at (%d, %d) does not fit %d x %d", H_in, W_in, top, left, H, W);
+    if ((long long)(H + 1) * (W + 1) > MAX_PLANE) return fail(SSM_ERR_SHAPE, "H*W too large (%d x %d)", H, W);
+    if (!src || !quads) return fail(SSM_ERR_NULL, "ssm_quads_from_u8: src or quads is NULL");
+    if (((uintptr_t)quads) % 16 != 0) return fail(SSM_ERR_ALIGN, "ssm_quads_from_u8: quads must be 16-byte aligned");
+    const long long groups = (long long)F * (H + 1) * ((W + 1 + 3) / 4);
+    const unsigned grid = (unsigned)((groups + 255) / 256 < 148ll * 32 ? (groups + 255) / 256 : 148ll * 32);
+    quads_from_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_frame_stride, src_row_stride, bgr != 0, H_in, W_in, H, W,
+                                                                top, left, (uint4*)quads, groups);
+    SSM_LAUNCH_CHECK("ssm_quads_from_u8");
+    return SSM_OK;
+}
+
+extern "C++" {
+template <int MODE>
+static int flow_pack_q8_launch(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                               const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
+                               int B, int N, int H, int W, cudaStream_t s) {
+    const Geom g = make_geom(H, W);
+    const Norm3 nm = make_norm(norm6);
+    const unsigned grid = q8_grid(B, H, W);
+    if (!nhwc) {
+        flow_pack_fwd_q8_kernel<MODE, float, false><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads, cview<float>(flow4),
+                                                                              t, mview<float>(out16), N, g, nm);
+    } else if (out_dtype == SSM_DTYPE_BF16) {
+        View<__nv_bfloat16> o; o.p = (__nv_bfloat16*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
+        flow_pack_fwd_q8_kernel<MODE, __nv_bfloat16, true><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads,
+                                                                                     cview<float>(flow4), t, o, N, g, nm);
+    } else {
+        View<float> o; o.p = (float*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
+        flow_pack_fwd_q8_kernel<MODE, float, true><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads, cview<float>(flow4),
+                                                                             t, o, N, g, nm);
+    }
+    SSM_LAUNCH_CHECK("ssm_flow_pack_fwd_q8");
+    return SSM_OK;
+}
+}  // extern "C++"
+
+static int flow_pack_q8_impl(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                             const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
+                             int B, int N, int H, int W, int coord_mode, void* stream) {
+    SSM_TRY(check_q8("ssm_flow_pack_fwd_q8", B, N, H, W, coord_mode, quads, norm6));
+    SSM_TRY(check_tensor(img6, "img6", SSM_DTYPE_F32, true));
+    SSM_TRY(check_tensor(flow4, "flow4", SSM_DTYPE_F32, true));
+    SSM_TRY(check_pairable(img6, "img6", SSM_DTYPE_F32));
+    SSM_TRY(check_pairable(flow4, "flow4", SSM_DTYPE_F32));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    if (nhwc) {
+        if (out_dtype != SSM_DTYPE_F32 && out_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out_dtype %d", out_dtype);
+        if (((uintptr_t)nhwc) % 32 != 0) return fail(SSM_ERR_ALIGN, "out16_nhwc must be 32-byte aligned");
+    } else {
+        SSM_TRY(check_tensor(out16, "out16", SSM_DTYPE_F32, true));
+        SSM_TRY(check_pairable(out16, "out16", SSM_DTYPE_F32));
+    }
+    return coord_mode == SSM_COORD_DIV
+        ? flow_pack_q8_launch<SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, (cudaStream_t)stream)
+        : flow_pack_q8_launch<SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, (cudaStream_t)stream);
+}
+
+int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
+    return flow_pack_q8_impl(img6, quads, flow4, t, out16, nullptr, SSM_DTYPE_F32, norm6, B, N, H, W, coord_mode, stream);
+}
+
+int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
+                              void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
+                              int coord_mode, void* stream) {
+    if (!out16_nhwc) return fail(SSM_ERR_NULL, "out16_nhwc is NULL");
+    return flow_pack_q8_impl(img6, quads, flow4, t, nullptr, out16_nhwc, out_dtype, norm6, B, N, H, W, coord_mode, stream);
+}
+
+extern "C++" {
+template <int MODE, typename TY, bool OUT_U8>
+static int fuse_q8_launch(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, const float* t,
+                          const ssm_tensor* out3, const U8Out& u8, const float* norm6, int B, int N, int H, int W, cudaStream_t s) {
+    fuse_fwd_q8_kernel<MODE, TY, OUT_U8><<<q8_grid(B, H, W), Q8_THREADS, 0, s>>>(
+        (const uint4*)quads, cview<float>(flow4), cview<TY>(out5), t, mview<float>(out3), u8, N, make_geom(H, W), make_norm(norm6));
+    SSM_LAUNCH_CHECK("ssm_fuse_flow_fwd_q8");
+    return SSM_OK;
+}
+}  // extern "C++"
+
+static int fuse_q8_impl(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                        const ssm_tensor* out3, const U8Out* u8, const float* norm6, int B, int N, int H, int W,
+                        int coord_mode, void* stream) {
+    SSM_TRY(check_q8("ssm_fuse_flow_fwd_q8", B, N, H, W, coord_mode, quads, norm6));
+    if (out5_dtype != SSM_DTYPE_F32 && out5_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out5_dtype %d", out5_dtype);
+    SSM_TRY(check_tensor(flow4, "flow4", SSM_DTYPE_F32, true));
+    SSM_TRY(check_tensor(out5, "out5", out5_dtype, true));
+    SSM_TRY(check_pairable(flow4, "flow4", SSM_DTYPE_F32));
+    SSM_TRY(check_pairable(out5, "out5", out5_dtype));
+    if (!t) return fail(SSM_ERR_NULL, "t is NULL");
+    U8Out none = {};
+    if (!u8) {
+        SSM_TRY(check_tensor(out3, "out3", SSM_DTYPE_F32, true));
+        SSM_TRY(check_pairable(out3, "out3", SSM_DTYPE_F32));
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+#define SSM_Q8_FUSE(MODE)                                                                                                       \
+    do {                                                                                                                        \
+        if (u8) return out5_dtype == SSM_DTYPE_F32 ? fuse_q8_launch<MODE, float, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s) \
+                                                   : fuse_q8_launch<MODE, __nv_bfloat16, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s); \
+        return out5_dtype == SSM_DTYPE_F32 ? fuse_q8_launch<MODE, float, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s) \
+                                           : fuse_q8_launch<MODE, __nv_bfloat16, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s); \
+    } while (0)
+    if (coord_mode == SSM_COORD_DIV) SSM_Q8_FUSE(SSM_COORD_DIV);
+    SSM_Q8_FUSE(SSM_COORD_RCP);
+#undef SSM_Q8_FUSE
+}
+
+int ssm_fuse_flow_fwd_q8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
+    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, out3, nullptr, norm6, B, N, H, W, coord_mode, stream);
+}
+
+int ssm_fuse_flow_fwd_q8_u8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                            unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int top, int left,
+                            int H_out, int W_out, const float* mean3, const float* std3, float scale, int bgr, int saturate,
+                            const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
+    if (!dst || !mean3 || !std3) return fail(SSM_ERR_NULL, "ssm_fuse_flow_fwd_q8_u8: dst, mean3 or std3 is NULL");
+    if (H_out <= 0 || W_out <= 0 || top < 0 || left < 0 || top + H_out > H || left + W_out > W)
+        return fail(SSM_ERR_SHAPE, "ssm_fuse_flow_fwd_q8_u8: the %d x %d crop at (%d, %d) leaves %d x %d", H_out, W_out, top, left, H, W);
+    U8Out u8;
+    u8.dst = dst; u8.frame_stride = dst_frame_stride; u8.row_stride = dst_row_stride;
+    u8.top = top; u8.left = left; u8.H_out = H_out; u8.W_out = W_out; u8.bgr = bgr != 0; u8.saturate = saturate != 0;
+    for (int k = 0; k < 3; ++k) { u8.mean[k] = mean3[k]; u8.std[k] = std3[k]; }
+    u8.scale = scale;
+    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, nullptr, &u8, norm6, B, N, H, W, coord_mode, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-buffer entry point: pair-sized chunks, three slots of caller-owned device scratch on three
 // streams, so the H2D copy of pair b+1, the kernels of pair b and the D2H copy of pair b-1 overlap.
 static size_t host_slot_bytes(int N, int H, int W) {
@@ -852,6 +1020,106 @@ int ssm_synthesize_host(const float* img6_host, const float* flow4_host, const f
         if (st[i]) {
             e = cudaStreamSynchronize(st[i]);
             if (e != cudaSuccess && rc == SSM_OK) rc = cuda_fail(e, "ssm_synthesize_host sync");
+            cudaStreamDestroy(st[i]);
+        }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry point for 8-bit frames: uint8 images in, uint8 interpolated images out.  Same 3-slot
+// copy/compute pipeline as ssm_synthesize_host; per pair it moves 2 images + flows + the U-Net output up and
+// N images down (the fp32 entry moves 6 + 4 + 5N fp32 planes up and 3N fp32 planes down).
+struct U8Slot {
+    size_t frames, img6, quads, flow, out5, in16, out, t, lut, total;
+};
+static U8Slot u8_slot(int N, int H_in, int W_in, int H, int W, int out5_dtype) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t npx = (size_t)H * W, esz5 = out5_dtype == SSM_DTYPE_F32 ? 4 : 2;
+    U8Slot s; size_t o = 0;
+    s.frames = o; o += up((size_t)2 * H_in * W_in * 3);
+    s.img6 = o;   o += up(6 * npx * 4);
+    s.quads = o;  o += up((size_t)2 * (H + 1) * (W + 1) * 16);
+    s.flow = o;   o += up(4 * npx * 4);
+    s.out5 = o;   o += up((size_t)5 * N * npx * esz5);
+    s.in16 = o;   o += up((size_t)16 * N * npx * 4);
+    s.out = o;    o += up((size_t)N * H_in * W_in * 3);
+    s.t = o;      o += up((size_t)N * 4);
+    s.lut = o;    o += up(768 * 4);
+    s.total = o;
+    return s;
+}
+
+size_t ssm_synthesize_host_u8_scratch_bytes(int B, int N, int H_in, int W_in, int H, int W, int out5_dtype) {
+    if (B <= 0 || N <= 0 || H_in <= 0 || W_in <= 0 || H <= 0 || W <= 0) return 0;
+    return u8_slot(N, H_in, W_in, H, W, out5_dtype).total * (B < 3 ? B : 3);
+}
+
+int ssm_synthesize_host_u8(const unsigned char* frames_host, int bgr, const float* flow4_host, const void* out5_host,
+                           int out5_dtype, const float* t_host, unsigned char* out_host, const float* lut_host,
+                           const float* norm6, const float* mean3, const float* std3, int saturate,
+                           int B, int N, int H_in, int W_in, int H, int W, int top, int left, int coord_mode,
+                           void* scratch_v, size_t scratch_bytes) {
+    SSM_TRY(check_common(B, N, 16, H, W, SSM_DTYPE_F32, coord_mode));
+    if (!frames_host || !flow4_host || !out5_host || !t_host || !out_host || !lut_host || !norm6 || !mean3 || !std3)
+        return fail(SSM_ERR_NULL, "ssm_synthesize_host_u8: a required host pointer is NULL");
+    if (out5_dtype != SSM_DTYPE_F32 && out5_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out5_dtype %d", out5_dtype);
+    if (H_in <= 0 || W_in <= 0 || top < 0 || left < 0 || top + H_in > H || left + W_in > W)
+        return fail(SSM_ERR_SHAPE, "ssm_synthesize_host_u8: the %d x %d images at (%d, %d) do not fit %d x %d", H_in, W_in, top, left, H, W);
+    if (W % 4 != 0) return fail(SSM_ERR_SHAPE, "ssm_synthesize_host_u8: padded width must be a multiple of 4 (got %d)", W);
+    if (!scratch_v || scratch_bytes < ssm_synthesize_host_u8_scratch_bytes(B, N, H_in, W_in, H, W, out5_dtype))
+        return fail(SSM_ERR_WORKSPACE, "ssm_synthesize_host_u8: needs %zu bytes of device scratch, got %zu",
+                    ssm_synthesize_host_u8_scratch_bytes(B, N, H_in, W_in, H, W, out5_dtype), scratch_v ? scratch_bytes : (size_t)0);
+    if (((uintptr_t)scratch_v) % 256 != 0) return fail(SSM_ERR_ALIGN, "scratch must be 256-byte aligned");
+    const U8Slot L = u8_slot(N, H_in, W_in, H, W, out5_dtype);
+    const size_t npx = (size_t)H * W, esz5 = out5_dtype == SSM_DTYPE_F32 ? 4 : 2;
+    const size_t img_bytes = (size_t)H_in * W_in * 3;
+    const int slots = B < 3 ? B : 3;
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    int rc = SSM_OK;
+    cudaError_t e;
+    for (int i = 0; i < slots && rc == SSM_OK; ++i) {
+        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host_u8 cudaStreamCreate");
+    }
+    const float pad3[3] = {lut_host[0], lut_host[256], lut_host[512]};      // byte 0, normalised (pad before normalising)
+    for (int b = 0; b < B && rc == SSM_OK; ++b) {
+        const int k = b % slots;
+        cudaStream_t s = st[k];
+        char* base = (char*)scratch_v + L.total * k;
+        unsigned char* d_frames = (unsigned char*)(base + L.frames);
+        float* d_img = (float*)(base + L.img6);
+        void* d_quads = base + L.quads;
+        float* d_flow = (float*)(base + L.flow);
+        void* d_out5 = base + L.out5;
+        float* d_in16 = (float*)(base + L.in16);
+        unsigned char* d_out = (unsigned char*)(base + L.out);
+        float* d_t = (float*)(base + L.t);
+        float* d_lut = (float*)(base + L.lut);
+#define SSM_H(expr) if (rc == SSM_OK && (e = (expr)) != cudaSuccess) rc = cuda_fail(e, "ssm_synthesize_host_u8 " #expr)
+        SSM_H(cudaMemcpyAsync(d_frames, frames_host + (size_t)b * 2 * img_bytes, 2 * img_bytes, cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_flow, flow4_host + (size_t)b * 4 * npx, 4 * npx * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_t, t_host + (size_t)b * N, N * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (b < slots) SSM_H(cudaMemcpyAsync(d_lut, lut_host, 768 * sizeof(float), cudaMemcpyHostToDevice, s));
+        SSM_H(cudaMemcpyAsync(d_out5, (const char*)out5_host + (size_t)b * N * 5 * npx * esz5, (size_t)N * 5 * npx * esz5, cudaMemcpyHostToDevice, s));
+        if (rc != SSM_OK) break;
+        ssm_tensor T_img{d_img, (int64_t)(3 * npx), 0, (int64_t)npx};            // as F = 2 frames of 3 planes
+        ssm_tensor T_img6{d_img, (int64_t)(6 * npx), 0, (int64_t)npx};
+        ssm_tensor T_flow{d_flow, (int64_t)(4 * npx), 0, (int64_t)npx};
+        ssm_tensor T_out5{d_out5, (int64_t)(5 * N * npx), (int64_t)(5 * npx), (int64_t)npx};
+        ssm_tensor T_in16{d_in16, (int64_t)(16 * N * npx), (int64_t)(16 * npx), (int64_t)npx};
+        rc = ssm_frames_from_u8(d_frames, (long long)img_bytes, W_in * 3, bgr, 2, H_in, W_in, H, W, top, left, d_lut, pad3, &T_img, nullptr,
+                                SSM_DTYPE_F32, s);
+        if (rc == SSM_OK) rc = ssm_quads_from_u8(d_frames, (long long)img_bytes, W_in * 3, bgr, 2, H_in, W_in, H, W, top, left, d_quads, s);
+        if (rc == SSM_OK) rc = ssm_flow_pack_fwd_q8(&T_img6, d_quads, &T_flow, d_t, &T_in16, norm6, 1, N, H, W, coord_mode, s);
+        if (rc == SSM_OK) rc = ssm_fuse_flow_fwd_q8_u8(d_quads, &T_flow, &T_out5, out5_dtype, d_t, d_out, (long long)img_bytes, W_in * 3, top, left,
+                                                       H_in, W_in, mean3, std3, 255.0f, bgr, saturate, norm6, 1, N, H, W, coord_mode, s);
+        SSM_H(cudaMemcpyAsync(out_host + (size_t)b * N * img_bytes, d_out, (size_t)N * img_bytes, cudaMemcpyDeviceToHost, s));
+#undef SSM_H
+    }
+    for (int i = 0; i < slots; ++i)
+        if (st[i]) {
+            e = cudaStreamSynchronize(st[i]);
+            if (e != cudaSuccess && rc == SSM_OK) rc = cuda_fail(e, "ssm_synthesize_host_u8 sync");
             cudaStreamDestroy(st[i]);
         }
     return rc;

@@ -88,3 +88,19 @@ def random_timesteps(B, N=1, seed=SEED + 3, device="cpu"):
 def pad32(n):
     """Reference padding rule: ceil to a multiple of 32 (evaluate_interpolation_results.py:89-90)."""
     return (n + 31) // 32 * 32
+
+
+def images_u8(F_, h, w, seed=SEED, device="cpu", smooth=True):
+    """F x h x w x 3 uint8 images (RGB byte order): the low-passed noise of `frames` quantised to 8 bits, as a decoded
+    video frame is (the reference reads uint8 images, scripts/visualize_interpolation.py:61-72), or white noise."""
+    g = _gen(seed, device)
+    if not smooth:
+        return torch.randint(0, 256, (F_, h, w, 3), dtype=torch.uint8, generator=g, device=device)
+    x = torch.rand((F_, 3, h, w), generator=g, device=device)
+    k = torch.full((3, 1, 5, 5), 1.0 / 25.0, device=device)
+    for _ in range(4):
+        x = F.conv2d(F.pad(x, (2, 2, 2, 2), mode="replicate"), k, groups=3)
+    lo = x.amin(dim=(2, 3), keepdim=True)
+    hi = x.amax(dim=(2, 3), keepdim=True)
+    x = (x - lo) / (hi - lo + 1e-12)
+    return (x.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous()

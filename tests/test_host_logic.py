@@ -314,5 +314,32 @@ def test_fullmodel_accepts_a_partial_config():
     cfg = configparser.RawConfigParser()
     cfg.read_string("[STAGE1]\nBOTTLENECK=CONV\n[STAGE2]\nBOTTLENECK=CONV\nCROSS_SKIP=TRUE\n")
     with torch.device("meta"):
-        m = ssm_b200.FullModel(cfg=cfg)
+        m = ssm_b200.FullModel(cfg=cfg, loss=ssm_b200.losses.SSMLosses(cfg, perceptual_features="zero"))
     assert m.loss.loss_weights == (60.0, 20.0, 10.0) and m.cross_skip
+
+
+def test_perceptual_term_is_never_dropped_silently():
+    """The reference always adds LAMBDA_P * VGG16 conv4_3 L2 (losses.py:12-41, 213).  With LAMBDA_P != 0 the loss module
+    either has the pretrained extractor or refuses to be built; dropping the term takes an explicit opt-out, and an
+    inference-only FullModel still constructs (the failure is deferred to the first training forward)."""
+    import warnings
+    from ssm_b200.losses import SSMLosses
+    try:
+        full = SSMLosses()                       # LAMBDA_P = 20: needs torchvision's pretrained VGG16
+        assert full.perceptual_features is not None
+    except RuntimeError as e:                    # offline
+        assert "VGG16" in str(e) and "perceptual_features" in str(e)
+        with torch.device("meta"):
+            m = ssm_b200.FullModel(cfg=None)
+        assert m.loss is None and "VGG16" in str(m._loss_error)
+        with pytest.raises(RuntimeError, match="no loss module"):
+            m(torch.zeros(1, 2, 3, 32, 32), torch.full((1, 1, 1, 1, 1), 0.5), target_images=torch.zeros(1, 1, 3, 32, 32),
+              inference_mode=False)
+    assert SSMLosses(perceptual_features="zero").perceptual_features is None
+    assert SSMLosses(lambda_p=0.0).perceptual_features is None            # nothing to drop
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        SSMLosses(perceptual_features=None)
+    assert any("DROPPED" in str(x.message) for x in w)
+    rnd = SSMLosses(perceptual_features="random")
+    assert len(rnd.perceptual_features) == 23 and not any(p.requires_grad for p in rnd.perceptual_features.parameters())

@@ -188,3 +188,24 @@ def test_c_oracle_matches_torch_oracle_on_random_small_cases(B, H, W, seed, flow
         scale = max(1.0, gflow.abs().max().item(), gout.abs().max().item())
         assert_close_fp32(gy, gout, "grad out5", tol=2e-5 * scale)
         assert_close_fp32(gf, gflow, "grad flow", tol=2e-5 * scale)
+
+
+# ---- 8-bit frames: the reference's load_batch + normalize_tensor in front of the path ------------------------
+from util import q8_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", q8_cases())
+def test_oracle_on_uint8_frames_matches_reference(name):
+    """tests/golden/make_golden_q8.py ran the reference's own image loading, padding, normalisation,
+    compute_inputs and compute_output_image on uint8 images; the oracle restatements reproduce it."""
+    d = load_golden(name)
+    B = d["flow4"].shape[0]
+    img = torch_oracle.load_batch_and_normalize(d["bgr_u8"].numpy())[0]               # 2B x 3 x H x W
+    img6 = img.reshape(B, 6, *img.shape[-2:]).contiguous()
+    assert torch.equal(img6, d["img6"]), "normalised frames are not bit-identical"
+    for n, tv in enumerate(d["t"].tolist()):
+        t = torch.full((B,), tv)
+        in16 = c_oracle.compute_inputs(img6, d["flow4"], t)
+        assert_close_fp32(in16, d["in16"][:, n], "compute_inputs n=%d" % n)
+        frame = c_oracle.compute_output_image(img6, d["in16"][:, n].contiguous(), d["out5"][:, n].contiguous(), t)
+        assert_close_fp32(frame, d["frames"][:, n], "compute_output_image n=%d" % n)

@@ -1,0 +1,170 @@
+"""GPU suite (-m gpu): the 8-bit-frame entry points (ssm_quads_from_u8, ssm_flow_pack_fwd_q8[_nhwc],
+ssm_fuse_flow_fwd_q8[_u8], ssm_synthesize_host_u8) through the C ABI against
+  * fixtures produced by the reference's own image loading + normalisation + path (tests/golden/make_golden_q8.py),
+  * the C oracle run on the normalised frames (the reference order: normalise, then interpolate),
+  * the fp32 kernels of this library on the same frames,
+and full-size properties at BASELINE.json's size.  Tolerance: 1e-5 (north_star, fp32); the pass-through channels and
+the estimated flows are bit-identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+import ssm_b200
+from oracle import c_oracle, torch_oracle
+from ssm_b200 import q8, synthetic
+from util import assert_close_fp32, load_golden, max_err, q8_cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MODES = [("cpu", c_oracle.COORD_DIV), ("cuda", c_oracle.COORD_RCP)]
+
+
+def _prepared(bgr_u8):
+    """uint8 BGR images (numpy F x h x w x 3) -> device tensors (planar, quads, norm, (top, left))."""
+    images = torch.from_numpy(np.ascontiguousarray(bgr_u8)).to(DEV)
+    # the fixtures come from a CPU run of the reference: the table is filled with the CPU bit pattern of its expression
+    return q8.prepare(images, order="bgr", lut=ssm_b200.normalisation_lut(device="cpu"))
+
+
+@pytest.mark.parametrize("name", q8_cases())
+def test_reference_fixture(name):
+    d = load_golden(name)
+    B, N = d["flow4"].shape[0], d["t"].numel()
+    planar, quads, norm, _ = _prepared(d["bgr_u8"].numpy())
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    assert torch.equal(img6.cpu(), d["img6"]), "normalised frames are not bit-identical to the reference's"
+    t = d["t"].view(1, N).expand(B, N).contiguous()
+    flow4, out5 = d["flow4"].to(DEV), d["out5"].to(DEV)
+    in16 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N)
+    assert torch.equal(in16[:, :, 6:10].cpu(), d["in16"][:, :, 6:10]), "estimated flows not bit-identical"
+    assert torch.equal(in16[:, :, 0:3].cpu(), d["in16"][:, :, 0:3]) and torch.equal(in16[:, :, 13:16].cpu(), d["in16"][:, :, 13:16])
+    assert_close_fp32(in16, d["in16"], "compute_inputs from uint8 frames")
+    frames = q8.fuse_from_flow(quads, flow4, out5, t, norm)
+    assert_close_fp32(frames, d["frames"], "compute_output_image from uint8 frames")
+
+
+def _u8_images(F, h, w, seed, smooth):
+    if smooth:
+        x = synthetic.frames(F, h, w, n_frames=1, seed=seed, smooth=True)
+        x = (x - x.amin()) / (x.amax() - x.amin())
+        return (x.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous()
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (F, h, w, 3), dtype=torch.uint8, generator=g)
+
+
+@pytest.mark.parametrize("mode_name,mode", MODES)
+@pytest.mark.parametrize("B,N,h,w,kind,smooth,flow_px", [
+    (2, 3, 64, 96, "smooth", True, 8.0),
+    (1, 7, 45, 77, "noise", False, 8.0),       # ragged source, padded to 64 x 96
+    (2, 2, 33, 30, "border", True, 8.0),       # samples cross every border of the padded frame
+    (1, 2, 8, 1920, "integer", False, 8.0),
+    (1, 1, 2, 2, "zero", False, 8.0),
+    (2, 2, 352, 352, "smooth", True, 20.0),    # +-100 px flows
+])
+def test_q8_vs_c_oracle(mode_name, mode, B, N, h, w, kind, smooth, flow_px):
+    images = _u8_images(2 * B, h, w, seed=300 + h + w, smooth=smooth)
+    planar, quads, norm, (top, left) = q8.prepare(images.to(DEV), order="rgb", lut=ssm_b200.normalisation_lut(device="cpu"))
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=flow_px, seed=301 + h, kind=kind)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=302 + w)
+    t = synthetic.timesteps(B, N)
+    in16 = q8.flow_pack(img6, quads, flow4.to(DEV), t, norm, n_timesteps=N, coord_mode=mode_name)
+    frames = q8.fuse_from_flow(quads, flow4.to(DEV), out5.to(DEV), t, norm, coord_mode=mode_name)
+    img6_c = img6.cpu()
+    worst16 = worst3 = 0.0
+    for n in range(N):
+        r16 = c_oracle.compute_inputs(img6_c, flow4, t[:, n], coord_mode=mode)
+        assert torch.equal(in16[:, n, 6:10].cpu(), r16[:, 6:10]), "estimated flows not bit-identical"
+        assert torch.equal(in16[:, n, 0:3].cpu(), r16[:, 0:3]) and torch.equal(in16[:, n, 13:16].cpu(), r16[:, 13:16])
+        worst16 = max(worst16, assert_close_fp32(in16[:, n], r16, "q8 flow_pack n=%d" % n))
+        r3 = c_oracle.compute_output_image(img6_c, r16, out5[:, n].contiguous(), t[:, n], coord_mode=mode)
+        worst3 = max(worst3, assert_close_fp32(frames[:, n], r3, "q8 fuse n=%d" % n))
+    print("q8 vs C oracle %s %dx%d: warped %.2e fused %.2e" % (mode_name, H, W, worst16, worst3))
+
+
+def test_q8_layouts_and_bf16_unet_output():
+    """channels-last / bf16 stage-2 input and a bf16 U-Net output, against the planar fp32 q8 kernels"""
+    B, N, h, w = 2, 3, 40, 62
+    images = _u8_images(2 * B, h, w, seed=77, smooth=True)
+    planar, quads, norm, _ = q8.prepare(images.to(DEV))
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=8.0, seed=78).to(DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=79).to(DEV)
+    t = synthetic.timesteps(B, N)
+    ref16 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N)
+    cl32 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N, channels_last_dtype=torch.float32)
+    assert cl32.stride() == (N * 16 * H * W, 16 * H * W, 1, 16 * W, 16) and torch.equal(cl32, ref16)
+    cl16 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N, channels_last_dtype=torch.bfloat16)
+    assert torch.equal(cl16, ref16.bfloat16()), "channels-last bf16 is not the fp32 result rounded once"
+    y16 = out5.bfloat16()
+    a = q8.fuse_from_flow(quads, flow4, y16, t, norm)
+    b = q8.fuse_from_flow(quads, flow4, y16.float(), t, norm)
+    assert torch.equal(a, b), "a bf16 U-Net output must read as its fp32 widening"
+
+
+@pytest.mark.parametrize("order", ["bgr", "rgb"])
+def test_q8_uint8_output_matches_unfused_pipeline(order):
+    """ssm_fuse_flow_fwd_q8_u8 == ssm_fuse_flow_fwd_q8 followed by ssm_frames_to_u8 (crop, de-normalise, clamp)"""
+    B, N, h, w = 2, 2, 45, 70
+    images = _u8_images(2 * B, h, w, seed=91, smooth=True)
+    planar, quads, norm, (top, left) = q8.prepare(images.to(DEV), order=order)
+    H, W = planar.shape[-2:]
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=6.0, seed=92).to(DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=93).to(DEV)
+    t = synthetic.timesteps(B, N)
+    frames = q8.fuse_from_flow(quads, flow4, out5, t, norm)
+    want = ssm_b200.frames_to_u8(frames.view(B * N, 3, H, W), top=top, left=left, h_out=h, w_out=w, order=order, saturate=True)
+    got = q8.fuse_from_flow_to_u8(quads, flow4, out5, t, norm, crop=(top, left, h, w), order=order, saturate=True)
+    assert torch.equal(got.view(B * N, h, w, 3), want)
+    # zero flow + a visibility that selects frame 0 reproduces the source image exactly
+    zf = torch.zeros_like(flow4)
+    y0 = torch.zeros_like(out5)
+    y0[:, :, 0] = -40.0                                      # V_t<-1 = sigmoid(-40) = 0: only frame 0 contributes
+    back = q8.fuse_from_flow_to_u8(quads, zf, y0, t, norm, crop=(top, left, h, w), order=order, saturate=True)
+    src0 = images.view(B, 2, h, w, 3)[:, 0].to(DEV)
+    diff = (back.int() - src0.unsqueeze(1).int()).abs().max().item()
+    assert diff <= 1, "zero-flow round trip moved a byte by %d" % diff      # (x*std+mean)*255 truncates: off by one at most
+
+
+def test_q8_host_entry_matches_device_path():
+    B, N, h, w = 3, 3, 45, 70
+    images = _u8_images(2 * B, h, w, seed=55, smooth=True).view(B, 2, h, w, 3).contiguous()
+    planar, quads, norm, (top, left) = q8.prepare(images.view(2 * B, h, w, 3).to(DEV))
+    H, W = planar.shape[-2:]
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=6.0, seed=56)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=57)
+    t = synthetic.timesteps(B, N)
+    want = q8.fuse_from_flow_to_u8(quads, flow4.to(DEV), out5.to(DEV), t, norm, crop=(top, left, h, w))
+    got = q8.synthesize_host(images.pin_memory(), flow4.pin_memory(), out5.pin_memory(), t)
+    assert torch.equal(got, want.cpu())
+    got16 = q8.synthesize_host(images.pin_memory(), flow4.pin_memory(), out5.bfloat16().pin_memory(), t)
+    want16 = q8.fuse_from_flow_to_u8(quads, flow4.to(DEV), out5.bfloat16().to(DEV), t, norm, crop=(top, left, h, w))
+    assert torch.equal(got16, want16.cpu())
+
+
+def test_q8_full_size_against_fp32_kernels():
+    """BASELINE.json configs[1] size (4 of the 16 pairs): the 8-bit path against this library's fp32 kernels on the
+    normalised frames -- two independent gather implementations -- plus one C-oracle slice."""
+    B, N, h, w = 4, 7, 1080, 1920
+    images = _u8_images(2 * B, h, w, seed=11, smooth=True)
+    planar, quads, norm, _ = q8.prepare(images.to(DEV))
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=12, device=DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=13, device=DEV)
+    t = synthetic.timesteps(B, N, device=DEV)
+    in16 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N)
+    frames = q8.fuse_from_flow(quads, flow4, out5, t, norm)
+    ref16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=N)
+    ref3 = ssm_b200.fuse_from_flow(img6, flow4, out5, t)
+    assert torch.equal(in16[:, :, 6:10], ref16[:, :, 6:10]) and torch.equal(in16[:, :, 0:3], ref16[:, :, 0:3])
+    e16, e3 = max_err(in16, ref16), max_err(frames, ref3)
+    print("q8 vs fp32 kernels at 1088x1920: warped %.2e fused %.2e" % (e16, e3))
+    assert e16 <= 1e-5 and e3 <= 1e-5
+    # one oracle slice: rows 500..507 of pair 1, timestep 3 (the oracle computes whole frames: restrict the comparison)
+    r16 = c_oracle.compute_inputs(img6[1:2].cpu(), flow4[1:2].cpu(), t[1:2, 3].cpu())
+    assert_close_fp32(in16[1, 3, :, 500:508], r16[0, :, 500:508], "q8 flow_pack vs C oracle at full size")

@@ -18,7 +18,12 @@ BF16_RTOL = 2.0 ** -7
 def golden_cases():
     """hot-path fixtures (warp / compute_inputs / compute_output_image)"""
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("loop_") and not n.startswith("frames_"))
+                  if not n.startswith(("loop_", "frames_", "q8_", "large_", "sliding_")))
+
+
+def q8_cases():
+    """8-bit-frame fixtures (the reference's load_batch + normalize_tensor + compute_inputs / compute_output_image)"""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "q8_*.npz"))))
 
 
 def loop_cases():

@@ -4,20 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): 16 synthetic 1088x1920 (1080p padded to /32) frame pairs per
-GPU, 7 intermediate timesteps, fp32.  One step = one pass of the hot path over the batch:
-an RGBx staging copy of the frames (one launch), compute_inputs for all 7 timesteps (one fused launch)
-and extract_outputs/compute_output_image for all 7 timesteps (one fused launch, estimated flows
-recomputed in-kernel from the stage-1 flows: ssm_fuse_flow_fwd) = 112 interpolated frames per GPU.  The two flow U-Nets are out of
-scope (they stay on PyTorch/cuDNN); the stage-2 output is a seeded surrogate.
+Workload (BASELINE.json configs[1]): 16 synthetic 1080p frame pairs per GPU, 7 intermediate timesteps.  The frames are
+8-bit images (what a decoded video frame is and what the reference reads, scripts/visualize_interpolation.py:61-72),
+1080x1920 centred in 1088x1920 (padded to /32 with byte 0, :76-87), normalised with the reference's expression.
+One step = one pass of the hot path over the batch:
+    ssm_quads_from_u8        staging: the 2x2 byte entry tables the gathers read (one launch; charged to the step's time,
+                             not to its bytes)
+    ssm_flow_pack_fwd_q8     compute_inputs for all 7 timesteps (one launch)
+    ssm_fuse_flow_fwd_q8     extract_outputs + compute_output_image for all 7 timesteps (one launch)
+= 112 interpolated frames per GPU.  The two flow U-Nets are out of scope (they stay on PyTorch/cuDNN); the stage-1
+flows and the stage-2 output are seeded surrogates.
 
-  value      frames/s, inputs resident in HBM, device-timed with CUDA events, max over ranks
-  e2e        same metric through ssm_synthesize_host: pinned HOST buffers in, fused frames out,
-             host<->device copies inside the timed region
-  roofline   dominant kernel (flow_pack_fwd) algorithmic bytes / event-timed duration vs measured HBM peak
-  cpu_baseline  the reference's torch-op path (oracle/torch_oracle.py, kind "port") on the host cores,
-             rank 0, bounded sample
---impl reference times that CPU path as an arm of its own.
+  value        frames/s, inputs resident in HBM, device-timed with CUDA events, max over ranks
+  e2e          same metric through ssm_synthesize_host_u8: pinned HOST buffers (uint8 frames, fp32 flows, bf16 U-Net output)
+               in, uint8 interpolated images out, host<->device copies inside the timed region
+  roofline     dominant kernel (compute_inputs: 65 % of the path's bytes), algorithmic bytes / event-timed duration vs the
+               measured HBM peak; roofline_kernels lists every kernel of the path, both frame formats
+  fp32_frames_path  the same step for callers that hold normalised fp32 frames (the reference's tensor interface and the
+               round-1 headline): ssm_pack_frames + ssm_flow_pack_fwd + ssm_fuse_flow_fwd
+  configs      BASELINE.json configs[2..4]: C3 training step (DDP), C4 SSMR windows, C5 4K x 31 timesteps (tools/bench_configs.py)
+  cpu_baseline the reference's torch-op path (oracle/torch_oracle.py, kind "port") on the host cores, rank 0, bounded sample
+  reference_gpu  the reference's torch-op path on this GPU (cuDNN sampler on / off), same workload
+--impl reference times the CPU path as an arm of its own, on the same 16-pair workload.
 """
 import argparse
 import json
@@ -32,10 +40,21 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+H_IN, W_IN = 1080, 1920
 H, W, PAIRS, NT = 1088, 1920, 16, 7
 NPX = H * W
 WORKLOAD = "ssm_original_1080p_b16_n7"
 METRIC = "interpolated_1080p_frames_per_sec"
+
+
+def config_dict(world):
+    """`config` of the JSON line, identical in both arms"""
+    return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
+            "frames": "uint8 %dx%d images centred in %dx%d, normalised with the reference's mean/std" % (H_IN, W_IN, H, W),
+            "frames_per_step": PAIRS * NT * world,
+            "l2": "inputs_exceed_l2 (8.7 GB read, 18.9 GB written per step)",
+            "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
+            "parallelism": "pairs sharded over %d rank(s), no collective" % world}
 
 
 def _peaks():
@@ -48,12 +67,12 @@ def _peaks():
 
 
 def _traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    """DRAM bytes per launch of every profiled kernel, from the committed ncu --set full captures."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get("flow_pack_fwd_dram_bytes_per_launch")
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
 class ClockSampler:
@@ -149,65 +168,108 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(sample):
-    """One bounded sample of the reference CPU path: compute_inputs + compute_output_image once per
-    timestep, as the reference's loops do (evaluate_interpolation_results.py:234-242)."""
-    from oracle import torch_oracle
-    img6, flow4, out5, t = sample
-    outs = []
-    with torch.no_grad():
-        for n in range(t.shape[1]):
-            tn = t[:, n].view(-1, 1, 1, 1)
-            in16 = torch_oracle.compute_inputs(img6, flow4, tn)
-            outs.append(torch_oracle.compute_output_image(img6, in16, out5[:, n], tn))
-    return outs
-
-
-def cpu_sample(pairs=1):
+# The reference's own path: uint8 images -> load_batch padding + normalize_tensor -> compute_inputs +
+# compute_output_image once per timestep, as its loops do (evaluate_interpolation_results.py:234-242).
+def reference_sample(pairs, device="cpu", seed=42):
     from ssm_b200 import synthetic
-    img6 = synthetic.frames(pairs, H, W, seed=42)
-    flow4 = synthetic.flows(pairs, H, W, 4, flow_px=20.0, seed=43)
-    out5 = synthetic.unet_out5(pairs, NT, H, W, seed=44)
-    t = synthetic.timesteps(pairs, NT)
-    return img6, flow4, out5, t
+    images = synthetic.images_u8(2 * pairs, H_IN, W_IN, seed=seed, device=device)
+    flow4 = synthetic.flows(pairs, H, W, 4, flow_px=20.0, seed=seed + 1, device=device)
+    out5 = synthetic.unet_out5(pairs, NT, H, W, seed=seed + 2, device=device)
+    t = synthetic.timesteps(pairs, NT, device=device)
+    return images, flow4, out5, t
 
 
-def time_cpu_reference(steps, warmup, pairs=1):
+def reference_step(sample, chunk=2):
+    """the whole sample, `chunk` pairs at a time (the reference's op sequence materialises ~750 B/px of temporaries
+    per call: 16 pairs at once would need ~25 GB)"""
+    from oracle import torch_oracle
+    images, flow4, out5, t = sample
+    pairs = flow4.shape[0]
+    count = 0
+    with torch.no_grad():
+        for b in range(0, pairs, chunk):
+            e = min(b + chunk, pairs)
+            # images are RGB here; load_batch_and_normalize takes cv2's BGR order
+            frames = torch_oracle.load_batch_and_normalize(images[2 * b:2 * e].flip(-1).cpu().numpy(), device=flow4.device)[0]
+            img6 = frames.reshape(e - b, 6, H, W)
+            for n in range(NT):
+                tn = t[b:e, n].view(-1, 1, 1, 1)
+                in16 = torch_oracle.compute_inputs(img6, flow4[b:e], tn)
+                frame = torch_oracle.compute_output_image(img6, in16, out5[b:e, n], tn)      # noqa: F841 (the result)
+                count += frame.shape[0]
+                del in16
+    return count
+
+
+def time_cpu_reference(steps, warmup, pairs):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = cpu_sample(pairs)
+    sample = reference_sample(pairs)
+    warm = reference_sample(1) if pairs > 1 else sample     # warm-up on one pair: it is untimed
     for _ in range(warmup):
-        cpu_reference_step(sample)
+        reference_step(warm)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_reference_step(sample)
+        reference_step(sample)
         times.append(time.perf_counter() - t0)
-    frames = pairs * NT
-    return frames, times, cores
+    return pairs * NT, times, cores
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    frames, times, cores = time_cpu_reference(args.steps, args.warmup)
+    # the full 16-pair workload per step (about 9 s on 16 cores); warm-up steps run one pair
+    frames, times, cores = time_cpu_reference(args.steps, min(args.warmup, 2), PAIRS)
     total = sum(times)
     value = frames * len(times) / total
-    sample = "%d pair x %d timesteps at %dx%d per step (of the %d-pair workload), torch CPU ops, %d threads" % (
-        1, NT, H, W, PAIRS, cores)
+    sample = ("the whole %d-pair x %d-timestep workload per step (%d frames) at %dx%d; uint8 frames normalised by the "
+              "reference's expression, then compute_inputs + compute_output_image per timestep; torch CPU ops, %d threads; "
+              "warm-up steps on one pair") % (PAIRS, NT, frames, H, W, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
-                   "frames_per_step": frames, "l2": "inputs_exceed_l2"},
+        "config": config_dict(1),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def time_reference_on_gpu(dev, chunk=4):
+    """The reference's torch-op path on this GPU (what SURVEY.md section 2b names as the bar on the same box,
+    scripts/models/layers.py:119): 16 pairs x 7 timesteps, in chunks of `chunk` pairs (the op sequence materialises
+    ~750 B/px of temporaries per call), cuDNN's spatial-transformer sampler on and off (= ATen's grid_sampler)."""
+    images, flow4, out5, t = reference_sample(PAIRS, device=dev)
+    res = {}
+    for name, flag in (("cudnn_on", True), ("cudnn_off", False)):
+        prev = torch.backends.cudnn.enabled
+        torch.backends.cudnn.enabled = flag
+        try:
+            def run():
+                reference_step((images, flow4, out5, t), chunk=chunk)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            res[name] = {"ms_per_step": ms, "frames_per_s": PAIRS * NT / (ms * 1e-3)}
+        except Exception as e:
+            res[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        finally:
+            torch.backends.cudnn.enabled = prev
+        torch.cuda.empty_cache()
+    res["note"] = ("oracle/torch_oracle.py == the reference's op sequence (~110 ATen launches and two host-built sampling grids "
+                   "per timestep), run on cuda:0 outside the product; %d pairs x %d timesteps in chunks of %d pairs" % (PAIRS, NT, chunk))
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -231,6 +293,39 @@ def whole_model_step(timeout_s=300):
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
+def host_copy_ceiling(dev, world, nbytes=1 << 30, reps=3):
+    """Plain pinned-memory copies, H2D and D2H at the same time on two streams, all ranks at once: the bandwidth the
+    host side of this box gives `world` GPUs, i.e. the ceiling of any host-buffer entry point."""
+    import torch.distributed as dist
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+    gbs = nbytes * reps / dt / 1e9
+    return {"h2d_gbs_per_gpu": gbs, "d2h_gbs_per_gpu": gbs, "aggregate_each_direction_gbs": gbs * world,
+            "how": "1 GiB pinned H2D and 1 GiB pinned D2H concurrently on two streams, %d rank(s) at once, max time over ranks" % world}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,7 +336,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the backward-kernel timings")
-    ap.add_argument("--no-variants", action="store_true", help="skip the smooth-flow and bf16-storage variants")
+    ap.add_argument("--no-variants", action="store_true", help="skip the smooth-flow, bf16-storage and layout variants")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[2..4] (C3 training step, C4 SSMR, C5 4K)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's torch-op path on this GPU")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -251,7 +348,7 @@ def main():
 
     import torch.distributed as dist
     import ssm_b200
-    from ssm_b200 import sharding, synthetic
+    from ssm_b200 import q8, sharding, synthetic
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the synthesis path has no CPU fallback")
@@ -268,24 +365,52 @@ def main():
     B = len(work)
     assert B == PAIRS and all(t0 == 0 and t1 == NT for _, t0, t1 in work)
     seed0 = 42 + 1000 * rank
-    img6 = synthetic.frames(B, H, W, seed=seed0, device=dev)
+    images = synthetic.images_u8(2 * B, H_IN, W_IN, seed=seed0, device=dev)          # 2B x 1080 x 1920 x 3, RGB bytes
+    lut = ssm_b200.normalisation_lut(device="cpu").to(dev)       # the CPU bit pattern of the reference's expression
+    planar, quads, norm, (top, left) = q8.prepare(images, order="rgb", lut=lut, pad_values=lut[:, 0].tolist())
+    img6 = planar.view(B, 6, H, W)                                 # the normalised frames (pre-step, as in the reference)
     flow4 = synthetic.flows(B, H, W, 4, flow_px=20.0, seed=seed0 + 1, device=dev)
     out5 = synthetic.unet_out5(B, NT, H, W, seed=seed0 + 2, device=dev)
     t = synthetic.timesteps(B, NT, device=dev)
 
     # caller-owned result buffers (out=): the steady-state loop makes no allocator calls, so no
     # cudaMalloc (which synchronises and maps pages) can land inside the timed region
-    rgbx_buf = torch.empty((B, 2, H, W, 4), dtype=torch.float32, device=dev)
     in16_buf = torch.empty((B, NT, 16, H, W), dtype=torch.float32, device=dev)
     frames_buf = torch.empty((B, NT, 3, H, W), dtype=torch.float32, device=dev)
+    rgbx_buf = torch.empty((B, 2, H, W, 4), dtype=torch.float32, device=dev)
+    L = ssm_b200._abi.lib()
+    import ctypes
+    quads_ptr, images_ptr = ctypes.c_void_p(quads.data_ptr()), ctypes.c_void_p(images.data_ptr())
+    stream = ssm_b200._abi.stream_ptr(dev)
+
+    def stage_quads():
+        rc = L.ssm_quads_from_u8(images_ptr, images.stride(0), images.stride(1), 0, 2 * B, H_IN, W_IN, H, W, top, left, quads_ptr, stream)
+        ssm_b200._abi.check(rc, "ssm_quads_from_u8")
 
     def step(flow=None, y=None, events=None):
-        """One pass of the hot path over the batch: RGBx staging copy + the two fused launches."""
+        """One pass of the hot path over the batch: entry-table staging + the two fused launches."""
         f = flow4 if flow is None else flow
         with torch.no_grad():
             if events:
                 events[0].record()
-            rgbx = ssm_b200.pack_frames(img6, out=rgbx_buf)      # RGBx staging copy, shared by both kernels
+            stage_quads()
+            if events:
+                events[1].record()
+            in16 = q8.flow_pack(img6, quads, f, t, norm, n_timesteps=NT, out=in16_buf)
+            if events:
+                events[2].record()
+            frames = q8.fuse_from_flow(quads, f, out5 if y is None else y, t, norm, out=frames_buf)
+            if events:
+                events[3].record()
+        return in16, frames
+
+    def step_fp32(flow=None, y=None, events=None):
+        """The same step for normalised fp32 frames (the reference's tensor interface; round-1 headline)."""
+        f = flow4 if flow is None else flow
+        with torch.no_grad():
+            if events:
+                events[0].record()
+            rgbx = ssm_b200.pack_frames(img6, out=rgbx_buf)
             if events:
                 events[1].record()
             in16 = ssm_b200.flow_pack(img6, f, t, n_timesteps=NT, packed=rgbx, out=in16_buf)
@@ -323,40 +448,48 @@ def main():
         tt = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = tt.item()
-    rgbx_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
-    pack_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
-    fuse_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev)
-    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
     frames_per_step = B * NT * world
     value = frames_per_step * K / (elapsed_ms * 1e-3)
 
-    # roofline of the dominant kernel: algorithmic bytes = (10 + 16 N) * 4 B/px per pair
+    # ---- roofline: algorithmic bytes per SURVEY 8(d), the reference's fp32 tensors read / written once ----------------
+    #   compute_inputs          (10 + 16 N) * 4 B/px per pair
+    #   compute_output_image    (10 + 8 N) * 4 B/px per pair (estimated flows recomputed from the stage-1 flows)
     peak, peak_src = _peaks()
+    traffic = _traffic()
     pack_bytes = (10 + 16 * NT) * 4 * NPX * B
-    # a3+a4 with the estimated flows recomputed from flow4: reads I (6) + F (4) per pair and out5 (5) per
-    # timestep, writes 3 per timestep (the reference-shaped call that re-reads in16[:, 6:10] is (6 + 12 N))
     fuse_bytes = (10 + 8 * NT) * 4 * NPX * B
-    pack_gbs = pack_bytes / (pack_ms * 1e-3) / 1e9
-    fuse_gbs = fuse_bytes / (fuse_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "flow_pack_fwd_kernel<float>", "achieved": pack_gbs, "peak": peak,
-                "unit": "GB/s", "frac": pack_gbs / peak, "traffic": _traffic(), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": pack_bytes, "launch_ms": pack_ms,
-                "frac_of_nominal_8tbs": pack_gbs / 8000.0}
-    # the RGBx staging copy is overhead, not algorithmic traffic: it is charged to the path's time
-    # but not to its bytes
-    rgbx_bytes = (6 + 8) * 4 * NPX * B
-    path_ms = rgbx_ms + pack_ms + fuse_ms
-    path_gbs = (pack_bytes + fuse_bytes) / (path_ms * 1e-3) / 1e9
-    kernels = {
-        "pack_frames": {"ms": rgbx_ms, "moved_gbs": rgbx_bytes / (rgbx_ms * 1e-3) / 1e9, "note": "staging copy, overhead"},
-        "flow_pack_fwd": {"ms": pack_ms, "algorithmic_gbs": pack_gbs, "frac_of_peak": pack_gbs / peak},
-        "fuse_fwd": {"ms": fuse_ms, "algorithmic_gbs": fuse_gbs, "frac_of_peak": fuse_gbs / peak},
-        "path": {"ms": path_ms, "algorithmic_gbs": path_gbs, "frac_of_peak": path_gbs / peak},
-        "step_ms_distribution": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
-    }
 
-    # same kernels on a smooth flow field (control grid at 1/64 resolution): real optical flow is
-    # piecewise smooth; the headline workload above uses SURVEY 8(d)'s much rougher 1/8-resolution field
+    def kernel_table(evs, names, staging_bytes):
+        ms = [statistics.mean(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(3)]
+        gbs = [staging_bytes / (ms[0] * 1e-3) / 1e9, pack_bytes / (ms[1] * 1e-3) / 1e9, fuse_bytes / (ms[2] * 1e-3) / 1e9]
+        path_ms = sum(ms)
+        path_gbs = (pack_bytes + fuse_bytes) / (path_ms * 1e-3) / 1e9
+        step_ms = [e[0].elapsed_time(e[3]) for e in evs]
+        tab = {
+            names[0]: {"ms": ms[0], "moved_gbs": gbs[0], "note": "staging, overhead: charged to the path's time, not to its bytes"},
+            names[1]: {"ms": ms[1], "algorithmic_gbs": gbs[1], "frac_of_peak": gbs[1] / peak},
+            names[2]: {"ms": ms[2], "algorithmic_gbs": gbs[2], "frac_of_peak": gbs[2] / peak},
+            "path": {"ms": path_ms, "algorithmic_gbs": path_gbs, "frac_of_peak": path_gbs / peak,
+                     "frac_of_nominal_8tbs": path_gbs / 8000.0},
+            "step_ms_distribution": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
+        }
+        return tab, ms, gbs
+
+    quads_bytes = (2 * 3 * H_IN * W_IN + 2 * 16 * (H + 1) * (W + 1)) * B
+    kernels, kms, kgbs = kernel_table(ev, ("quads_from_u8", "flow_pack_fwd_q8", "fuse_fwd_q8"), quads_bytes)
+    roofline = {"bound": "hbm", "kernel": "flow_pack_fwd_q8_kernel", "achieved": kgbs[1], "peak": peak,
+                "unit": "GB/s", "frac": kgbs[1] / peak, "traffic": traffic.get("flow_pack_fwd_q8_dram_bytes_per_launch"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": pack_bytes, "launch_ms": kms[1],
+                "frac_of_nominal_8tbs": kgbs[1] / 8000.0}
+    roofline_kernels = [
+        {"kernel": "flow_pack_fwd_q8_kernel", "frames": "uint8", "bound": "hbm", "achieved": kgbs[1], "peak": peak, "unit": "GB/s",
+         "frac": kgbs[1] / peak, "algorithmic_bytes_per_launch": pack_bytes, "launch_ms": kms[1],
+         "traffic": traffic.get("flow_pack_fwd_q8_dram_bytes_per_launch")},
+        {"kernel": "fuse_fwd_q8_kernel", "frames": "uint8", "bound": "hbm", "achieved": kgbs[2], "peak": peak, "unit": "GB/s",
+         "frac": kgbs[2] / peak, "algorithmic_bytes_per_launch": fuse_bytes, "launch_ms": kms[2],
+         "traffic": traffic.get("fuse_fwd_q8_dram_bytes_per_launch")},
+    ]
+
     def timed(fn, reps=10, warm=3):
         for _ in range(warm):
             fn()
@@ -373,6 +506,27 @@ def main():
         return {"ms_per_step": ms, "frames_per_s": B * NT / (ms * 1e-3),
                 "path_algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "path_frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
 
+    # ---- the same step on normalised fp32 frames (RGBx staging copy + fp32 gathers): every rank, 10 steps -------------
+    for _ in range(3):
+        step_fp32()
+    torch.cuda.synchronize()
+    ev32 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(10)]
+    for k in range(10):
+        step_fp32(events=ev32[k])
+    torch.cuda.synchronize()
+    fp32_path, fms, fgbs = kernel_table(ev32, ("pack_frames", "flow_pack_fwd", "fuse_fwd"), (6 + 8) * 4 * NPX * B)
+    fp32_path["frames_per_s_this_rank"] = B * NT / (fp32_path["path"]["ms"] * 1e-3)
+    fp32_path["note"] = ("callers that hold normalised fp32 frames (the reference's tensor interface): RGBx staging copy + fp32 "
+                         "16-byte gathers; round-1 headline workload, same flows / U-Net output / times")
+    roofline_kernels += [
+        {"kernel": "flow_pack_fwd_kernel<float>", "frames": "fp32", "bound": "hbm", "achieved": fgbs[1], "peak": peak, "unit": "GB/s",
+         "frac": fgbs[1] / peak, "algorithmic_bytes_per_launch": pack_bytes, "launch_ms": fms[1],
+         "traffic": traffic.get("flow_pack_fwd_dram_bytes_per_launch")},
+        {"kernel": "fuse_fwd_kernel<float, RECOMP>", "frames": "fp32", "bound": "hbm", "achieved": fgbs[2], "peak": peak, "unit": "GB/s",
+         "frac": fgbs[2] / peak, "algorithmic_bytes_per_launch": fuse_bytes, "launch_ms": fms[2],
+         "traffic": traffic.get("fuse_fwd_dram_bytes_per_launch")},
+    ]
+
     smooth = smooth_res = bf16 = layouts = None
     if rank == 0 and not args.no_variants:
         gen = torch.Generator(device=dev).manual_seed(7)
@@ -381,8 +535,11 @@ def main():
             c = torch.randn(lead + (B, ch, H // div, W // div), device=dev, generator=gen) * scale
             return torch.nn.functional.interpolate(c.view(-1, ch, H // div, W // div), size=(H, W), mode="bilinear",
                                                    align_corners=False).view(lead + (B, ch, H, W)).contiguous()
+        # same kernels on a smooth flow field (control grid at 1/64 resolution): real optical flow is piecewise smooth;
+        # the headline workload uses SURVEY 8(d)'s much rougher 1/8-resolution field
         flow_s = lowres(4, 64, 20.0)
         smooth = variant(timed(lambda: step(flow_s)), pack_bytes + fuse_bytes)
+        smooth["fp32_frames_ms_per_step"] = timed(lambda: step_fp32(flow_s))
         # ... and with a spatially smooth stage-2 output as well (a trained U-Net's residual flows and
         # visibility logits are smooth; the surrogate of the headline workload is white noise)
         y_s = torch.empty_like(out5)
@@ -391,8 +548,9 @@ def main():
         y_s[:, :, 0] *= 2.0
         y_s[:, :, 1:] *= 0.5
         smooth_res = variant(timed(lambda: step(flow_s, y_s)), pack_bytes + fuse_bytes)
+        smooth_res["fp32_frames_ms_per_step"] = timed(lambda: step_fp32(flow_s, y_s))
         del flow_s, y_s
-        # bf16 storage, fp32 arithmetic (north_star tolerance 2e-2): half the bytes per element
+        # bf16 storage of every tensor, fp32 arithmetic (north_star tolerance 2e-2): half the bytes per element
         img_h, flow_h, out5_h = img6.bfloat16(), flow4.bfloat16(), out5.bfloat16()
 
         def step_bf16():
@@ -401,40 +559,33 @@ def main():
                 a = ssm_b200.flow_pack(img_h, flow_h, t, n_timesteps=NT, packed=r)
                 return a, ssm_b200.fuse_from_flow(img_h, flow_h, out5_h, t, packed=r)
         bf16 = variant(timed(step_bf16), (pack_bytes + fuse_bytes) // 2)
-        bf16["note"] = "bf16 storage of every tensor, fp32 arithmetic; not the headline (the reference is fp32)"
-        del img_h, flow_h
+        bf16["note"] = ("bf16 storage of every tensor (RGBx bf16 gathers), fp32 arithmetic; not the headline (the reference is fp32); "
+                        "uint8_frames: the same with the gathers reading the uint8 entry tables")
+        in16_h = torch.empty((B, NT, 16, H, W), dtype=torch.bfloat16, device=dev)
+        frames_h = torch.empty((B, NT, 3, H, W), dtype=torch.bfloat16, device=dev)
+
+        def step_bf16_q8():
+            with torch.no_grad():
+                stage_quads()
+                a = q8.flow_pack(img_h, quads, flow_h, t, norm, n_timesteps=NT, out=in16_h)
+                return a, q8.fuse_from_flow(quads, flow_h, out5_h, t, norm, out=frames_h)
+        bf16["uint8_frames"] = variant(timed(step_bf16_q8), (pack_bytes + fuse_bytes) // 2)
+        del img_h, flow_h, in16_h, frames_h
         # the layouts either side of a channels-last stage-2 U-Net under bf16 autocast:
-        # compute_inputs writes B x N x H x W x 16 bf16, compute_output_image reads a bf16 U-Net output;
-        # frames, flows and the fused frames stay fp32
+        # compute_inputs writes B x N x H x W x 16 bf16, compute_output_image reads a bf16 U-Net output
         nhwc_buf = torch.empty((B, NT, H, W, 16), dtype=torch.bfloat16, device=dev).permute(0, 1, 4, 2, 3)
 
         def step_layouts():
             with torch.no_grad():
-                r = ssm_b200.pack_frames(img6, out=rgbx_buf)
-                a = ssm_b200.flow_pack_channels_last(img6, flow4, t, n_timesteps=NT, dtype=torch.bfloat16, packed=r,
-                                                     out=nhwc_buf)
-                return a, ssm_b200.fuse_from_flow(img6, flow4, out5_h, t, packed=r, out=frames_buf)
+                stage_quads()
+                a = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=NT, out=nhwc_buf, channels_last_dtype=torch.bfloat16)
+                return a, q8.fuse_from_flow(quads, flow4, out5_h, t, norm, out=frames_buf)
         layouts = variant(timed(step_layouts), ((10 * 4 + 16 * 2 * NT) + (10 * 4 + (5 * 2 + 3 * 4) * NT)) * NPX * B)
+        layouts["note"] = ("compute_inputs written channels-last bf16 (what conv1a consumes under channels-last bf16 autocast) and the "
+                           "bf16 U-Net output read directly; uint8 frames, fp32 flows and result; not the headline")
+        del out5_h, nhwc_buf
 
-        # what the generic plumbing does for the same U-Net: planar fp32 compute_inputs, one torch pass that
-        # converts it to channels-last bf16, one that widens the bf16 U-Net output to fp32
-        out5_f = torch.empty_like(out5)
-
-        def step_generic():
-            with torch.no_grad():
-                r = ssm_b200.pack_frames(img6, out=rgbx_buf)
-                a = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=NT, packed=r, out=in16_buf)
-                nhwc_buf.copy_(a)
-                out5_f.copy_(out5_h)
-                return ssm_b200.fuse_from_flow(img6, flow4, out5_f, t, packed=r, out=frames_buf)
-        layouts["generic_ms_per_step"] = timed(step_generic)
-        layouts["note"] = ("compute_inputs written channels-last bf16 (what conv1a consumes under channels-last bf16 "
-                           "autocast) and the bf16 U-Net output read directly; generic_ms_per_step = the planar fp32 "
-                           "kernels plus the two torch conversion passes they need for the same U-Net; fp32 "
-                           "frames/flows/result; not the headline")
-        del out5_h, nhwc_buf, out5_f
-
-    # ---- training backward of the same kernels (flow / U-Net-output gradients; frames are data) ----
+    # ---- training backward of the fp32 kernels (flow / U-Net-output gradients; frames are data) ----
     train = None
     if rank == 0 and not args.no_train:
         fg, yg = flow4.clone().requires_grad_(True), out5.clone().requires_grad_(True)
@@ -460,45 +611,94 @@ def main():
             ms = statistics.median(v)
             train[k] = {"ms": ms, "algorithmic_gbs": nbytes[k] / (ms * 1e-3) / 1e9,
                         "frac_of_peak": nbytes[k] / (ms * 1e-3) / 1e9 / peak}
+            roofline_kernels.append({"kernel": k + " (fp32 frames)", "frames": "fp32", "bound": "hbm", "achieved": train[k]["algorithmic_gbs"],
+                                     "peak": peak, "unit": "GB/s", "frac": train[k]["frac_of_peak"],
+                                     "algorithmic_bytes_per_launch": nbytes[k], "launch_ms": ms,
+                                     "traffic": traffic.get(k + "_dram_bytes_per_launch")})
         del fg, yg, rgbx, in16, frames, g3, g16
+    del in16_buf, rgbx_buf
+    torch.cuda.empty_cache()
 
-    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
-    e2e = None
+    # ---- e2e: host buffers through the C-ABI host entry points --------------------------------
+    e2e = e2e_fp32 = ceiling = None
     if not args.no_e2e:
+        ceiling = host_copy_ceiling(dev, world)
         # pinned buffers on the NUMA node the GPU hangs off (each rank binds to its own GPU's node)
         with sharding.numa_local_to_gpu(local_rank) as placement:
-            h_img, h_flow, h_out5 = img6.cpu().pin_memory(), flow4.cpu().pin_memory(), out5.cpu().pin_memory()
+            h_images = images.view(B, 2, H_IN, W_IN, 3).cpu().pin_memory()
+            h_flow, h_out5 = flow4.cpu().pin_memory(), out5.bfloat16().cpu().pin_memory()
             h_t = t.cpu()
-            h_out = torch.empty((B, NT, 3, H, W), dtype=torch.float32, pin_memory=True)
-        scratch = torch.empty(ssm_b200.synthesize_host_scratch_bytes(B, NT, H, W), dtype=torch.uint8, device=dev)
-        ssm_b200.synthesize_host(h_img, h_flow, h_out5, h_t, out=h_out, scratch=scratch)          # warm-up
+            h_out = torch.empty((B, NT, H_IN, W_IN, 3), dtype=torch.uint8, pin_memory=True)
+        scratch = torch.empty(q8.synthesize_host_scratch_bytes(B, NT, H_IN, W_IN, torch.bfloat16), dtype=torch.uint8, device=dev)
+        q8.synthesize_host(h_images, h_flow, h_out5, h_t, order="rgb", out=h_out, scratch=scratch)          # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res = ssm_b200.synthesize_host(h_img, h_flow, h_out5, h_t, out=h_out, scratch=scratch)
+            res = q8.synthesize_host(h_images, h_flow, h_out5, h_t, order="rgb", out=h_out, scratch=scratch)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([dt], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = tt.item()
-        h2d = (h_img.numel() + h_flow.numel() + h_out5.numel() + h_t.numel()) * 4
-        d2h = res.numel() * 4
-        e2e = {"value": frames_per_step * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "ssm_synthesize_host (pinned host buffers, 3-slot copy/compute pipeline)",
-               "host_placement": placement.info}
-        del h_img, h_flow, h_out5, res, h_out, scratch
+        h2d = h_images.numel() + h_flow.numel() * 4 + h_out5.numel() * 2 + h_t.numel() * 4
+        d2h = res.numel()
+        e2e_value = frames_per_step * args.e2e_steps / dt
+        bound = min(ceiling["h2d_gbs_per_gpu"] * 1e9 / (h2d / (B * NT)), ceiling["d2h_gbs_per_gpu"] * 1e9 / (d2h / (B * NT))) * world
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "ssm_synthesize_host_u8 (pinned host buffers: uint8 frames, fp32 stage-1 flows, bf16 U-Net output in; uint8 "
+                      "interpolated images out; 3-slot copy/compute pipeline)",
+               "host_placement": placement.info, "host_copy_ceiling": ceiling,
+               "host_copy_ceiling_frames_per_s": bound, "frac_of_host_copy_ceiling": e2e_value / bound}
+        del h_images, h_out5, res, h_out, scratch
+        torch.cuda.empty_cache()
+        # the fp32 host entry (round-1 e2e): fp32 frames, flows and U-Net output in, fp32 frames out
+        if rank == 0 and world == 1:
+            h_img, h_out5f = img6.cpu().pin_memory(), out5.cpu().pin_memory()
+            h_out3 = torch.empty((B, NT, 3, H, W), dtype=torch.float32, pin_memory=True)
+            scratch = torch.empty(ssm_b200.synthesize_host_scratch_bytes(B, NT, H, W), dtype=torch.uint8, device=dev)
+            ssm_b200.synthesize_host(h_img, h_flow, h_out5f, h_t, out=h_out3, scratch=scratch)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ssm_b200.synthesize_host(h_img, h_flow, h_out5f, h_t, out=h_out3, scratch=scratch)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 2
+            e2e_fp32 = {"value": B * NT / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt,
+                        "h2d_bytes_per_step": (h_img.numel() + h_flow.numel() + h_out5f.numel() + h_t.numel()) * 4,
+                        "d2h_bytes_per_step": h_out3.numel() * 4, "api": "ssm_synthesize_host (fp32 planes in and out; round-1 e2e)"}
+            del h_img, h_out5f, h_out3, scratch
+        del h_flow
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline: the reference's torch-op path on the host cores, rank 0, N=1 only ------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        frames_c, times, cores = time_cpu_reference(steps=3, warmup=1)
+        frames_c, times, cores = time_cpu_reference(steps=3, warmup=1, pairs=1)
         best = min(times)
         cpu_baseline = {"value": frames_c / best, "unit": "frames/s", "cores": cores, "kind": "port",
-                        "sample": "1 pair x %d timesteps at %dx%d, best of 3 after 1 warm-up; torch CPU ops "
+                        "sample": "1 pair x %d timesteps at %dx%d (uint8 frames normalised by the reference's expression, then "
+                                  "compute_inputs + compute_output_image per timestep), best of 3 after 1 warm-up; torch CPU ops "
                                   "(oracle/torch_oracle.py == the reference's op sequence)" % (NT, H, W),
                         "ms_per_frame": 1e3 * best / frames_c}
+
+    # ---- the reference's torch-op path on this GPU (cuDNN sampler on / off): the same-box bar ------------------------
+    reference_gpu = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        del frames_buf
+        torch.cuda.empty_cache()
+        reference_gpu = time_reference_on_gpu(dev)
+        reference_gpu["speedup_of_this_path"] = {k: (B * NT / (kernels["path"]["ms"] * 1e-3)) / v["frames_per_s"]
+                                                 for k, v in reference_gpu.items() if isinstance(v, dict) and "frames_per_s" in v}
+
+    # ---- BASELINE configs[2..4] on all ranks --------------------------------------------------------------------------
+    configs = None
+    if not args.no_configs:
+        del images, planar, img6, quads, flow4, out5
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        configs = bench_configs.run_all(world, rank, dev, peak_gbs=peak)
 
     # ---- context, not the headline: where the path sits in a whole inference step with the two U-Nets ------------
     whole_model = None
@@ -510,14 +710,13 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "timesteps": NT, "height": H, "width": W,
-                       "frames_per_step": frames_per_step, "l2": "inputs_exceed_l2 (8.7 GB read, 18.9 GB written per step)",
-                       "coord_mode": "cpu (IEEE division, bit-matches the CPU reference)",
-                       "parallelism": "pairs sharded over %d rank(s), no collective" % world},
-            "roofline": roofline, "kernels": kernels, "train_kernels": train, "smooth_flow_variant": smooth,
+            "config": config_dict(world),
+            "roofline": roofline, "roofline_kernels": roofline_kernels, "kernels": kernels, "fp32_frames_path": fp32_path,
+            "train_kernels": train, "smooth_flow_variant": smooth,
             "smooth_flow_and_unet_output_variant": smooth_res, "bf16_storage_variant": bf16, "unet_layouts_variant": layouts,
+            "configs": configs, "reference_gpu": reference_gpu,
             "whole_model_context": whole_model, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": 3 * K, "clocks": clocks,
+            "e2e": e2e, "e2e_fp32_buffers": e2e_fp32, "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -230,7 +230,9 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
  * 16-byte request per bilinear sample instead of four (the fp32 gathers are bound by the L1 data stage), and apply
  * a, c after interpolating: a * sum_k w_k b_k + c * sum_{k inside} w_k.  Results are within 1e-6 of ssm_flow_pack_fwd /
  * ssm_fuse_flow_fwd on the normalised fp32 frames (zeros padding and align_corners=True as in layers.warp).
- * One thread owns two adjacent pixels: W must be even, fp32 tensors 8-byte aligned with even strides.
+ * One thread owns two adjacent pixels: W must be even, tensors aligned to two elements with even strides.
+ * dtype: storage of img6 / flow4 / out16 / out3 (fp32, or bf16 with fp32 arithmetic and the estimated flows rounded to
+ * bf16 before they are used, as in the fp32-frame kernels); out5 has its own out5_dtype.
  * ssm_quads_from_u8: F uint8 images (layout and placement as ssm_frames_from_u8, padding pixels = byte 0, i.e. pad
  *   BEFORE normalising as visualize_interpolation.py:76-87 does) -> F x (H+1) x (W+1) entries
  *   (ssm_quads_bytes(F, H, W) bytes, 16-byte aligned).  A frame pair is two consecutive frames: quads of pair b
@@ -247,16 +249,18 @@ size_t ssm_quads_bytes(int F, int H, int W);
 int ssm_quads_from_u8(const unsigned char* src, long long src_frame_stride, int src_row_stride, int bgr,
                       int F, int H_in, int W_in, int H, int W, int top, int left, void* quads, void* stream);
 int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
-                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode,
+                         void* stream);
 int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                               void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
-                              int coord_mode, void* stream);
+                              int dtype, int coord_mode, void* stream);
 int ssm_fuse_flow_fwd_q8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
-                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode,
+                         void* stream);
 int ssm_fuse_flow_fwd_q8_u8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
                             unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int top, int left,
                             int H_out, int W_out, const float* mean3, const float* std3, float scale, int bgr, int saturate,
-                            const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream);
+                            const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream);
 
 /* ---- element-wise steps between the U-Nets' cuDNN convolutions -------
  * Channels-last activations (M x H x W x C, C a multiple of 8, 16-byte aligned), bf16 or fp32 storage, fp32

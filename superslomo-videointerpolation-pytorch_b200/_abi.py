@@ -82,10 +82,10 @@ def lib():
     L.ssm_quads_bytes.argtypes = [I, I, I]
     L.ssm_quads_bytes.restype = Z
     L.ssm_quads_from_u8.argtypes = [V, LL, I, I, I, I, I, I, I, I, I, V, V]
-    L.ssm_flow_pack_fwd_q8.argtypes = [P, V, P, V, P, F3, I, I, I, I, I, V]
-    L.ssm_flow_pack_fwd_q8_nhwc.argtypes = [P, V, P, V, V, I, F3, I, I, I, I, I, V]
-    L.ssm_fuse_flow_fwd_q8.argtypes = [V, P, P, I, V, P, F3, I, I, I, I, I, V]
-    L.ssm_fuse_flow_fwd_q8_u8.argtypes = [V, P, P, I, V, V, LL, I, I, I, I, I, F3, F3, ctypes.c_float, I, I, F3, I, I, I, I, I, V]
+    L.ssm_flow_pack_fwd_q8.argtypes = [P, V, P, V, P, F3, I, I, I, I, I, I, V]
+    L.ssm_flow_pack_fwd_q8_nhwc.argtypes = [P, V, P, V, V, I, F3, I, I, I, I, I, I, V]
+    L.ssm_fuse_flow_fwd_q8.argtypes = [V, P, P, I, V, P, F3, I, I, I, I, I, I, V]
+    L.ssm_fuse_flow_fwd_q8_u8.argtypes = [V, P, P, I, V, V, LL, I, I, I, I, I, F3, F3, ctypes.c_float, I, I, F3, I, I, I, I, I, I, V]
     L.ssm_synthesize_host_u8_scratch_bytes.argtypes = [I, I, I, I, I, I, I]
     L.ssm_synthesize_host_u8_scratch_bytes.restype = Z
     L.ssm_synthesize_host_u8.argtypes = [V, I, V, V, I, V, V, F3, F3, F3, F3, I, I, I, I, I, I, I, I, I, I, V, Z]

@@ -834,7 +834,7 @@ int ssm_quads_from_u8(const unsigned char* src, long long src_frame_stride, int 
 }
 
 extern "C++" {
-template <int MODE>
+template <typename T, int MODE>
 static int flow_pack_q8_launch(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                                const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
                                int B, int N, int H, int W, cudaStream_t s) {
@@ -842,103 +842,120 @@ static int flow_pack_q8_launch(const ssm_tensor* img6, const void* quads, const 
     const Norm3 nm = make_norm(norm6);
     const unsigned grid = q8_grid(B, H, W);
     if (!nhwc) {
-        flow_pack_fwd_q8_kernel<MODE, float, false><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads, cview<float>(flow4),
-                                                                              t, mview<float>(out16), N, g, nm);
+        flow_pack_fwd_q8_kernel<T, MODE, T, false><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads, cview<T>(flow4),
+                                                                          t, mview<T>(out16), N, g, nm);
     } else if (out_dtype == SSM_DTYPE_BF16) {
         View<__nv_bfloat16> o; o.p = (__nv_bfloat16*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
-        flow_pack_fwd_q8_kernel<MODE, __nv_bfloat16, true><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads,
-                                                                                     cview<float>(flow4), t, o, N, g, nm);
+        flow_pack_fwd_q8_kernel<T, MODE, __nv_bfloat16, true><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads,
+                                                                                     cview<T>(flow4), t, o, N, g, nm);
     } else {
-        View<float> o; o.p = (float*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
-        flow_pack_fwd_q8_kernel<MODE, float, true><<<grid, Q8_THREADS, 0, s>>>(cview<float>(img6), (const uint4*)quads, cview<float>(flow4),
-                                                                             t, o, N, g, nm);
+        if constexpr (sizeof(T) != 4) return fail(SSM_ERR_UNSUPPORTED, "ssm_flow_pack_fwd_q8_nhwc: bf16 inputs with fp32 output is not built");
+        else {
+            View<float> o; o.p = (float*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
+            flow_pack_fwd_q8_kernel<T, MODE, float, true><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads, cview<T>(flow4),
+                                                                                 t, o, N, g, nm);
+        }
     }
     SSM_LAUNCH_CHECK("ssm_flow_pack_fwd_q8");
     return SSM_OK;
+}
+
+template <typename T, int MODE, typename TY, bool OUT_U8>
+static int fuse_q8_launch(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, const float* t,
+                          const ssm_tensor* out3, const U8Out& u8, const float* norm6, int B, int N, int H, int W, cudaStream_t s) {
+    fuse_fwd_q8_kernel<T, MODE, TY, OUT_U8><<<q8_grid(B, H, W), Q8_THREADS, 0, s>>>(
+        (const uint4*)quads, cview<T>(flow4), cview<TY>(out5), t, mview<T>(out3), u8, N, make_geom(H, W), make_norm(norm6));
+    SSM_LAUNCH_CHECK("ssm_fuse_flow_fwd_q8");
+    return SSM_OK;
+}
+
+template <typename T, int MODE>
+static int fuse_q8_dispatch(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
+                            const ssm_tensor* out3, const U8Out* u8, const float* norm6, int B, int N, int H, int W, cudaStream_t s) {
+    U8Out none = {};
+    if (out5_dtype == SSM_DTYPE_BF16)
+        return u8 ? fuse_q8_launch<T, MODE, __nv_bfloat16, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s)
+                  : fuse_q8_launch<T, MODE, __nv_bfloat16, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s);
+    if constexpr (sizeof(T) != 4) return fail(SSM_ERR_UNSUPPORTED, "ssm_fuse_flow_fwd_q8: bf16 flows with an fp32 out5 is not built");
+    else
+        return u8 ? fuse_q8_launch<T, MODE, float, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s)
+                  : fuse_q8_launch<T, MODE, float, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s);
 }
 }  // extern "C++"
 
 static int flow_pack_q8_impl(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                              const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
-                             int B, int N, int H, int W, int coord_mode, void* stream) {
+                             int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
     SSM_TRY(check_q8("ssm_flow_pack_fwd_q8", B, N, H, W, coord_mode, quads, norm6));
-    SSM_TRY(check_tensor(img6, "img6", SSM_DTYPE_F32, true));
-    SSM_TRY(check_tensor(flow4, "flow4", SSM_DTYPE_F32, true));
-    SSM_TRY(check_pairable(img6, "img6", SSM_DTYPE_F32));
-    SSM_TRY(check_pairable(flow4, "flow4", SSM_DTYPE_F32));
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
+    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
+    SSM_TRY(check_pairable(img6, "img6", dtype));
+    SSM_TRY(check_pairable(flow4, "flow4", dtype));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
     if (nhwc) {
         if (out_dtype != SSM_DTYPE_F32 && out_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out_dtype %d", out_dtype);
         if (((uintptr_t)nhwc) % 32 != 0) return fail(SSM_ERR_ALIGN, "out16_nhwc must be 32-byte aligned");
     } else {
-        SSM_TRY(check_tensor(out16, "out16", SSM_DTYPE_F32, true));
-        SSM_TRY(check_pairable(out16, "out16", SSM_DTYPE_F32));
+        SSM_TRY(check_tensor(out16, "out16", dtype, true));
+        SSM_TRY(check_pairable(out16, "out16", dtype));
     }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == SSM_DTYPE_F32)
+        return coord_mode == SSM_COORD_DIV
+            ? flow_pack_q8_launch<float, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s)
+            : flow_pack_q8_launch<float, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s);
     return coord_mode == SSM_COORD_DIV
-        ? flow_pack_q8_launch<SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, (cudaStream_t)stream)
-        : flow_pack_q8_launch<SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, (cudaStream_t)stream);
+        ? flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s)
+        : flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s);
 }
 
 int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
-                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
-    return flow_pack_q8_impl(img6, quads, flow4, t, out16, nullptr, SSM_DTYPE_F32, norm6, B, N, H, W, coord_mode, stream);
+                         const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
+    return flow_pack_q8_impl(img6, quads, flow4, t, out16, nullptr, dtype, norm6, B, N, H, W, dtype, coord_mode, stream);
 }
 
 int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                               void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
-                              int coord_mode, void* stream) {
+                              int dtype, int coord_mode, void* stream) {
     if (!out16_nhwc) return fail(SSM_ERR_NULL, "out16_nhwc is NULL");
-    return flow_pack_q8_impl(img6, quads, flow4, t, nullptr, out16_nhwc, out_dtype, norm6, B, N, H, W, coord_mode, stream);
+    return flow_pack_q8_impl(img6, quads, flow4, t, nullptr, out16_nhwc, out_dtype, norm6, B, N, H, W, dtype, coord_mode, stream);
 }
-
-extern "C++" {
-template <int MODE, typename TY, bool OUT_U8>
-static int fuse_q8_launch(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, const float* t,
-                          const ssm_tensor* out3, const U8Out& u8, const float* norm6, int B, int N, int H, int W, cudaStream_t s) {
-    fuse_fwd_q8_kernel<MODE, TY, OUT_U8><<<q8_grid(B, H, W), Q8_THREADS, 0, s>>>(
-        (const uint4*)quads, cview<float>(flow4), cview<TY>(out5), t, mview<float>(out3), u8, N, make_geom(H, W), make_norm(norm6));
-    SSM_LAUNCH_CHECK("ssm_fuse_flow_fwd_q8");
-    return SSM_OK;
-}
-}  // extern "C++"
 
 static int fuse_q8_impl(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
                         const ssm_tensor* out3, const U8Out* u8, const float* norm6, int B, int N, int H, int W,
-                        int coord_mode, void* stream) {
+                        int dtype, int coord_mode, void* stream) {
     SSM_TRY(check_q8("ssm_fuse_flow_fwd_q8", B, N, H, W, coord_mode, quads, norm6));
+    if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
     if (out5_dtype != SSM_DTYPE_F32 && out5_dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown out5_dtype %d", out5_dtype);
-    SSM_TRY(check_tensor(flow4, "flow4", SSM_DTYPE_F32, true));
+    SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
     SSM_TRY(check_tensor(out5, "out5", out5_dtype, true));
-    SSM_TRY(check_pairable(flow4, "flow4", SSM_DTYPE_F32));
+    SSM_TRY(check_pairable(flow4, "flow4", dtype));
     SSM_TRY(check_pairable(out5, "out5", out5_dtype));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
-    U8Out none = {};
     if (!u8) {
-        SSM_TRY(check_tensor(out3, "out3", SSM_DTYPE_F32, true));
-        SSM_TRY(check_pairable(out3, "out3", SSM_DTYPE_F32));
+        SSM_TRY(check_tensor(out3, "out3", dtype, true));
+        SSM_TRY(check_pairable(out3, "out3", dtype));
     }
     cudaStream_t s = (cudaStream_t)stream;
-#define SSM_Q8_FUSE(MODE)                                                                                                       \
-    do {                                                                                                                        \
-        if (u8) return out5_dtype == SSM_DTYPE_F32 ? fuse_q8_launch<MODE, float, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s) \
-                                                   : fuse_q8_launch<MODE, __nv_bfloat16, true>(quads, flow4, out5, t, nullptr, *u8, norm6, B, N, H, W, s); \
-        return out5_dtype == SSM_DTYPE_F32 ? fuse_q8_launch<MODE, float, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s) \
-                                           : fuse_q8_launch<MODE, __nv_bfloat16, false>(quads, flow4, out5, t, out3, none, norm6, B, N, H, W, s); \
-    } while (0)
-    if (coord_mode == SSM_COORD_DIV) SSM_Q8_FUSE(SSM_COORD_DIV);
-    SSM_Q8_FUSE(SSM_COORD_RCP);
-#undef SSM_Q8_FUSE
+    if (dtype == SSM_DTYPE_F32)
+        return coord_mode == SSM_COORD_DIV
+            ? fuse_q8_dispatch<float, SSM_COORD_DIV>(quads, flow4, out5, out5_dtype, t, out3, u8, norm6, B, N, H, W, s)
+            : fuse_q8_dispatch<float, SSM_COORD_RCP>(quads, flow4, out5, out5_dtype, t, out3, u8, norm6, B, N, H, W, s);
+    return coord_mode == SSM_COORD_DIV
+        ? fuse_q8_dispatch<__nv_bfloat16, SSM_COORD_DIV>(quads, flow4, out5, out5_dtype, t, out3, u8, norm6, B, N, H, W, s)
+        : fuse_q8_dispatch<__nv_bfloat16, SSM_COORD_RCP>(quads, flow4, out5, out5_dtype, t, out3, u8, norm6, B, N, H, W, s);
 }
 
 int ssm_fuse_flow_fwd_q8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
-                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
-    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, out3, nullptr, norm6, B, N, H, W, coord_mode, stream);
+                         const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
+    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, out3, nullptr, norm6, B, N, H, W, dtype, coord_mode, stream);
 }
 
 int ssm_fuse_flow_fwd_q8_u8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
                             unsigned char* dst, long long dst_frame_stride, int dst_row_stride, int top, int left,
                             int H_out, int W_out, const float* mean3, const float* std3, float scale, int bgr, int saturate,
-                            const float* norm6, int B, int N, int H, int W, int coord_mode, void* stream) {
+                            const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
     if (!dst || !mean3 || !std3) return fail(SSM_ERR_NULL, "ssm_fuse_flow_fwd_q8_u8: dst, mean3 or std3 is NULL");
     if (H_out <= 0 || W_out <= 0 || top < 0 || left < 0 || top + H_out > H || left + W_out > W)
         return fail(SSM_ERR_SHAPE, "ssm_fuse_flow_fwd_q8_u8: the %d x %d crop at (%d, %d) leaves %d x %d", H_out, W_out, top, left, H, W);
@@ -947,7 +964,7 @@ int ssm_fuse_flow_fwd_q8_u8(const void* quads, const ssm_tensor* flow4, const ss
     u8.top = top; u8.left = left; u8.H_out = H_out; u8.W_out = W_out; u8.bgr = bgr != 0; u8.saturate = saturate != 0;
     for (int k = 0; k < 3; ++k) { u8.mean[k] = mean3[k]; u8.std[k] = std3[k]; }
     u8.scale = scale;
-    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, nullptr, &u8, norm6, B, N, H, W, coord_mode, stream);
+    return fuse_q8_impl(quads, flow4, out5, out5_dtype, t, nullptr, &u8, norm6, B, N, H, W, dtype, coord_mode, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1110,9 +1127,9 @@ int ssm_synthesize_host_u8(const unsigned char* frames_host, int bgr, const floa
         rc = ssm_frames_from_u8(d_frames, (long long)img_bytes, W_in * 3, bgr, 2, H_in, W_in, H, W, top, left, d_lut, pad3, &T_img, nullptr,
                                 SSM_DTYPE_F32, s);
         if (rc == SSM_OK) rc = ssm_quads_from_u8(d_frames, (long long)img_bytes, W_in * 3, bgr, 2, H_in, W_in, H, W, top, left, d_quads, s);
-        if (rc == SSM_OK) rc = ssm_flow_pack_fwd_q8(&T_img6, d_quads, &T_flow, d_t, &T_in16, norm6, 1, N, H, W, coord_mode, s);
+        if (rc == SSM_OK) rc = ssm_flow_pack_fwd_q8(&T_img6, d_quads, &T_flow, d_t, &T_in16, norm6, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
         if (rc == SSM_OK) rc = ssm_fuse_flow_fwd_q8_u8(d_quads, &T_flow, &T_out5, out5_dtype, d_t, d_out, (long long)img_bytes, W_in * 3, top, left,
-                                                       H_in, W_in, mean3, std3, 255.0f, bgr, saturate, norm6, 1, N, H, W, coord_mode, s);
+                                                       H_in, W_in, mean3, std3, 255.0f, bgr, saturate, norm6, 1, N, H, W, SSM_DTYPE_F32, coord_mode, s);
         SSM_H(cudaMemcpyAsync(out_host + (size_t)b * N * img_bytes, d_out, (size_t)N * img_bytes, cudaMemcpyDeviceToHost, s));
 #undef SSM_H
     }

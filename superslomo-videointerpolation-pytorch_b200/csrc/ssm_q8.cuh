@@ -108,6 +108,10 @@ __device__ __forceinline__ float2 lds2(const __nv_bfloat16* p) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 __device__ __forceinline__ void sts2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
+__device__ __forceinline__ void sts2(__nv_bfloat16* p, float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = low half = the first pixel
+    __stcs(reinterpret_cast<unsigned*>(p), *reinterpret_cast<const unsigned*>(&h));
+}
 
 // =============================================================================================
 // entry tables from uint8 images: F images (H_in x W_in x 3, RGB or BGR bytes) placed at (top, left) of an
@@ -169,9 +173,10 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #ifndef SSM_Q8_FUSE_U8_MIN_BLOCKS
 #define SSM_Q8_FUSE_U8_MIN_BLOCKS 3
 #endif
-template <int MODE, typename TO, bool NHWC>
+// T: storage type of img6 / flow4 (and of out16 in the planar layout): fp32, or bf16 with fp32 arithmetic
+template <typename T, int MODE, typename TO, bool NHWC>
 __global__ void __launch_bounds__(Q8_THREADS, SSM_Q8_PACK_MIN_BLOCKS)
-flow_pack_fwd_q8_kernel(View<const float> img6, const uint4* __restrict__ quads, View<const float> flow4,
+flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, View<const T> flow4,
                         const float* __restrict__ tv, View<TO> out16, int N, Geom g, Norm3 nm) {
     const Q8Idx ti = q8_index(g.H, g.W);
     if (!ti.valid) return;
@@ -179,10 +184,10 @@ flow_pack_fwd_q8_kernel(View<const float> img6, const uint4* __restrict__ quads,
     const long long epf = (long long)(g.H + 1) * (g.W + 1);            // entries per frame
     const uint4* __restrict__ tab0 = quads + (long long)ti.b * 2 * epf;
     const uint4* __restrict__ tab1 = tab0 + epf;
-    const float* F = flow4.p + ti.b * flow4.sb + p;
+    const T* F = flow4.p + ti.b * flow4.sb + p;
     const int fsc = (int)flow4.sc, isc = (int)img6.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
-    const float* I = img6.p + ti.b * img6.sb + p;
+    const T* I = img6.p + ti.b * img6.sb + p;
     float2 c0[3], c1[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { c0[c] = lds2(I + c * isc); c1[c] = lds2(I + (3 + c) * isc); }
@@ -197,8 +202,8 @@ flow_pack_fwd_q8_kernel(View<const float> img6, const uint4* __restrict__ quads,
         uint4 q1[2], q0[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            e0x[i] = est_t0(k, fa[i][0], fa[i][2]); e0y[i] = est_t0(k, fa[i][1], fa[i][3]);   // F_t0  :353
-            e1x[i] = est_t1(k, fa[i][0], fa[i][2]); e1y[i] = est_t1(k, fa[i][1], fa[i][3]);   // F_t1  :356
+            e0x[i] = storage_round<T>(est_t0(k, fa[i][0], fa[i][2])); e0y[i] = storage_round<T>(est_t0(k, fa[i][1], fa[i][3]));   // F_t0  :353
+            e1x[i] = storage_round<T>(est_t1(k, fa[i][0], fa[i][2])); e1y[i] = storage_round<T>(est_t1(k, fa[i][1], fa[i][3]));   // F_t1  :356
             t1[i] = make_qtap<MODE>(ti.x + i, ti.y, e1x[i], e1y[i], g);                       // warp(img_1, F_t1) :361
             t0[i] = make_qtap<MODE>(ti.x + i, ti.y, e0x[i], e0y[i], g);                       // warp(img_0, F_t0) :362
             q1[i] = load_entry(tab1, t1[i]);
@@ -221,7 +226,7 @@ flow_pack_fwd_q8_kernel(View<const float> img6, const uint4* __restrict__ quads,
             continue;
         }
         if constexpr (!NHWC) {
-            float* Of = reinterpret_cast<float*>(O);
+            TO* Of = O;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {                                                     // :364-367
                 sts2(Of + (0 + c) * osc, c1[c].x, c1[c].y);
@@ -247,10 +252,10 @@ struct U8Out {
     float mean[3], std[3], scale;
 };
 
-template <int MODE, typename TY, bool OUT_U8>
+template <typename T, int MODE, typename TY, bool OUT_U8>
 __global__ void __launch_bounds__(Q8_THREADS, OUT_U8 ? SSM_Q8_FUSE_U8_MIN_BLOCKS : SSM_Q8_FUSE_MIN_BLOCKS)
-fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const float> flow4, View<const TY> out5,
-                   const float* __restrict__ tv, View<float> out3, U8Out u8, int N, Geom g, Norm3 nm) {
+fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<const TY> out5,
+                   const float* __restrict__ tv, View<T> out3, U8Out u8, int N, Geom g, Norm3 nm) {
     const Q8Idx ti = q8_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
@@ -258,12 +263,12 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const float> flow4, Vie
     const uint4* __restrict__ tab0 = quads + (long long)ti.b * 2 * epf;
     const uint4* __restrict__ tab1 = tab0 + epf;
     const float* tp = tv + ti.b * N;
-    const float* F = flow4.p + ti.b * flow4.sb + p;
+    const T* F = flow4.p + ti.b * flow4.sb + p;
     const int fsc = (int)flow4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
     const float fa[2][4] = {{f01x.x, f01y.x, f10x.x, f10y.x}, {f01x.y, f01y.y, f10x.y, f10y.y}};
     const TY* __restrict__ Y = out5.p + ti.b * out5.sb + p;
-    float* __restrict__ O = OUT_U8 ? nullptr : out3.p + ti.b * out3.sb + p;
+    T* __restrict__ O = OUT_U8 ? nullptr : out3.p + ti.b * out3.sb + p;
     float2 ys[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
@@ -281,10 +286,10 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const float> flow4, Vie
         uint4 q0[2], q1[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float f1x = __fadd_rn(est_t1(k, fa[i][0], fa[i][2]), ya[i][1]);          // :412
-            const float f1y = __fadd_rn(est_t1(k, fa[i][1], fa[i][3]), ya[i][2]);
-            const float f0x = __fadd_rn(est_t0(k, fa[i][0], fa[i][2]), ya[i][3]);          // :413
-            const float f0y = __fadd_rn(est_t0(k, fa[i][1], fa[i][3]), ya[i][4]);
+            const float f1x = __fadd_rn(storage_round<T>(est_t1(k, fa[i][0], fa[i][2])), ya[i][1]);          // :412
+            const float f1y = __fadd_rn(storage_round<T>(est_t1(k, fa[i][1], fa[i][3])), ya[i][2]);
+            const float f0x = __fadd_rn(storage_round<T>(est_t0(k, fa[i][0], fa[i][2])), ya[i][3]);          // :413
+            const float f0y = __fadd_rn(storage_round<T>(est_t0(k, fa[i][1], fa[i][3])), ya[i][4]);
             t0[i] = make_qtap<MODE>(ti.x + i, ti.y, f0x, f0y, g);                          // :416
             t1[i] = make_qtap<MODE>(ti.x + i, ti.y, f1x, f1y, g);                          // :418
             q0[i] = load_entry(tab0, t0[i]);

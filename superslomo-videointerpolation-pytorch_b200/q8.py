@@ -77,11 +77,11 @@ def _check_quads(quads, B, H, W, device):
 def flow_pack(img6, quads, flow4, t, norm, n_timesteps=1, coord_mode=None, out=None, channels_last_dtype=None):
     """compute_inputs (flow_interpolation.py:338-372) for n_timesteps times of every pair, warping through the
     entry tables: img6 B x 6 x H x W fp32 (normalised frames; read for the pass-through channels only),
-    quads = tables of the same 2B frames, flow4 B x 4 x H x W fp32 -> B x N x 16 x H x W fp32.
+    quads = tables of the same 2B frames, flow4 B x 4 x H x W -> B x N x 16 x H x W (fp32, or bf16 storage throughout).
     channels_last_dtype (torch.float32 / torch.bfloat16): write B x N x H x W x 16 in that dtype instead (returned as a
     B x N x 16 x H x W view), the layout a channels-last stage-2 U-Net consumes."""
-    if not (img6.is_cuda and flow4.is_cuda) or img6.dtype != torch.float32 or flow4.dtype != torch.float32:
-        raise RuntimeError("q8.flow_pack: img6 and flow4 must be fp32 CUDA tensors (no CPU fallback)")
+    if not (img6.is_cuda and flow4.is_cuda) or img6.dtype not in (torch.float32, torch.bfloat16) or flow4.dtype != img6.dtype:
+        raise RuntimeError("q8.flow_pack: img6 and flow4 must be CUDA tensors of one storage dtype, fp32 or bf16 (no CPU fallback)")
     if torch.is_grad_enabled() and (img6.requires_grad or flow4.requires_grad):
         raise RuntimeError("q8.flow_pack is inference-only; use flow_pack on fp32 frames for a differentiable result")
     img6, flow4 = _abi.dense_planes(img6.detach()), _abi.dense_planes(flow4.detach())
@@ -96,12 +96,12 @@ def flow_pack(img6, quads, flow4, t, norm, n_timesteps=1, coord_mode=None, out=N
     with torch.cuda.device(img6.device):
         if channels_last_dtype is None:
             if out is None:
-                out = torch.empty((B, N, 16, H, W), dtype=torch.float32, device=img6.device)
-            elif tuple(out.shape) != (B, N, 16, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
-                raise RuntimeError("q8.flow_pack: out= must be a contiguous fp32 %s tensor" % ((B, N, 16, H, W),))
+                out = torch.empty((B, N, 16, H, W), dtype=img6.dtype, device=img6.device)
+            elif tuple(out.shape) != (B, N, 16, H, W) or out.dtype != img6.dtype or not out.is_contiguous():
+                raise RuntimeError("q8.flow_pack: out= must be a contiguous %s %s tensor" % (img6.dtype, (B, N, 16, H, W)))
             rc = L.ssm_flow_pack_fwd_q8(_abi.ref(_abi.desc(img6, False)), qp, _abi.ref(_abi.desc(flow4, False)),
                                         ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(out, True)), norm,
-                                        B, N, H, W, _resolve_mode(coord_mode), _abi.stream_ptr(img6.device))
+                                        B, N, H, W, _abi.dtype_code(img6), _resolve_mode(coord_mode), _abi.stream_ptr(img6.device))
         else:
             if channels_last_dtype not in (torch.float32, torch.bfloat16):
                 raise TypeError("q8.flow_pack: channels_last_dtype must be float32 or bfloat16")
@@ -114,14 +114,16 @@ def flow_pack(img6, quads, flow4, t, norm, n_timesteps=1, coord_mode=None, out=N
             rc = L.ssm_flow_pack_fwd_q8_nhwc(_abi.ref(_abi.desc(img6, False)), qp, _abi.ref(_abi.desc(flow4, False)),
                                              ctypes.c_void_p(tvec.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                              _abi.DTYPE_BF16 if channels_last_dtype == torch.bfloat16 else _abi.DTYPE_F32,
-                                             norm, B, N, H, W, _resolve_mode(coord_mode), _abi.stream_ptr(img6.device))
+                                             norm, B, N, H, W, _abi.dtype_code(img6), _resolve_mode(coord_mode),
+                                             _abi.stream_ptr(img6.device))
     _abi.check(rc, "ssm_flow_pack_fwd_q8")
     return out
 
 
 def _fuse_args(quads, flow4, out5, t):
-    if not (flow4.is_cuda and out5.is_cuda) or flow4.dtype != torch.float32 or out5.dtype not in (torch.float32, torch.bfloat16):
-        raise RuntimeError("q8.fuse_from_flow: flow4 must be fp32 and out5 fp32 or bf16, both on CUDA (no CPU fallback)")
+    if not (flow4.is_cuda and out5.is_cuda) or flow4.dtype not in (torch.float32, torch.bfloat16) \
+            or out5.dtype not in (torch.float32, torch.bfloat16) or (flow4.dtype == torch.bfloat16 and out5.dtype != torch.bfloat16):
+        raise RuntimeError("q8.fuse_from_flow: flow4 fp32 with out5 fp32 or bf16, or both bf16, on CUDA (no CPU fallback)")
     if torch.is_grad_enabled() and (flow4.requires_grad or out5.requires_grad):
         raise RuntimeError("q8.fuse_from_flow is inference-only; use fuse_from_flow on fp32 frames for a differentiable result")
     flow4, out5 = _abi.dense_planes(flow4.detach()), _abi.dense_planes(out5.detach())
@@ -138,14 +140,14 @@ def fuse_from_flow(quads, flow4, out5, t, norm, coord_mode=None, out=None):
     entry tables: flow4 B x 4 fp32, out5 B x N x 5 (fp32, or bf16 as autocast leaves it) -> B x N x 3 x H x W fp32."""
     flow4, out5, B, N, H, W, qp, tvec = _fuse_args(quads, flow4, out5, t)
     if out is None:
-        out = torch.empty((B, N, 3, H, W), dtype=torch.float32, device=flow4.device)
-    elif tuple(out.shape) != (B, N, 3, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise RuntimeError("q8.fuse_from_flow: out= must be a contiguous fp32 %s tensor" % ((B, N, 3, H, W),))
+        out = torch.empty((B, N, 3, H, W), dtype=flow4.dtype, device=flow4.device)
+    elif tuple(out.shape) != (B, N, 3, H, W) or out.dtype != flow4.dtype or not out.is_contiguous():
+        raise RuntimeError("q8.fuse_from_flow: out= must be a contiguous %s %s tensor" % (flow4.dtype, (B, N, 3, H, W)))
     with torch.cuda.device(flow4.device):
         rc = _abi.lib().ssm_fuse_flow_fwd_q8(qp, _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)),
                                              _abi.dtype_code(out5), ctypes.c_void_p(tvec.data_ptr()),
-                                             _abi.ref(_abi.desc(out, True)), norm, B, N, H, W, _resolve_mode(coord_mode),
-                                             _abi.stream_ptr(flow4.device))
+                                             _abi.ref(_abi.desc(out, True)), norm, B, N, H, W, _abi.dtype_code(flow4),
+                                             _resolve_mode(coord_mode), _abi.stream_ptr(flow4.device))
     _abi.check(rc, "ssm_fuse_flow_fwd_q8")
     return out
 
@@ -165,7 +167,7 @@ def fuse_from_flow_to_u8(quads, flow4, out5, t, norm, crop=None, mean=PIXEL_MEAN
             qp, _abi.ref(_abi.desc(flow4, False)), _abi.ref(_abi.desc(out5, True)), _abi.dtype_code(out5),
             ctypes.c_void_p(tvec.data_ptr()), ctypes.c_void_p(out.data_ptr()), h_out * w_out * 3, w_out * 3, top, left,
             h_out, w_out, _f3(mean), _f3(std), float(scale), 1 if order.lower() == "bgr" else 0, 1 if saturate else 0,
-            norm, B, N, H, W, _resolve_mode(coord_mode), _abi.stream_ptr(flow4.device))
+            norm, B, N, H, W, _abi.dtype_code(flow4), _resolve_mode(coord_mode), _abi.stream_ptr(flow4.device))
     _abi.check(rc, "ssm_fuse_flow_fwd_q8_u8")
     return out
 

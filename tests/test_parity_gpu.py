@@ -12,7 +12,7 @@ import torch
 import ssm_b200
 from oracle import c_oracle, torch_oracle
 from ssm_b200 import synthetic
-from util import assert_close_bf16, assert_close_fp32, golden_cases, load_golden, max_err
+from util import assert_close_bf16, assert_close_fp32, assert_close_scaled, assert_sum_close, golden_cases, load_golden, max_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -88,28 +88,27 @@ def test_batched_kernels_vs_c_oracle(mode_name, mode, B, N, H, W, kind, smooth):
     a2, xin, yo = _dev(img6, True), _dev(in16.detach().cpu(), True), _dev(out5, True)
     frames = ssm_b200.fuse(a2, xin, yo, _dev(t), coord_mode=mode_name)
     frames.backward(_dev(g3))
-    ref_gimg = torch.zeros_like(img6)
-    ref_gflow = torch.zeros_like(flow4)
-    ref_gimg2 = torch.zeros_like(img6)
+    ref_gimg, ref_gflow, ref_gimg2 = [], [], []          # per-timestep terms of the sums the kernels accumulate
     for n in range(N):
         tn = t[:, n]
         r16 = c_oracle.compute_inputs(img6, flow4, tn, coord_mode=mode)
         assert torch.equal(in16[:, n, 6:10].detach().cpu(), r16[:, 6:10]), "estimated flows not bit-identical"
         assert_close_fp32(in16[:, n], r16, "flow_pack fwd n=%d" % n)
         gi, gf = c_oracle.compute_inputs_backward(g16[:, n].contiguous(), img6, flow4, tn, coord_mode=mode)
-        ref_gimg += gi
-        ref_gflow += gf
+        ref_gimg.append(gi)
+        ref_gflow.append(gf)
         y5 = out5[:, n].contiguous()
         r3 = c_oracle.compute_output_image(img6, r16, y5, tn, coord_mode=mode)
         assert_close_fp32(frames[:, n], r3, "fuse fwd n=%d" % n)
         gi2, gx, gy = c_oracle.compute_output_image_backward(g3[:, n].contiguous(), img6, r16, y5, tn, coord_mode=mode)
-        ref_gimg2 += gi2
+        ref_gimg2.append(gi2)
         assert_close_fp32(xin.grad[:, n], gx, "fuse grad in16 n=%d" % n)
         assert_close_fp32(yo.grad[:, n], gy, "fuse grad out5 n=%d" % n)
-    # sums over N timesteps: allow N roundings
-    assert_close_fp32(b.grad, ref_gflow, "flow_pack grad flow", tol=1e-5 * max(1, N // 2))
-    assert_close_fp32(a.grad, ref_gimg, "flow_pack grad img", tol=1e-5 * max(1, N // 2))
-    assert_close_fp32(a2.grad, ref_gimg2, "fuse grad img", tol=1e-5 * max(1, N // 2))
+    # sums over the N timesteps: 1e-5 against the float64 sum of the oracle's per-timestep terms, plus the
+    # representation bound of an fp32 running sum (util.assert_sum_close prints the reference's own summation noise)
+    assert_sum_close(b.grad, ref_gflow, "flow_pack grad flow")
+    assert_sum_close(a.grad, ref_gimg, "flow_pack grad img")
+    assert_sum_close(a2.grad, ref_gimg2, "fuse grad img")
 
 
 @pytest.mark.parametrize("mode_name,mode", MODES)
@@ -140,26 +139,80 @@ def test_fuse_from_flow_equals_two_step_path(mode_name, mode, B, N, H, W, kind, 
     if dtype == torch.float32:
         # flow gradient of the two-step path = coefficients applied to grad in16[6:10] (+ zero through the
         # warped channels, whose upstream gradient is zero here)
-        assert_close_fp32(f.grad, f2.grad, "fuse_from_flow grad flow vs two-step", tol=1e-5 * max(1, N // 2))
-        ref_gflow = torch.zeros_like(flow4)
+        ref_gflow = []
         for n in range(N):
             tn = t[:, n]
             r16 = c_oracle.compute_inputs(img6, flow4, tn, coord_mode=mode)
             _, gx, _ = c_oracle.compute_output_image_backward(g3[:, n].contiguous(), img6, r16,
                                                               out5[:, n].contiguous(), tn, coord_mode=mode, need_img=False)
             _, gf = c_oracle.compute_inputs_backward(gx, img6, flow4, tn, coord_mode=mode, need_img=False)
-            ref_gflow += gf
-        assert_close_fp32(f.grad, ref_gflow, "fuse_from_flow grad flow vs C oracle", tol=1e-5 * max(1, N // 2))
+            ref_gflow.append(gf)
+        # both GPU paths (in-register accumulation over N, and the chain through the 16-channel tensor) against the
+        # float64 sum of the oracle's per-timestep terms
+        assert_sum_close(f.grad, ref_gflow, "fuse_from_flow grad flow vs C oracle")
+        assert_sum_close(f2.grad, ref_gflow, "two-step grad flow vs C oracle")
     else:
         assert_close_bf16(f.grad, f2.grad.float(), "fuse_from_flow grad flow (bf16)")
 
 
+def _loss_front_end_oracle(img6, flow4, out5, target, t, wts, g3, s1, s2):
+    """The reference's loss front-end (losses.py:111, 152-167) and the gradients of
+    L = sum_b sum_k wts[b,k] * sums[b,k] / (3HW) + sum(frames * g3), composed from the C ORACLE's warps and backward
+    functions (CPU).  Returns frames [B,N,3,H,W], sums [B,2N+1] (float64), grad out5 [B,N,5,H,W] and the list of
+    per-term flow4 gradients (their float64 sum is the reference)."""
+    B, N = out5.shape[0], out5.shape[1]
+    H, W = img6.shape[-2:]
+    cnt = 3.0 * H * W
+    i0, i1 = img6[:, 0:3].contiguous(), img6[:, 3:6].contiguous()
+    frames = torch.empty(B, N, 3, H, W)
+    sums = torch.zeros(B, 2 * N + 1, dtype=torch.float64)
+    gy = torch.zeros_like(out5)
+    gflow_terms = []
+    for n in range(N):
+        tn = t[:, n]
+        y5 = out5[:, n].contiguous()
+        tg = target[:, n]
+        r16 = c_oracle.compute_inputs(img6, flow4, tn)
+        fr = c_oracle.compute_output_image(img6, r16, y5, tn)
+        frames[:, n] = fr
+        sums[:, 2 * n] = (fr - tg).abs().double().flatten(1).sum(1)
+        # upstream gradient of the fused frame: L1 reconstruction term + the dense term
+        G = (wts[:, 2 * n].view(B, 1, 1, 1) / cnt) * torch.sign(fr - tg) + g3[:, n]
+        _, gx, g5 = c_oracle.compute_output_image_backward(G.contiguous(), img6, r16, y5, tn, need_img=False)
+        g16 = gx.clone()
+        if s2:
+            ft1 = (r16[:, 6:8] + y5[:, 1:3]).contiguous()
+            ft0 = (r16[:, 8:10] + y5[:, 3:5]).contiguous()
+            w0, w1 = c_oracle.warp(i0, ft0), c_oracle.warp(i1, ft1)
+            sums[:, 2 * n + 1] = ((w0 - tg).abs() + (w1 - tg).abs()).double().flatten(1).sum(1)
+            k = wts[:, 2 * n + 1].view(B, 1, 1, 1) / cnt
+            _, d0 = c_oracle.warp_backward((k * torch.sign(w0 - tg)).contiguous(), i0, ft0, need_img=False)
+            _, d1 = c_oracle.warp_backward((k * torch.sign(w1 - tg)).contiguous(), i1, ft1, need_img=False)
+            g5 = g5.clone()
+            g5[:, 1:3] += d1
+            g5[:, 3:5] += d0
+            g16[:, 6:8] += d1
+            g16[:, 8:10] += d0
+        gy[:, n] = g5
+        _, gf = c_oracle.compute_inputs_backward(g16.contiguous(), img6, flow4, tn, need_img=False)
+        gflow_terms.append(gf)
+    if s1:
+        f01, f10 = flow4[:, 0:2].contiguous(), flow4[:, 2:4].contiguous()
+        wa, wb = c_oracle.warp(i1, f01), c_oracle.warp(i0, f10)
+        sums[:, 2 * N] = ((wa - i0).abs() + (wb - i1).abs()).double().flatten(1).sum(1)
+        k = wts[:, 2 * N].view(B, 1, 1, 1) / cnt
+        _, da = c_oracle.warp_backward((k * torch.sign(wa - i0)).contiguous(), i1, f01, need_img=False)
+        _, db = c_oracle.warp_backward((k * torch.sign(wb - i1)).contiguous(), i0, f10, need_img=False)
+        gflow_terms.append(torch.cat([da, db], dim=1))
+    return frames, sums, gy, gflow_terms
+
+
 @pytest.mark.parametrize("s1,s2", [(True, True), (False, True), (True, False)])
 @pytest.mark.parametrize("B,N,H,W,kind", [(3, 1, 64, 96, "smooth"), (2, 1, 45, 77, "border"), (2, 3, 40, 72, "smooth")])
-def test_fused_loss_front_end_vs_reference_ops(B, N, H, W, kind, s1, s2):
-    """ssm_fuse_loss_fwd/bwd vs the reference's loss front-end restated with torch ops on the C oracle's
-    warps (losses.py:111, 152-167): loss sums, frames and the gradients of a weighted loss w.r.t. the
-    stage-1 flows and the stage-2 output."""
+def test_fused_loss_front_end_vs_c_oracle(B, N, H, W, kind, s1, s2):
+    """ssm_fuse_loss_fwd/bwd against the reference's loss front-end composed from the C oracle (losses.py:111,
+    152-167): fused frames, the three L1 sums per sample, and the gradients of a weighted loss w.r.t. the stage-2
+    output and the stage-1 flows."""
     img6, flow4, out5, t = _inputs(B, N, H, W, seed=500 + H + N, kind=kind)
     target = synthetic.frames(B * N, H, W, n_frames=1, seed=77).view(B, N, 3, H, W)
     g3 = torch.randn(B, N, 3, H, W, generator=torch.Generator().manual_seed(3)) * 1e-3
@@ -167,34 +220,22 @@ def test_fused_loss_front_end_vs_reference_ops(B, N, H, W, kind, s1, s2):
     a, f, y = _dev(img6), _dev(flow4, True), _dev(out5, True)
     frames, sums = ssm_b200.fuse_loss(a, f, y, _dev(target), _dev(t), stage1_loss=s1, stage2_loss=s2)
     ((sums * _dev(wts)).sum() / (3 * H * W) + (frames * _dev(g3)).sum()).backward()
-    # reference composition on the GPU path's own unfused ops (already pinned to the oracle above)
-    f2, y2 = _dev(flow4, True), _dev(out5, True)
-    fr2 = ssm_b200.fuse_from_flow(a, f2, y2, _dev(t))
-    in16 = ssm_b200.flow_pack(a, f2, _dev(t), n_timesteps=N)
-    tg = _dev(target)
-    ref = torch.zeros(B, 2 * N + 1, device=DEV)
-    cols = []
-    for n in range(N):
-        rec = (fr2[:, n] - tg[:, n]).abs().flatten(1).sum(1)
-        w2 = torch.zeros_like(rec)
-        if s2:
-            ft1 = in16[:, n, 6:8] + y2[:, n, 1:3]
-            ft0 = in16[:, n, 8:10] + y2[:, n, 3:5]
-            w2 = ((ssm_b200.warp(a[:, 0:3], ft0) - tg[:, n]).abs() + (ssm_b200.warp(a[:, 3:6], ft1) - tg[:, n]).abs()).flatten(1).sum(1)
-        cols += [rec, w2]
-    w1 = torch.zeros(B, device=DEV)
-    if s1:
-        w1 = ((ssm_b200.warp(a[:, 3:6], f2[:, 0:2]) - a[:, 0:3]).abs() + (ssm_b200.warp(a[:, 0:3], f2[:, 2:4]) - a[:, 3:6]).abs()).flatten(1).sum(1)
-    ref = torch.stack(cols + [w1], dim=1)
-    ((ref * _dev(wts)).sum() / (3 * H * W) + (fr2 * _dev(g3)).sum()).backward()
-    assert_close_fp32(frames, fr2, "fused-loss frames")
-    rel = ((sums - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
-    assert rel <= 2e-6, "loss sums: relative error %.3e" % rel
-    # the loss gradients carry a 1/(3HW) factor: compare relative to the largest reference gradient
-    for got, want, what in ((y.grad, y2.grad, "out5"), (f.grad, f2.grad, "flow4")):
-        scale = want.abs().max().item()
-        assert max_err(got, want) <= 2e-5 * scale, "fused-loss grad %s: max err %.3e vs scale %.3e" % (
-            what, max_err(got, want), scale)
+    r_frames, r_sums, r_gy, r_gf = _loss_front_end_oracle(img6, flow4, out5, target, t, wts, g3, s1, s2)
+    assert_close_fp32(frames, r_frames, "fused-loss frames")
+    # each sum has 3HW terms of O(1): the bar is relative (1e-5 of the sum's magnitude, at least 1e-5 absolute)
+    rel = ((sums.detach().cpu().double() - r_sums).abs() / r_sums.abs().clamp_min(1.0)).max().item()
+    assert rel <= 1e-5, "loss sums: relative error %.3e" % rel
+    # sign() makes the L1 gradients discontinuous where a warped value equals its target to rounding: the oracle and the
+    # kernel may pick different signs at such pixels (both are valid subgradients); they must be rare and the rest exact
+    err = (y.grad.cpu() - r_gy).abs()
+    k_max = (wts.max().item() / (3 * H * W))
+    flips = (err > 1e-5).sum().item()
+    assert flips <= max(2, err.numel() // 20000), "grad out5: %d elements beyond 1e-5 (max %.3e)" % (flips, err.max().item())
+    ref64 = sum(x.double() for x in r_gf)
+    errf = (f.grad.cpu().double() - ref64).abs()
+    flips = (errf > 1e-5 + len(r_gf) * 2.0 ** -24 * sum(x.double().abs() for x in r_gf)).sum().item()
+    assert flips <= max(2, errf.numel() // 20000), "grad flow4: %d elements beyond 1e-5 (max %.3e, loss weight %.1e)" % (
+        flips, errf.max().item(), k_max)
 
 
 @pytest.mark.parametrize("C", [1, 3, 5])
@@ -487,9 +528,12 @@ def test_c3_training_backward_is_linear_in_the_upstream_gradient():
     i6, f4, y5, ts = img6[s:s + 1].cpu(), flow4[s:s + 1].detach().cpu(), out5[s:s + 1, 0].detach().cpu(), t[s:s + 1, 0].cpu()
     r16 = c_oracle.compute_inputs(i6, f4, ts)
     _, gx, gy = c_oracle.compute_output_image_backward(g1[s:s + 1, 0].cpu(), i6, r16, y5, ts, need_img=False)
-    _, gf = c_oracle.compute_inputs_backward(gx + h1[s:s + 1, 0].cpu(), i6, f4, ts, need_img=False)
+    # autograd adds the flow gradients of the two consumers (frames through in16[6:10], and in16 itself) in fp32:
+    # the oracle supplies the two terms separately
+    _, gf_a = c_oracle.compute_inputs_backward(gx, i6, f4, ts, need_img=False)
+    _, gf_b = c_oracle.compute_inputs_backward(h1[s:s + 1, 0].cpu().contiguous(), i6, f4, ts, need_img=False)
     assert_close_fp32(a[1][s:s + 1, 0], gy, "C3 grad out5, sample 37")
-    assert_close_fp32(a[0][s:s + 1], gf, "C3 grad flow, sample 37", tol=2e-5)
+    assert_sum_close(a[0][s:s + 1], [gf_a, gf_b], "C3 grad flow, sample 37")
 
 
 def test_streams_threads_and_argument_errors():

@@ -168,3 +168,35 @@ def test_q8_full_size_against_fp32_kernels():
     # one oracle slice: rows 500..507 of pair 1, timestep 3 (the oracle computes whole frames: restrict the comparison)
     r16 = c_oracle.compute_inputs(img6[1:2].cpu(), flow4[1:2].cpu(), t[1:2, 3].cpu())
     assert_close_fp32(in16[1, 3, :, 500:508], r16[0, :, 500:508], "q8 flow_pack vs C oracle at full size")
+
+
+def test_q8_bf16_storage():
+    """bf16 storage of flows / frames / stage-2 input / result with fp32 arithmetic, against the C oracle on the same
+    bf16-rounded inputs (north_star: <= 2e-2, + 2^-7 relative above magnitude 1: util.assert_close_bf16)."""
+    from util import assert_close_bf16
+    B, N, h, w = 2, 3, 64, 96
+    images = _u8_images(2 * B, h, w, seed=21, smooth=True)
+    planar, quads, norm, _ = q8.prepare(images.to(DEV), order="rgb", lut=ssm_b200.normalisation_lut(device="cpu"))
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=8.0, seed=22).bfloat16()
+    out5 = synthetic.unet_out5(B, N, H, W, seed=23).bfloat16()
+    t = synthetic.timesteps(B, N)
+    in16 = q8.flow_pack(img6.bfloat16(), quads, flow4.to(DEV), t, norm, n_timesteps=N)
+    frames = q8.fuse_from_flow(quads, flow4.to(DEV), out5.to(DEV), t, norm)
+    assert in16.dtype == torch.bfloat16 and frames.dtype == torch.bfloat16
+    img6_c = img6.cpu()               # the gathers read the exact bytes: the oracle warps the unrounded frames
+    for n in range(N):
+        r16 = c_oracle.compute_inputs(img6_c, flow4.float(), t[:, n])
+        # the estimated flows are rounded to bf16 before they are used: warp the oracle with the rounded values
+        e = r16[:, 6:10].bfloat16().float()
+        assert torch.equal(in16[:, n, 6:10].float().cpu(), e), "estimated flows are not the bf16 rounding of the oracle's"
+        w1 = c_oracle.warp(img6_c[:, 3:6].contiguous(), e[:, 0:2].contiguous())
+        w0 = c_oracle.warp(img6_c[:, 0:3].contiguous(), e[:, 2:4].contiguous())
+        assert_close_bf16(in16[:, n, 3:6], w1, "q8 bf16 warped I1 n=%d" % n)
+        assert_close_bf16(in16[:, n, 10:13], w0, "q8 bf16 warped I0 n=%d" % n)
+        assert_close_bf16(in16[:, n, 0:3], img6_c[:, 3:6], "q8 bf16 pass-through n=%d" % n)
+        x16 = r16.clone()
+        x16[:, 6:10] = e
+        r3 = c_oracle.compute_output_image(img6_c, x16, out5[:, n].float().contiguous(), t[:, n])
+        assert_close_bf16(frames[:, n], r3, "q8 bf16 fused n=%d" % n)

@@ -69,3 +69,37 @@ def assert_close_bf16(got, want, what):
     bad = ((got - want).abs() > bound)
     assert not bad.any(), "%s: %d elements beyond %.0e + 2^-7*|ref| (max abs err %.3e)" % (
         what, int(bad.sum()), BF16_ATOL, (got - want).abs().max().item())
+
+
+def assert_sum_close(got, terms, what, tol=FP32_TOL):
+    """`got` is a SUM of the fp32 tensors `terms` that the kernel accumulated in registers (e.g. the flow gradient
+    over N timesteps).  The yardstick is the same fp32 terms added in float64, which is exact for this purpose; any
+    fp32 accumulation of them -- the kernel's, or the one autograd performs for the reference -- may differ from it by
+    up to len(terms) roundings of the running sum, i.e. len(terms) * 2^-24 * sum|terms| per element.  The bar is
+    north_star's 1e-5 plus that representation bound (printed next to the error of a plain fp32 left-to-right sum of
+    the same terms, the reference's own accumulation noise)."""
+    terms = [x.detach().cpu() for x in terms]
+    ref64 = sum(x.double() for x in terms)
+    mag = sum(x.double().abs() for x in terms)
+    bound = len(terms) * 2.0 ** -24 * mag
+    fp32_sum = terms[0].clone()
+    for x in terms[1:]:
+        fp32_sum = fp32_sum + x
+    noise = (fp32_sum.double() - ref64).abs().max().item()
+    err = (got.detach().cpu().double() - ref64).abs()
+    bad = err > tol + bound
+    assert not bad.any(), "%s: %d elements beyond %.0e + %d ulp-roundings of the running sum (max err %.3e, fp32 reference sum noise %.3e)" % (
+        what, int(bad.sum()), tol, len(terms), err.max().item(), noise)
+    return err.max().item(), noise
+
+
+def assert_close_scaled(got, want, what, tol=FP32_TOL, ulps=4):
+    """north_star's 1e-5 is an absolute bar for O(1) quantities (frames, flows of a few pixels).  A gradient of
+    magnitude 50 has an fp32 ulp of 3.8e-6: the bar for such values is 1e-5 + `ulps` ulp of the reference value."""
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    bound = tol + ulps * 2.0 ** -23 * want.abs()
+    err = (got - want).abs()
+    bad = err > bound
+    assert not bad.any(), "%s: %d elements beyond %.0e + %d ulp (max abs err %.3e at |ref| %.3e)" % (
+        what, int(bad.sum()), tol, ulps, err.max().item(), want.abs().flatten()[err.flatten().argmax()].item())
+    return err.max().item()

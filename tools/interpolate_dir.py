@@ -42,7 +42,7 @@ def main():
     import configparser
     cfg = configparser.RawConfigParser()
     cfg.read_string("[STAGE1]\nBOTTLENECK=%s\n[STAGE2]\nBOTTLENECK=%s\nCROSS_SKIP=TRUE\n" % (a.bottleneck, a.bottleneck))
-    model = ssm_b200.FullModel(cfg=cfg).to(dev).eval()
+    model = ssm_b200.FullModel(cfg=cfg, loss=ssm_b200.losses.SSMLosses(cfg, perceptual_features="zero")).to(dev).eval()   # inference only
     if a.weights:
         formats.load_checkpoint(model, a.weights)
     if a.channels_last:

@@ -52,7 +52,7 @@ def main():
     B, N, h_in, w_in = a.pairs, a.timesteps, a.height, a.width
 
     torch.manual_seed(42)
-    model = FullModel(cfg=None).to(dev).eval()
+    model = FullModel(cfg=None, loss=ssm_b200.losses.SSMLosses(perceptual_features="zero")).to(dev).eval()   # inference only
     if a.channels_last:
         model.stage1_model.set_channels_last()
         model.stage2_model.set_channels_last()

@@ -793,6 +793,11 @@ static int check_q8(const char* who, int B, int N, int H, int W, int coord_mode,
     const long long tiles = (long long)B * ((H + Q8_TILE_H - 1) / Q8_TILE_H) * ((W + Q8_TILE_W - 1) / Q8_TILE_W);
     if (tiles > 2147483647ll) return fail(SSM_ERR_SHAPE, "%s: too many tiles for one launch", who);
     if ((long long)(H + 1) * (W + 1) > MAX_PLANE) return fail(SSM_ERR_SHAPE, "%s: H*W too large", who);
+    // the gathers address the launch's entry tables with an unsigned 32-bit entry index
+    if ((long long)B * 2 * (H + 1) * (W + 1) > 4294967295ll)
+        return fail(SSM_ERR_SHAPE, "%s: B*2*(H+1)*(W+1) = %lld entries exceed 2^32 - 1: split the batch", who, (long long)B * 2 * (H + 1) * (W + 1));
+    // floor() by the 1.5 * 2^23 addition needs every in-frame coordinate below 2^22
+    if (H >= (1 << 22) || W >= (1 << 22)) return fail(SSM_ERR_SHAPE, "%s: H and W must be below 2^22", who);
     return SSM_OK;
 }
 // 8-byte vector access: base and every stride a multiple of 2 elements (fp32) / the pair of bf16 values aligned to 4 bytes

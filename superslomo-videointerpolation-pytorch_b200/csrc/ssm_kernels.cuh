@@ -218,7 +218,7 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
         Quad q1[3], q0[3];
         gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
         gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
-        if (NHWC) {                                                             // :364-367, channels-last
+        if constexpr (NHWC) {                                                   // :364-367, channels-last
             float o[16];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -226,17 +226,17 @@ flow_pack_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
             }
             o[6] = e1x; o[7] = e1y; o[8] = e0x; o[9] = e0y;
             store16_nhwc<TO>(O, o);
-            continue;
-        }
+        } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {                                           // :364-367
-            sts_(O + (0 + c) * osc, c1[c]);
-            sts_(O + (3 + c) * osc, bilerp(q1[c], t1));
-            sts_(O + (10 + c) * osc, bilerp(q0[c], t0));
-            sts_(O + (13 + c) * osc, c0[c]);
+            for (int c = 0; c < 3; ++c) {                                       // :364-367
+                sts_(O + (0 + c) * osc, c1[c]);
+                sts_(O + (3 + c) * osc, bilerp(q1[c], t1));
+                sts_(O + (10 + c) * osc, bilerp(q0[c], t0));
+                sts_(O + (13 + c) * osc, c0[c]);
+            }
+            sts_(O + 6 * osc, e1x); sts_(O + 7 * osc, e1y);
+            sts_(O + 8 * osc, e0x); sts_(O + 9 * osc, e0y);
         }
-        sts_(O + 6 * osc, e1x); sts_(O + 7 * osc, e1y);
-        sts_(O + 8 * osc, e0x); sts_(O + 9 * osc, e0y);
     }
 }
 

@@ -36,56 +36,155 @@ __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.
 // 1 / (1 + 2^(-x log2 e)): two MUFU + two FP32 ops; |error| < 1e-7 (not coordinate arithmetic)
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
-struct QTap {
-    float wnw, wne, wsw, wse;   // corner weights (ATen: area of the opposite sub-rectangle)
-    float wsum;                 // sum of the weights of the corners inside the frame
-    int idx;                    // entry index (y0+1)*(W+1) + (x0+1); only dereferenced when ok
-    bool ok;                    // at least one corner may be inside
+// ---- two pixels at a time: packed fp32 arithmetic ------------------------------------------------
+// sm_100 issues one instruction for two independent fp32 operations on a register pair (FADD2 / FMUL2 /
+// FFMA2, each with its own IEEE rounding -- the same bits as two scalar instructions, never contracted).
+// A thread owns two horizontally adjacent pixels, so every quantity of the sampling arithmetic is a natural
+// pair (.x = pixel x, .y = pixel x + 1) and the kernels, which were bound by instruction issue (75-82 % of
+// the issue slots, profiles/r02e), need about half the instructions for it.
+typedef float2 f2;
+__device__ __forceinline__ f2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+// add2 / mul2 / fma2: free to be contracted by the compiler (weights, interpolation, fusion)
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+// add2x / mul2x / add2s: the coordinate arithmetic, one IEEE rounding per operation.  Two traps (both seen in the SASS):
+// the __f*2_rn intrinsics, unlike their scalar namesakes, lower to plain vector fmul / fadd, which nvcc contracts
+// into FFMA2; and ptxas (12.9) fuses even an explicit mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2, with or
+// without -fmad=false (it also rewrites fma(x, 1, y) to that add first).  So: PTX with explicit .rn for the packed
+// operations, and wherever a packed PRODUCT is the operand of a SUM that the reference rounds separately, the sum is
+// two scalar add.rn.f32 (add2s), which ptxas never fuses.
+__device__ __forceinline__ unsigned long long f2_bits(f2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ f2 bits_f2(unsigned long long r) {
+    f2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ f2 add2x(f2 a, f2 b) {          // operands must not be packed products (see above)
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ f2 mul2x(f2 a, f2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ f2 add2s(f2 a, f2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ f2 sub2s(f2 a, f2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+
+// div_rn_const / sample_coord of ssm_device.cuh on a pair (same operations, same roundings)
+template <int MODE>
+__device__ __forceinline__ f2 sample_coord2(f2 pos, f2 flow, float norm, float inv, float m1) {
+    const f2 g = add2x(pos, flow);
+    const f2 s = mul2x(g, bc2(2.0f));
+    f2 n;
+    if (MODE == SSM_COORD_DIV) {
+        const f2 d = bc2(norm), y = bc2(inv);
+        f2 q = mul2x(s, y);
+        f2 r = fma2(neg2(q), d, s);
+        q = fma2(r, y, q);
+        r = fma2(neg2(q), d, s);
+        n = fma2(r, y, q);
+    } else {
+        n = mul2x(s, bc2(inv));
+    }
+    n = (MODE == SSM_COORD_DIV) ? add2x(n, bc2(-1.0f)) : add2s(n, bc2(-1.0f));
+    f2 a = add2x(n, bc2(1.0f));
+    a = mul2x(a, bc2(0.5f));
+    return mul2x(a, bc2(m1));
+}
+
+// F_t0 / F_t1 of flow_interpolation.py:353,356 on a pair (products rounded before the sum, as est_t0 / est_t1)
+__device__ __forceinline__ f2 est2_t0(const Coef& c, f2 f01, f2 f10) { return add2s(mul2x(bc2(c.c00), f01), mul2x(bc2(c.c01), f10)); }
+__device__ __forceinline__ f2 est2_t1(const Coef& c, f2 f01, f2 f10) { return sub2s(mul2x(bc2(c.c10), f01), mul2x(bc2(c.c11), f10)); }
+template <typename T> __device__ __forceinline__ f2 storage_round2(f2 v) { return v; }
+template <> __device__ __forceinline__ f2 storage_round2<__nv_bfloat16>(f2 v) {
+    return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y));
+}
+
+// the bilinear sample of one frame for the two pixels of a thread
+struct QTap2 {
+    f2 wnw, wne, wsw, wse;      // corner weights (ATen: area of the opposite sub-rectangle)
+    f2 wsum;                    // sum of the weights of the corners inside the frame
+    unsigned idx[2];            // entry index in the launch-wide table, frame base + (y0+1)*(W+1) + (x0+1); only dereferenced when ok
+    bool ok[2];                 // the sample has weight inside the frame (then the entry exists)
 };
 
+constexpr float Q8_FLOOR_MAGIC = 12582912.0f;       // 1.5 * 2^23: ulp 1 on [2^23, 2^24)
+constexpr int Q8_FLOOR_BITS = 0x4B400000;
+
+// xbias = bit pattern of the floor constant - 1 - index of the frame's first entry in the launch-wide table (q8_xbias)
 template <int MODE>
-__device__ __forceinline__ QTap make_qtap(int x, int y, float u, float v, const Geom& g) {
-    float ix = sample_coord<MODE>((float)x, u, g.xnorm, g.xinv, g.xm1);
-    float iy = sample_coord<MODE>((float)y, v, g.ynorm, g.yinv, g.ym1);
-    ix = fminf(fmaxf(ix, -2.0f), (float)g.W + 1.0f);      // far outside (or NaN): no corner inside
-    iy = fminf(fmaxf(iy, -2.0f), (float)g.H + 1.0f);
-    const float fx = floorf(ix), fy = floorf(iy);
-    // ix - fx is exact; 1 - (ix - fx) equals ATen's (fx + 1) - ix except for |ix| < 1, where it may differ by one
-    // rounding (6e-8) -- one instruction less per axis
-    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-    const int x0 = (int)fx, y0 = (int)fy;
-    QTap t;
-    t.wnw = wx0 * wy0; t.wne = wx1 * wy0; t.wsw = wx0 * wy1; t.wse = wx1 * wy1;
-    const float sx = ((unsigned)x0 < (unsigned)g.W ? wx0 : 0.0f) + ((unsigned)(x0 + 1) < (unsigned)g.W ? wx1 : 0.0f);
-    const float sy = ((unsigned)y0 < (unsigned)g.H ? wy0 : 0.0f) + ((unsigned)(y0 + 1) < (unsigned)g.H ? wy1 : 0.0f);
-    t.wsum = sx * sy;
-    t.ok = (unsigned)(x0 + 1) <= (unsigned)g.W && (unsigned)(y0 + 1) <= (unsigned)g.H;
-    t.idx = (y0 + 1) * (g.W + 1) + (x0 + 1);
+__device__ __forceinline__ QTap2 make_qtap2(f2 posx, f2 posy, f2 u, f2 v, const Geom& g, unsigned xbias) {
+    const f2 ix = sample_coord2<MODE>(posx, u, g.xnorm, g.xinv, g.xm1);
+    const f2 iy = sample_coord2<MODE>(posy, v, g.ynorm, g.yinv, g.ym1);
+    // floor without the conversion unit: RD(ix + 1.5 * 2^23) is floor(ix) + 1.5 * 2^23 exactly for |ix| < 2^22, its low
+    // mantissa bits are the integer, and subtracting the constant gives floor(ix) as a float.
+    const f2 rx = __fadd2_rd(ix, bc2(Q8_FLOOR_MAGIC)), ry = __fadd2_rd(iy, bc2(Q8_FLOOR_MAGIC));
+    const f2 fx = add2(rx, bc2(-Q8_FLOOR_MAGIC)), fy = add2(ry, bc2(-Q8_FLOOR_MAGIC));
+    // ix - fx is exact; saturation only matters for non-finite coordinates (NaN, inf - inf -> weight 0: such samples
+    // read nothing and give 0).  1 - (ix - fx) equals ATen's (fx + 1) - ix except for |ix| < 1, where it may differ
+    // by one rounding (6e-8).
+    const f2 wx1 = make_float2(__saturatef(ix.x - fx.x), __saturatef(ix.y - fx.y));
+    const f2 wy1 = make_float2(__saturatef(iy.x - fy.x), __saturatef(iy.y - fy.y));
+    const f2 wx0 = sub2(bc2(1.0f), wx1), wy0 = sub2(bc2(1.0f), wy1);
+    QTap2 t;
+    t.wnw = mul2(wx0, wy0); t.wne = mul2(wx1, wy0); t.wsw = mul2(wx0, wy1); t.wse = mul2(wx1, wy1);
+    // total weight of the columns inside the frame: 1 in the interior, ix + 1 for ix in [-1, 0), W - ix for
+    // ix in [W-1, W), 0 outside or NaN = min(sat(ix + 1), sat(W - ix)), the same roundings as wx1 / wx0 there
+    const float Wf = g.xm1 + 1.0f, Hf = g.ym1 + 1.0f;
+    const f2 sx = make_float2(fminf(__saturatef(ix.x + 1.0f), __saturatef(Wf - ix.x)), fminf(__saturatef(ix.y + 1.0f), __saturatef(Wf - ix.y)));
+    const f2 sy = make_float2(fminf(__saturatef(iy.x + 1.0f), __saturatef(Hf - iy.x)), fminf(__saturatef(iy.y + 1.0f), __saturatef(Hf - iy.y)));
+    t.wsum = mul2(sx, sy);
+    // wsum > 0  =>  -1 < ix < W and -1 < iy < H  =>  the entry (x0, y0) in [-1, W-1] x [-1, H-1] exists.  wsum == 0: every
+    // corner inside the frame has weight 0 (or the coordinate is not finite): the sample is 0 without reading anything.
+    t.ok[0] = t.wsum.x > 0.0f; t.ok[1] = t.wsum.y > 0.0f;
+    const unsigned w1 = (unsigned)(g.W + 1);
+    t.idx[0] = ((unsigned)__float_as_int(ry.x) - (unsigned)(Q8_FLOOR_BITS - 1)) * w1 + ((unsigned)__float_as_int(rx.x) - xbias);
+    t.idx[1] = ((unsigned)__float_as_int(ry.y) - (unsigned)(Q8_FLOOR_BITS - 1)) * w1 + ((unsigned)__float_as_int(rx.y) - xbias);
     return t;
 }
 
-__device__ __forceinline__ uint4 load_entry(const uint4* __restrict__ table, const QTap& t) {
+// kept in a register for the whole kernel (the compiler otherwise recomputes the table offset, ~8 instructions, in front
+// of every gather)
+__device__ __forceinline__ unsigned q8_xbias(unsigned first_entry) {
+    unsigned r = (unsigned)(Q8_FLOOR_BITS - 1) - first_entry;
+    asm volatile("" : "+r"(r));
+    return r;
+}
+
+__device__ __forceinline__ uint4 load_entry(const uint4* __restrict__ quads, unsigned idx, bool ok) {
     // unsigned 32-bit entry index: the address is one IMAD.WIDE.U32 (base + idx * 16)
-    return t.ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(table) + (size_t)(unsigned)t.idx * 16u))
-                : make_uint4(0u, 0u, 0u, 0u);
+    return ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(quads) + (size_t)idx * 16u))
+              : make_uint4(0u, 0u, 0u, 0u);
 }
 
-// byte k of w as a float: PRMT builds the bit pattern of 2^23 + b, one FADD removes the 2^23 (exact)
-__device__ __forceinline__ float byte_f(unsigned w, int k) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + k)) - 8388608.0f;
-}
+// byte k of w as the bit pattern of 2^23 + b (one PRMT); subtracting 2^23 (exact) gives the byte as a float
+__device__ __forceinline__ float byte_bits(unsigned w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + k)); }
 
-// normalised bilinear sample of the three channels from one entry
-__device__ __forceinline__ void q8_sample(const uint4& q, const QTap& t, const Norm3& nm, float (&out)[3]) {
-    const unsigned w[3] = {q.x, q.y, q.z};
+// normalised bilinear samples of the three channels for the two pixels, from their two entries
+__device__ __forceinline__ void q8_sample2(const uint4& qa, const uint4& qb, const QTap2& t, const Norm3& nm, f2 (&out)[3]) {
+    const unsigned wa[3] = {qa.x, qa.y, qa.z}, wb[3] = {qb.x, qb.y, qb.z};
+    const f2 m23 = bc2(-8388608.0f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         // bytes 0-2 nw, 3-5 ne, 6-8 sw, 9-11 se
-        float s = byte_f(w[c >> 2], c & 3) * t.wnw;
-        s = fmaf(byte_f(w[(3 + c) >> 2], (3 + c) & 3), t.wne, s);
-        s = fmaf(byte_f(w[(6 + c) >> 2], (6 + c) & 3), t.wsw, s);
-        s = fmaf(byte_f(w[(9 + c) >> 2], (9 + c) & 3), t.wse, s);
-        out[c] = fmaf(nm.a[c], s, nm.c[c] * t.wsum);
+        const f2 bnw = add2(make_float2(byte_bits(wa[c >> 2], c & 3), byte_bits(wb[c >> 2], c & 3)), m23);
+        const f2 bne = add2(make_float2(byte_bits(wa[(3 + c) >> 2], (3 + c) & 3), byte_bits(wb[(3 + c) >> 2], (3 + c) & 3)), m23);
+        const f2 bsw = add2(make_float2(byte_bits(wa[(6 + c) >> 2], (6 + c) & 3), byte_bits(wb[(6 + c) >> 2], (6 + c) & 3)), m23);
+        const f2 bse = add2(make_float2(byte_bits(wa[(9 + c) >> 2], (9 + c) & 3), byte_bits(wb[(9 + c) >> 2], (9 + c) & 3)), m23);
+        f2 s = mul2(bnw, t.wnw);
+        s = fma2(bne, t.wne, s);
+        s = fma2(bsw, t.wsw, s);
+        s = fma2(bse, t.wse, s);
+        out[c] = fma2(bc2(nm.a[c]), s, mul2(bc2(nm.c[c]), t.wsum));
     }
 }
 
@@ -162,13 +261,18 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 // a2: compute_inputs from entry tables     reference scripts/models/flow_interpolation.py:338-372
 //     (batched over N timesteps, as flow_pack_fwd_kernel).  TO / NHWC: see flow_pack_fwd_kernel.
 // =============================================================================================
+// CTAs per SM, measured with the packed-arithmetic kernels (profiles/r02h_q8_timing_*.json; 3 CTAs = 80 registers,
+// 4 CTAs = 64 registers with a few spilled bytes): compute_inputs 2.86 ms at 3, 2.94 at 4; compute_output_image with an
+// fp32 U-Net output 1.86 ms at 3, 2.03 at 4; with a bf16 U-Net output 2.25 at 3, 2.12 at 4; with the fused uint8
+// output 2.13 at 3, 2.36 at 4.
 #ifndef SSM_Q8_PACK_MIN_BLOCKS
 #define SSM_Q8_PACK_MIN_BLOCKS 3
 #endif
-// measured (profiles/r02f_q8_timing_*.json): compute_output_image gains from 4 CTAs per SM (64 registers, 2.40 -> 2.25 ms)
-// except with the fused uint8 output, which then spills (2.53 -> 2.94 ms); compute_inputs is best at 3 (80 registers)
 #ifndef SSM_Q8_FUSE_MIN_BLOCKS
-#define SSM_Q8_FUSE_MIN_BLOCKS 4
+#define SSM_Q8_FUSE_MIN_BLOCKS 3
+#endif
+#ifndef SSM_Q8_FUSE_BF16_MIN_BLOCKS
+#define SSM_Q8_FUSE_BF16_MIN_BLOCKS 4
 #endif
 #ifndef SSM_Q8_FUSE_U8_MIN_BLOCKS
 #define SSM_Q8_FUSE_U8_MIN_BLOCKS 3
@@ -181,9 +285,10 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
     const Q8Idx ti = q8_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
-    const long long epf = (long long)(g.H + 1) * (g.W + 1);            // entries per frame
-    const uint4* __restrict__ tab0 = quads + (long long)ti.b * 2 * epf;
-    const uint4* __restrict__ tab1 = tab0 + epf;
+    // entry index of the launch-wide table as an unsigned 32-bit number (B * 2 * entries per frame < 2^32, checked on
+    // the host): the address of a gather is one IMAD.WIDE.U32 on the kernel parameter, no pointer kept in registers
+    const unsigned epf = (unsigned)(g.H + 1) * (unsigned)(g.W + 1);
+    const unsigned xb0 = q8_xbias((unsigned)ti.b * 2u * epf), xb1 = q8_xbias((unsigned)ti.b * 2u * epf + epf);
     const T* F = flow4.p + ti.b * flow4.sb + p;
     const int fsc = (int)flow4.sc, isc = (int)img6.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
@@ -194,48 +299,41 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
     const float* tp = tv + ti.b * N;
     TO* __restrict__ O = out16.p + ti.b * out16.sb + (NHWC ? (long long)p * 16 : (long long)p);
     const int osc = (int)out16.sc;
-    const float fa[2][4] = {{f01x.x, f01y.x, f10x.x, f10y.x}, {f01x.y, f01y.y, f10x.y, f10y.y}};
+    const f2 posx = make_float2((float)ti.x, (float)(ti.x + 1)), posy = bc2((float)ti.y);
     for (int n = 0; n < N; ++n, O += out16.sn) {
         const Coef k = make_coef(__ldg(tp + n));
-        float e1x[2], e1y[2], e0x[2], e0y[2];
-        QTap t1[2], t0[2];
-        uint4 q1[2], q0[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            e0x[i] = storage_round<T>(est_t0(k, fa[i][0], fa[i][2])); e0y[i] = storage_round<T>(est_t0(k, fa[i][1], fa[i][3]));   // F_t0  :353
-            e1x[i] = storage_round<T>(est_t1(k, fa[i][0], fa[i][2])); e1y[i] = storage_round<T>(est_t1(k, fa[i][1], fa[i][3]));   // F_t1  :356
-            t1[i] = make_qtap<MODE>(ti.x + i, ti.y, e1x[i], e1y[i], g);                       // warp(img_1, F_t1) :361
-            t0[i] = make_qtap<MODE>(ti.x + i, ti.y, e0x[i], e0y[i], g);                       // warp(img_0, F_t0) :362
-            q1[i] = load_entry(tab1, t1[i]);
-            q0[i] = load_entry(tab0, t0[i]);
-        }
-        float w1[2][3], w0[2][3];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) { q8_sample(q1[i], t1[i], nm, w1[i]); q8_sample(q0[i], t0[i], nm, w0[i]); }
-        if (NHWC) {                                                                           // :364-367, channels-last
+        const f2 e0x = storage_round2<T>(est2_t0(k, f01x, f10x)), e0y = storage_round2<T>(est2_t0(k, f01y, f10y));   // F_t0  :353
+        const f2 e1x = storage_round2<T>(est2_t1(k, f01x, f10x)), e1y = storage_round2<T>(est2_t1(k, f01y, f10y));   // F_t1  :356
+        const QTap2 t1 = make_qtap2<MODE>(posx, posy, e1x, e1y, g, xb1);                             // warp(img_1, F_t1) :361
+        const uint4 q1a = load_entry(quads, t1.idx[0], t1.ok[0]), q1b = load_entry(quads, t1.idx[1], t1.ok[1]);
+        const QTap2 t0 = make_qtap2<MODE>(posx, posy, e0x, e0y, g, xb0);                             // warp(img_0, F_t0) :362
+        const uint4 q0a = load_entry(quads, t0.idx[0], t0.ok[0]), q0b = load_entry(quads, t0.idx[1], t0.ok[1]);
+        f2 w1[3], w0[3];
+        q8_sample2(q1a, q1b, t1, nm, w1);
+        q8_sample2(q0a, q0b, t0, nm, w0);
+        if constexpr (NHWC) {                                                                 // :364-367, channels-last
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 float o[16];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    o[c] = i ? c1[c].y : c1[c].x; o[3 + c] = w1[i][c]; o[10 + c] = w0[i][c]; o[13 + c] = i ? c0[c].y : c0[c].x;
+                    o[c] = i ? c1[c].y : c1[c].x; o[3 + c] = i ? w1[c].y : w1[c].x;
+                    o[10 + c] = i ? w0[c].y : w0[c].x; o[13 + c] = i ? c0[c].y : c0[c].x;
                 }
-                o[6] = e1x[i]; o[7] = e1y[i]; o[8] = e0x[i]; o[9] = e0y[i];
+                o[6] = i ? e1x.y : e1x.x; o[7] = i ? e1y.y : e1y.x; o[8] = i ? e0x.y : e0x.x; o[9] = i ? e0y.y : e0y.x;
                 store16_nhwc<TO>(O + 16 * i, o);
             }
-            continue;
-        }
-        if constexpr (!NHWC) {
+        } else {
             TO* Of = O;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {                                                     // :364-367
                 sts2(Of + (0 + c) * osc, c1[c].x, c1[c].y);
-                sts2(Of + (3 + c) * osc, w1[0][c], w1[1][c]);
-                sts2(Of + (10 + c) * osc, w0[0][c], w0[1][c]);
+                sts2(Of + (3 + c) * osc, w1[c].x, w1[c].y);
+                sts2(Of + (10 + c) * osc, w0[c].x, w0[c].y);
                 sts2(Of + (13 + c) * osc, c0[c].x, c0[c].y);
             }
-            sts2(Of + 6 * osc, e1x[0], e1x[1]); sts2(Of + 7 * osc, e1y[0], e1y[1]);
-            sts2(Of + 8 * osc, e0x[0], e0x[1]); sts2(Of + 9 * osc, e0y[0], e0y[1]);
+            sts2(Of + 6 * osc, e1x.x, e1x.y); sts2(Of + 7 * osc, e1y.x, e1y.y);
+            sts2(Of + 8 * osc, e0x.x, e0x.y); sts2(Of + 9 * osc, e0y.x, e0y.y);
         }
     }
 }
@@ -253,61 +351,54 @@ struct U8Out {
 };
 
 template <typename T, int MODE, typename TY, bool OUT_U8>
-__global__ void __launch_bounds__(Q8_THREADS, OUT_U8 ? SSM_Q8_FUSE_U8_MIN_BLOCKS : SSM_Q8_FUSE_MIN_BLOCKS)
+__global__ void __launch_bounds__(Q8_THREADS, OUT_U8 ? SSM_Q8_FUSE_U8_MIN_BLOCKS : (sizeof(TY) == 2 ? SSM_Q8_FUSE_BF16_MIN_BLOCKS : SSM_Q8_FUSE_MIN_BLOCKS))
 fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<const TY> out5,
                    const float* __restrict__ tv, View<T> out3, U8Out u8, int N, Geom g, Norm3 nm) {
     const Q8Idx ti = q8_index(g.H, g.W);
     if (!ti.valid) return;
     const int p = ti.y * g.W + ti.x;
-    const long long epf = (long long)(g.H + 1) * (g.W + 1);
-    const uint4* __restrict__ tab0 = quads + (long long)ti.b * 2 * epf;
-    const uint4* __restrict__ tab1 = tab0 + epf;
+    const unsigned epf = (unsigned)(g.H + 1) * (unsigned)(g.W + 1);
+    const unsigned xb0 = q8_xbias((unsigned)ti.b * 2u * epf), xb1 = q8_xbias((unsigned)ti.b * 2u * epf + epf);
     const float* tp = tv + ti.b * N;
     const T* F = flow4.p + ti.b * flow4.sb + p;
     const int fsc = (int)flow4.sc, ysc = (int)out5.sc, osc = (int)out3.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
-    const float fa[2][4] = {{f01x.x, f01y.x, f10x.x, f10y.x}, {f01x.y, f01y.y, f10x.y, f10y.y}};
     const TY* __restrict__ Y = out5.p + ti.b * out5.sb + p;
     T* __restrict__ O = OUT_U8 ? nullptr : out3.p + ti.b * out3.sb + p;
-    float2 ys[5];
+    const f2 posx = make_float2((float)ti.x, (float)(ti.x + 1)), posy = bc2((float)ti.y);
+    f2 ys[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
     for (int n = 0; n < N; ++n) {
         const float tt = __ldg(tp + n);
         const Coef k = make_coef(tt);
-        const float omt = k.omt;
-        const float ya[2][5] = {{ys[0].x, ys[1].x, ys[2].x, ys[3].x, ys[4].x}, {ys[0].y, ys[1].y, ys[2].y, ys[3].y, ys[4].y}};
+        const f2 y0 = ys[0], y1 = ys[1], y2 = ys[2], y3 = ys[3], y4 = ys[4];
         if (n + 1 < N) {             // streaming loads of the next timestep, in flight during the gathers
             Y += out5.sn;
 #pragma unroll
             for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
         }
-        QTap t0[2], t1[2];
-        uint4 q0[2], q1[2];
+        const f2 f1x = add2x(storage_round2<T>(est2_t1(k, f01x, f10x)), y1);                  // :412
+        const f2 f1y = add2x(storage_round2<T>(est2_t1(k, f01y, f10y)), y2);
+        const f2 f0x = add2x(storage_round2<T>(est2_t0(k, f01x, f10x)), y3);                  // :413
+        const f2 f0y = add2x(storage_round2<T>(est2_t0(k, f01y, f10y)), y4);
+        const QTap2 t0 = make_qtap2<MODE>(posx, posy, f0x, f0y, g, xb0);                            // :416
+        const uint4 q0a = load_entry(quads, t0.idx[0], t0.ok[0]), q0b = load_entry(quads, t0.idx[1], t0.ok[1]);
+        const QTap2 t1 = make_qtap2<MODE>(posx, posy, f1x, f1y, g, xb1);                            // :418
+        const uint4 q1a = load_entry(quads, t1.idx[0], t1.ok[0]), q1b = load_entry(quads, t1.idx[1], t1.ok[1]);
+        // V_t<-1 = sigmoid(out[:, 0]) (:386-388) as 1 / (1 + 2^(-x log2 e)); V_t<-0 = 1 - V_t<-1 (:390)
+        const f2 e = mul2(y0, bc2(-1.4426950408889634f));
+        const f2 d = add2(make_float2(ex2_approx(e.x), ex2_approx(e.y)), bc2(1.0f));
+        const f2 v1 = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+        const f2 v0 = sub2(bc2(1.0f), v1);
+        const f2 a0 = mul2(bc2(k.omt), v0), a1 = mul2(bc2(tt), v1);
+        const f2 z = add2(a0, a1);
+        const f2 rz = make_float2(rcp_approx(z.x), rcp_approx(z.y));                           // 1/Z  :425
+        f2 s0[3], s1[3], res[3];
+        q8_sample2(q0a, q0b, t0, nm, s0);
+        q8_sample2(q1a, q1b, t1, nm, s1);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float f1x = __fadd_rn(storage_round<T>(est_t1(k, fa[i][0], fa[i][2])), ya[i][1]);          // :412
-            const float f1y = __fadd_rn(storage_round<T>(est_t1(k, fa[i][1], fa[i][3])), ya[i][2]);
-            const float f0x = __fadd_rn(storage_round<T>(est_t0(k, fa[i][0], fa[i][2])), ya[i][3]);          // :413
-            const float f0y = __fadd_rn(storage_round<T>(est_t0(k, fa[i][1], fa[i][3])), ya[i][4]);
-            t0[i] = make_qtap<MODE>(ti.x + i, ti.y, f0x, f0y, g);                          // :416
-            t1[i] = make_qtap<MODE>(ti.x + i, ti.y, f1x, f1y, g);                          // :418
-            q0[i] = load_entry(tab0, t0[i]);
-            q1[i] = load_entry(tab1, t1[i]);
-        }
-        float res[2][3];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float v1 = sigmoid_fast(ya[i][0]);                                        // :386-388
-            const float v0 = 1.0f - v1;                                                     // :390
-            const float a0 = omt * v0, a1 = tt * v1;
-            const float rz = rcp_approx(a0 + a1);                                           // 1/Z  :425
-            float s0[3], s1[3];
-            q8_sample(q0[i], t0[i], nm, s0);
-            q8_sample(q1[i], t1[i], nm, s1);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) res[i][c] = (a0 * s0[c] + a1 * s1[c]) * rz;        // :420-427
-        }
+        for (int c = 0; c < 3; ++c) res[c] = mul2(fma2(a1, s1[c], mul2(a0, s0[c])), rz);       // :420-427
         if (OUT_U8) {
             const int oy = ti.y - u8.top;
             if ((unsigned)oy < (unsigned)u8.H_out) {
@@ -319,13 +410,13 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<co
                         unsigned char* o = row + (long long)ox * 3;
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
-                            o[u8.bgr ? 2 - c : c] = to_u8(res[i][c], u8.std[c], u8.mean[c], u8.scale, u8.saturate);
+                            o[u8.bgr ? 2 - c : c] = to_u8(i ? res[c].y : res[c].x, u8.std[c], u8.mean[c], u8.scale, u8.saturate);
                     }
                 }
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) sts2(O + c * osc, res[0][c], res[1][c]);
+            for (int c = 0; c < 3; ++c) sts2(O + c * osc, res[c].x, res[c].y);
             O += out3.sn;
         }
     }

@@ -615,7 +615,41 @@ def main():
                                      "peak": peak, "unit": "GB/s", "frac": train[k]["frac_of_peak"],
                                      "algorithmic_bytes_per_launch": nbytes[k], "launch_ms": ms,
                                      "traffic": traffic.get(k + "_dram_bytes_per_launch")})
-        del fg, yg, rgbx, in16, frames, g3, g16
+        # the same backward with image gradients (frames require grad): deterministic fixed-point scatter on top
+        ig = img6.clone().requires_grad_(True)
+        frames_i = ssm_b200.fuse_from_flow(ig, fg, yg, t, packed=rgbx)
+        ims = []
+        for i in range(4):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            torch.autograd.grad(frames_i, (ig, fg, yg), g3, retain_graph=True)
+            e[1].record()
+            torch.cuda.synchronize()
+            if i >= 1:
+                ims.append(e[0].elapsed_time(e[1]))
+        ms = statistics.median(ims)
+        nb = nbytes["fuse_flow_bwd"] + 6 * 4 * NPX * B
+        train["fuse_flow_bwd_with_image_grad"] = {"ms": ms, "algorithmic_gbs": nb / (ms * 1e-3) / 1e9, "frac_of_peak": nb / (ms * 1e-3) / 1e9 / peak,
+                                                  "times_the_gather_only_backward": ms / train["fuse_flow_bwd"]["ms"]}
+        del fg, yg, rgbx, in16, frames, g3, g16, ig, frames_i
+        torch.cuda.empty_cache()
+        # stand-alone warp (a1, layers.py:73-120) on the 16 first frames: planar gathers and the RGBx copy
+        xw, fw = img6[:, 0:3].contiguous().requires_grad_(True), flow4[:, 0:2].contiguous().requires_grad_(True)
+        gw = torch.randn_like(xw)
+        pk = ssm_b200.pack_image(xw)
+        warp_t = {}
+        for name, kw in (("planar", {}), ("rgbx", {"packed": pk})):
+            yw = ssm_b200.warp(xw, fw, **kw)
+            warp_t["warp_fwd_" + name] = (timed(lambda: ssm_b200.warp(xw.detach(), fw.detach(), **{k: v for k, v in kw.items()})), 8)
+            warp_t["warp_bwd_flow_" + name] = (timed(lambda: torch.autograd.grad(yw, (fw,), gw, retain_graph=True)), 10)
+            if name == "planar":
+                warp_t["warp_bwd_flow_and_image"] = (timed(lambda: torch.autograd.grad(yw, (xw, fw), gw, retain_graph=True), reps=3, warm=1), 13)
+            del yw
+        warp_t["pack_image"] = (timed(lambda: ssm_b200.pack_image(xw, out=pk)), 7)
+        for k, (ms, per_px) in warp_t.items():
+            nb = per_px * 4 * NPX * B
+            train[k] = {"ms": ms, "algorithmic_gbs": nb / (ms * 1e-3) / 1e9, "frac_of_peak": nb / (ms * 1e-3) / 1e9 / peak}
+        del xw, fw, gw, pk
     del in16_buf, rgbx_buf
     torch.cuda.empty_cache()
 

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 6
+#define SSM_ABI_VERSION 7
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -87,6 +87,20 @@ int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_te
                  const ssm_tensor* grad_img, const ssm_tensor* grad_flow,
                  int B, int C, int H, int W, int dtype, int coord_mode,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same with the image given as an RGBx copy (C = 3 only): ssm_pack_image writes img3 (B x 3 x H x W planar) as
+ * B x H x W x 4 elements of the storage dtype (ssm_packed_image_bytes, 16-byte aligned); each bilinear tap of the
+ * warp is then one 16-byte request instead of three 4-byte ones.  Worth it when an image is warped more than once
+ * (SSMLosses.get_warp_loss warps each frame by two flows, losses.py:152-162).  The image gradient does not read
+ * the image, so ssm_warp_bwd_packed takes no planar img. */
+size_t ssm_packed_image_bytes(int B, int H, int W, int dtype);
+int ssm_pack_image(const ssm_tensor* img3, void* packed, int B, int H, int W, int dtype, void* stream);
+int ssm_warp_fwd_packed(const void* packed, const ssm_tensor* flow, const ssm_tensor* out,
+                        int B, int H, int W, int dtype, int coord_mode, void* stream);
+int ssm_warp_bwd_packed(const ssm_tensor* grad_out, const void* packed, const ssm_tensor* flow,
+                        const ssm_tensor* grad_img, const ssm_tensor* grad_flow,
+                        int B, int H, int W, int dtype, int coord_mode,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- frame re-layout (no reference counterpart; an internal staging step of a2/a4) -----------
  * The gathers of a2 and a3+a4 are bound by L1 request throughput when the three colour planes of

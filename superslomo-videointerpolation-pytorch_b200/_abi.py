@@ -18,7 +18,7 @@ COORD_DIV, COORD_RCP = 0, 1
 # every symbol include/ssm_b200.h declares
 EXPORTS = (
     "ssm_version", "ssm_last_error",
-    "ssm_warp_fwd", "ssm_warp_bwd",
+    "ssm_warp_fwd", "ssm_warp_bwd", "ssm_packed_image_bytes", "ssm_pack_image", "ssm_warp_fwd_packed", "ssm_warp_bwd_packed",
     "ssm_flow_pack_fwd", "ssm_flow_pack_bwd", "ssm_flow_pack_fwd_nhwc",
     "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_flow_fwd_mixed",
     "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd", "ssm_fuse_loss_workspace_bytes",
@@ -58,6 +58,11 @@ def lib():
     L.ssm_last_error.restype = ctypes.c_char_p
     L.ssm_warp_fwd.argtypes = [P, P, P, I, I, I, I, I, I, V]
     L.ssm_warp_bwd.argtypes = [P, P, P, P, P, I, I, I, I, I, I, V, Z, V]
+    L.ssm_packed_image_bytes.argtypes = [I, I, I, I]
+    L.ssm_packed_image_bytes.restype = Z
+    L.ssm_pack_image.argtypes = [P, V, I, I, I, I, V]
+    L.ssm_warp_fwd_packed.argtypes = [V, P, P, I, I, I, I, I, V]
+    L.ssm_warp_bwd_packed.argtypes = [P, V, P, P, P, I, I, I, I, I, V, Z, V]
     L.ssm_selftest_division.argtypes = [I, V, V]
     L.ssm_selftest_division.restype = I
     L.ssm_pack_frames.argtypes = [P, V, I, I, I, I, V]
@@ -96,7 +101,7 @@ def lib():
     L.ssm_upsample2x_bwd_nhwc.argtypes = [V, V, I, I, I, I, LL, I, V]
     L.ssm_leaky_bwd_nhwc.argtypes = [V, V, V, LL, I, ctypes.c_float, I, V]
     L.ssm_avgpool2_bwd_nhwc.argtypes = [V, V, I, I, I, I, I, V]
-    for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
+    for n in ("ssm_warp_fwd", "ssm_warp_bwd", "ssm_pack_image", "ssm_warp_fwd_packed", "ssm_warp_bwd_packed", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd",
               "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed",
               "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
               "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host",

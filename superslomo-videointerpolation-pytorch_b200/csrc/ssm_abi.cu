@@ -121,6 +121,10 @@ template <typename F> int dispatch(int dtype, int mode, F&& f) {
                                  : f.template run<__nv_bfloat16, SSM_COORD_RCP>();
 }
 
+unsigned sw_grid(int B, int H, int W) {      // one CTA per 64 x 16 tile of source pixels (ssm_scatter.cuh)
+    return (unsigned)((long long)B * ((H + SW_TILE_H - 1) / SW_TILE_H) * ((W + SW_TILE_W - 1) / SW_TILE_W));
+}
+
 unsigned finalize_grid(long long total) {
     long long blocks = (total + 255) / 256;
     long long cap = 148ll * 16;
@@ -128,18 +132,31 @@ unsigned finalize_grid(long long total) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed != NULL: the image is the RGBx copy (B x H x W x 4, C = 3); img is then unused by the gathers
+static ssm_tensor packed_image_desc(const void* packed, int H, int W) {
+    ssm_tensor d;
+    d.data = const_cast<void*>(packed); d.stride_b = (long long)H * W * 4; d.stride_n = 0; d.stride_c = 1;
+    return d;
+}
+
 struct WarpFwd {
-    const ssm_tensor *img, *flow, *out; int B, C, H, W; cudaStream_t s;
+    const ssm_tensor *img, *flow, *out; const void* packed; int B, C, H, W; cudaStream_t s;
     template <typename T, int MODE> int run() {
-        warp_fwd_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-            cview<T>(img), cview<T>(flow), mview<T>(out), C, make_geom(H, W));
+        if (packed) {
+            const ssm_tensor pd = packed_image_desc(packed, H, W);
+            warp_fwd_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(&pd), cview<T>(flow), mview<T>(out), 3, make_geom(H, W));
+        } else {
+            warp_fwd_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                cview<T>(img), cview<T>(flow), mview<T>(out), C, make_geom(H, W));
+        }
         SSM_LAUNCH_CHECK("ssm_warp_fwd");
         return SSM_OK;
     }
 };
 
 struct WarpBwd {
-    const ssm_tensor *gout, *img, *flow, *gimg, *gflow; int B, C, H, W; void* ws; cudaStream_t s;
+    const ssm_tensor *gout, *img, *flow, *gimg, *gflow; const void* packed; int B, C, H, W; void* ws; cudaStream_t s;
     template <typename T, int MODE> int run() {
         const Geom g = make_geom(H, W);
         const bool want_img = gimg && gimg->data, want_flow = gflow && gflow->data;
@@ -151,8 +168,14 @@ struct WarpBwd {
             if (e != cudaSuccess) return cuda_fail(e, "ssm_warp_bwd memset");
         }
         if (want_flow) {
-            warp_bwd_flow_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-                cview<T>(gout), cview<T>(img), cview<T>(flow), mview<T>(gflow), C, g, hdr);
+            if (packed) {
+                const ssm_tensor pd = packed_image_desc(packed, H, W);
+                warp_bwd_flow_kernel<T, MODE, true><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                    cview<T>(gout), cview<T>(&pd), cview<T>(flow), mview<T>(gflow), 3, g, hdr);
+            } else {
+                warp_bwd_flow_kernel<T, MODE, false><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                    cview<T>(gout), cview<T>(img), cview<T>(flow), mview<T>(gflow), C, g, hdr);
+            }
             SSM_LAUNCH_CHECK("ssm_warp_bwd (flow)");
         } else if (want_img) {
             absmax_kernel<T><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(cview<T>(gout), C, g, hdr);
@@ -160,13 +183,25 @@ struct WarpBwd {
         }
         if (want_img) {
             const int cb = count_bits_for(npx);
-            warp_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
-                cview<T>(gout), cview<T>(flow), acc, C, g, hdr, cb);
+            if (C == 3)
+                warp_scatter_win_kernel<T, MODE><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(cview<T>(gout), cview<T>(flow), acc, g, hdr);
+            else
+                warp_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+                    cview<T>(gout), cview<T>(flow), acc, C, g, hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (scatter)");
             const long long total = (long long)B * C * npx;
             scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg), C, npx, total, hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (finalize)");
         }
+        return SSM_OK;
+    }
+};
+
+struct PackImage {
+    const ssm_tensor* img3; void* packed; int B, H, W; cudaStream_t s;
+    template <typename T, int MODE> int run() {
+        pack_image_kernel<T><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(cview<T>(img3), (T*)packed, make_geom(H, W));
+        SSM_LAUNCH_CHECK("ssm_pack_image");
         return SSM_OK;
     }
 };
@@ -232,7 +267,7 @@ struct PackBwd {
             cview<T>(g16), cview<T>(img6), (const T*)packed, cview<T>(flow4), t, mview<T>(gflow4), direct, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_flow_pack_bwd");
         const int cb = count_bits_for((long long)N * npx);
-        flow_pack_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+        flow_pack_scatter_kernel<T, MODE><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(
             cview<T>(g16), cview<T>(flow4), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_flow_pack_bwd (scatter)");
         const long long total = (long long)B * 6 * npx;
@@ -296,7 +331,7 @@ struct FuseBwd {
             mview<T>(gflows4), stage, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd");
         const int cb = count_bits_for((long long)N * npx);
-        fuse_scatter_kernel<T, MODE, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
+        fuse_scatter_kernel<T, MODE, RECOMP><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(
             stage, cview<T>(flows4), cview<T>(out5), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd (scatter)");
         const long long total = (long long)B * 6 * npx;
@@ -394,7 +429,30 @@ int ssm_warp_fwd(const ssm_tensor* img, const ssm_tensor* flow, const ssm_tensor
     SSM_TRY(check_tensor(img, "img", dtype, true));
     SSM_TRY(check_tensor(flow, "flow", dtype, true));
     SSM_TRY(check_tensor(out, "out", dtype, true));
-    return dispatch(dtype, coord_mode, WarpFwd{img, flow, out, B, C, H, W, (cudaStream_t)stream});
+    return dispatch(dtype, coord_mode, WarpFwd{img, flow, out, nullptr, B, C, H, W, (cudaStream_t)stream});
+}
+
+size_t ssm_packed_image_bytes(int B, int H, int W, int dtype) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)B * H * W * 4 * (dtype == SSM_DTYPE_F32 ? 4 : 2);
+}
+
+int ssm_pack_image(const ssm_tensor* img3, void* packed, int B, int H, int W, int dtype, void* stream) {
+    SSM_TRY(check_common(B, 1, 3, H, W, dtype, SSM_COORD_DIV));
+    SSM_TRY(check_tensor(img3, "img3", dtype, true));
+    if (!packed) return fail(SSM_ERR_NULL, "packed is NULL");
+    if (((uintptr_t)packed) % 16 != 0) return fail(SSM_ERR_ALIGN, "packed must be 16-byte aligned");
+    return dispatch(dtype, SSM_COORD_DIV, PackImage{img3, packed, B, H, W, (cudaStream_t)stream});
+}
+
+int ssm_warp_fwd_packed(const void* packed, const ssm_tensor* flow, const ssm_tensor* out,
+                        int B, int H, int W, int dtype, int coord_mode, void* stream) {
+    SSM_TRY(check_common(B, 1, 3, H, W, dtype, coord_mode));
+    if (!packed) return fail(SSM_ERR_NULL, "packed is NULL");
+    if (((uintptr_t)packed) % 16 != 0) return fail(SSM_ERR_ALIGN, "packed must be 16-byte aligned");
+    SSM_TRY(check_tensor(flow, "flow", dtype, true));
+    SSM_TRY(check_tensor(out, "out", dtype, true));
+    return dispatch(dtype, coord_mode, WarpFwd{nullptr, flow, out, packed, B, 3, H, W, (cudaStream_t)stream});
 }
 
 int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_tensor* flow,
@@ -414,7 +472,28 @@ int ssm_warp_bwd(const ssm_tensor* grad_out, const ssm_tensor* img, const ssm_te
         if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
     }
     return dispatch(dtype, coord_mode,
-                    WarpBwd{grad_out, img, flow, grad_img, grad_flow, B, C, H, W, workspace, (cudaStream_t)stream});
+                    WarpBwd{grad_out, img, flow, grad_img, grad_flow, nullptr, B, C, H, W, workspace, (cudaStream_t)stream});
+}
+
+int ssm_warp_bwd_packed(const ssm_tensor* grad_out, const void* packed, const ssm_tensor* flow,
+                        const ssm_tensor* grad_img, const ssm_tensor* grad_flow,
+                        int B, int H, int W, int dtype, int coord_mode,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    SSM_TRY(check_common(B, 1, 3, H, W, dtype, coord_mode));
+    if (!packed) return fail(SSM_ERR_NULL, "packed is NULL");
+    if (((uintptr_t)packed) % 16 != 0) return fail(SSM_ERR_ALIGN, "packed must be 16-byte aligned");
+    SSM_TRY(check_tensor(grad_out, "grad_out", dtype, true));
+    SSM_TRY(check_tensor(flow, "flow", dtype, true));
+    SSM_TRY(check_tensor(grad_img, "grad_img", dtype, false));
+    SSM_TRY(check_tensor(grad_flow, "grad_flow", dtype, false));
+    if (grad_img && grad_img->data) {
+        if (!workspace || workspace_bytes < ssm_warp_bwd_workspace_bytes(B, 3, H, W))
+            return fail(SSM_ERR_WORKSPACE, "ssm_warp_bwd_packed: grad_img needs %zu workspace bytes, got %zu",
+                        ssm_warp_bwd_workspace_bytes(B, 3, H, W), workspace ? workspace_bytes : (size_t)0);
+        if (((uintptr_t)workspace) % 16 != 0) return fail(SSM_ERR_ALIGN, "workspace must be 16-byte aligned");
+    }
+    return dispatch(dtype, coord_mode,
+                    WarpBwd{grad_out, nullptr, flow, grad_img, grad_flow, packed, B, 3, H, W, workspace, (cudaStream_t)stream});
 }
 
 size_t ssm_packed_frames_bytes(int B, int H, int W, int dtype) {

@@ -91,10 +91,34 @@ pack_frames_kernel(View<const T> img6, T* __restrict__ packed, Geom g) {
     }
 }
 
+// one image (B x 3 x H x W planar) -> B x H x W x 4 (RGBx): the stand-alone warp's staging copy, for callers that
+// warp the same image more than once (losses.py:152-162 warps each frame by two flows)
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS)
+pack_image_kernel(View<const T> img3, T* __restrict__ packed, Geom g) {
+    TileIdx ti = tile_index(g.H, g.W);
+    if (!ti.valid) return;
+    const int p = ti.y * g.W + ti.x;
+    const long long npx = (long long)g.H * g.W;
+    const T* I = img3.p + ti.b * img3.sb + p;
+    T* o = packed + ((long long)ti.b * npx + p) * 4;
+    const float r = lds_(I), gg = lds_(I + img3.sc), bb = lds_(I + 2 * img3.sc);
+    if (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(r, gg, bb, 0.0f);
+    } else {
+        const unsigned lo = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(r)) |
+                            ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(gg)) << 16);
+        const unsigned hi = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(bb));
+        *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+    }
+}
+
 // =============================================================================================
-// a1: warp forward          reference scripts/models/layers.py:73-120   (any channel count: planar)
+// a1: warp forward          reference scripts/models/layers.py:73-120
+//     planar: any channel count, one 4-byte gather per tap and channel.  PACKED (C = 3): img.p points at the RGBx
+//     copy of the image (pack_image_kernel, batch stride H*W*4): one 16-byte gather per tap.
 // =============================================================================================
-template <typename T, int MODE>
+template <typename T, int MODE, bool PACKED>
 __global__ void __launch_bounds__(TILE_THREADS)
 warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int C, Geom g) {
     TileIdx ti = tile_index(g.H, g.W);
@@ -105,16 +129,23 @@ warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int C, Geom 
     Taps t = make_taps<MODE>(ti.x, ti.y, u, v, g);
     const T* ip = img.p + ti.b * img.sb;
     T* op = out.p + ti.b * out.sb + p;
-    for (int c = 0; c < C; ++c) {
-        Quad q = gather_quad(ip + c * img.sc, t, g.W);
-        sts_(op + c * out.sc, bilerp(q, t));
+    if constexpr (PACKED) {
+        Quad q[3];
+        gather3<T, true>(ip, 0, t, g.W, q);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sts_(op + c * out.sc, bilerp(q[c], t));
+    } else {
+        for (int c = 0; c < C; ++c) {
+            Quad q = gather_quad(ip + c * img.sc, t, g.W);
+            sts_(op + c * out.sc, bilerp(q, t));
+        }
     }
 }
 
 // warp backward, gather part: gradient w.r.t. the flow.  When hdr is given it also records
 // max |grad_out| for the deterministic image-gradient pass (ssm_scatter.cuh), which re-reads
 // grad_out and flow directly.
-template <typename T, int MODE>
+template <typename T, int MODE, bool PACKED>
 __global__ void __launch_bounds__(TILE_THREADS)
 warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, View<T> gflow, int C, Geom g,
                      ScatterHdr* hdr) {
@@ -128,11 +159,22 @@ warp_bwd_flow_kernel(View<const T> gout, View<const T> img, View<const T> flow, 
         const T* ip = img.p + ti.b * img.sb;
         const T* gp = gout.p + ti.b * gout.sb + p;
         float gix = 0.0f, giy = 0.0f;
-        for (int c = 0; c < C; ++c) {
-            Quad q = gather_quad(ip + c * img.sc, t, g.W);
-            float gc = lds_(gp + c * gout.sc);
-            amax = fmaxf(amax, fabsf(gc));
-            bilerp_grad(q, t, gc, gix, giy);
+        if constexpr (PACKED) {
+            Quad q[3];
+            gather3<T, true>(ip, 0, t, g.W, q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float gc = lds_(gp + c * gout.sc);
+                amax = fmaxf(amax, fabsf(gc));
+                bilerp_grad(q[c], t, gc, gix, giy);
+            }
+        } else {
+            for (int c = 0; c < C; ++c) {
+                Quad q = gather_quad(ip + c * img.sc, t, g.W);
+                float gc = lds_(gp + c * gout.sc);
+                amax = fmaxf(amax, fabsf(gc));
+                bilerp_grad(q, t, gc, gix, giy);
+            }
         }
         T* o = gflow.p + ti.b * gflow.sb + p;
         sts_(o, coord_grad_to_flow<MODE>(gix, g.xgrad, g.xnorm, g.xinv));

@@ -1,41 +1,183 @@
-// ssm_scatter.cuh -- deterministic image-gradient accumulation for the warp backward (sm_100a).
+// ssm_scatter.cuh -- deterministic, segmented image-gradient accumulation for the warp backward (sm_100a).
 //
 // The image gradient of a backward warp is a scatter: every source pixel adds weight*grad to four
 // data-dependent destination pixels.  The reference (ATen / cuDNN grid_sampler backward) does this
 // with fp32 atomicAdd, whose result depends on the order in which the adds land and therefore
-// changes from run to run.  Here the destination accumulators are 64-bit fixed point:
+// changes from run to run.  Here every contribution is an INTEGER on one launch-wide grid, so any
+// order of additions gives the same bits:
 //
 //   1. the gather kernels, which read the upstream gradient anyway, record max |grad| of the launch
 //      (integer atomicMax on the bit pattern: order-independent);
-//   2. scale = 2^k is chosen from that maximum and the largest possible number of addends per
-//      destination (N*H*W) so that no sum can overflow 63 bits; k leaves >= 34 fraction bits
-//      below the largest contribution at 1080p x 7 timesteps;
-//   3. every contribution rn(weight*grad) is multiplied by 2^k (exact), rounded to an integer once
-//      and added with an integer atomic -- integer addition is associative, so the sum is
-//      bit-identical run to run whatever the order;
-//   4. a finalise pass converts the sum back (and adds the direct, non-warped gradient terms).
+//   2. scale = 2^k puts that maximum in [2^29, 2^30): a contribution rn(weight*grad) * 2^k (exact) is rounded
+//      ONCE to a 32-bit integer, 30 bits below the largest possible one;
+//   3. SEGMENTED accumulation (round 2): a CTA owns a 64 x 16 tile of source pixels and, per frame and
+//      timestep, a shared-memory window of int32 accumulators covering the tile shifted by the displacement of
+//      its centre pixel plus an 8-pixel halo.  Contributions that land in the window -- nearly all of them for
+//      a piecewise-smooth flow -- are added with shared-memory integer atomics; the few that fall outside go
+//      to the 64-bit global accumulators directly.  After the tile's pixels are done the window's non-zero
+//      cells are flushed with ONE 64-bit global atomic each (about a quarter of the contributions: a cell
+//      collects four taps on average).  int32 wrap-around is exact modulo 2^32 and every add checks its own
+//      overflow (the atomic returns the previous value), correcting the global cell by +-2^32, so the sums
+//      are exact whatever the data;
+//   4. a finalise pass converts the 64-bit sums back (and adds the direct, non-warped gradient terms).
 //
-// Each destination plane segment is therefore accumulated exactly (to 2^-k) and deterministically;
-// the only rounding is the one fp32 product per contribution, which the reference has as well.
+// Measured (tools/exp_scatter.cu, profiles/r02k_exp_scatter.jsonl; 16 pairs x 2 frames x 7 timesteps at
+// 1088x1920): global 64-bit atomics alone 19.5 ms (rough flow) / 10.1 ms (smooth); windowed 8.5 / 7.6 ms.
 #pragma once
 #include "ssm_kernels.cuh"
 
 namespace ssm {
 
-// power-of-two scale: the largest contribution (<= absmax) lands below 2^(62 - count_bits)
-__device__ __forceinline__ float scatter_scale(const ScatterHdr* h, int count_bits) {
+// power-of-two scale: the largest contribution (<= absmax) lands in [2^29, 2^30).  64-bit global sums cannot
+// overflow: the weights of one source pixel sum to 1, so a cell receives at most N*H*W * absmax < 2^25 * 2^30.
+// count_bits is unused (kept in the signatures of the kernels that predate the windowed scheme).
+__device__ __forceinline__ float scatter_scale(const ScatterHdr* h, int /*count_bits*/) {
     unsigned int bits = h->absmax_bits;
     if (bits == 0u) return 1.0f;
     if (bits >= 0x7f800000u) return __int_as_float(0x7fc00000);   // inf/NaN upstream: poison
     int e = (int)(bits >> 23) - 127;           // floor(log2(absmax)) (denormals: -127, fine)
-    int k = (62 - count_bits) - (e + 1);
+    int k = 29 - e;
     k = min(k, 126); k = max(k, -126);
     return __int_as_float((k + 127) << 23);
 }
 
 __device__ __forceinline__ void fx_add(long long* dst, float contrib, float scale) {
-    long long q = __float2ll_rn(contrib * scale);
-    if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)q);
+    const int q = __float2int_rn(contrib * scale);       // |contrib * scale| < 2^30; NaN -> 0 (the scale poisons the result)
+    if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)(long long)q);
+}
+
+// ---- the shared-memory window -----------------------------------------------------------------------------------
+constexpr int SW_TILE_W = 64, SW_TILE_H = 16;             // source pixels per CTA: 256 threads x 4 rows
+constexpr int SW_HALO = 8;
+constexpr int SW_W = SW_TILE_W + 2 * SW_HALO, SW_H = SW_TILE_H + 2 * SW_HALO, SW_PLANE = SW_W * SW_H;   // 80 x 32 cells
+constexpr int SW_THREADS = 256;
+#ifndef SSM_SW_MIN_BLOCKS
+#define SSM_SW_MIN_BLOCKS 4        // 64 registers; the kernels are latency-bound at 2 CTAs per SM (119 registers, profiles/r02p)
+#endif
+constexpr int SW_MIN_BLOCKS = SSM_SW_MIN_BLOCKS;
+constexpr int SW_CENTRE_LX = SW_TILE_W / 2, SW_CENTRE_ROW = SW_TILE_H / 2;
+
+struct SwTile { int b, x0, y0, lx, ly; };
+__device__ __forceinline__ SwTile sw_tile(int H, int W) {
+    const int tiles_x = (W + SW_TILE_W - 1) / SW_TILE_W, tiles_y = (H + SW_TILE_H - 1) / SW_TILE_H, tpp = tiles_x * tiles_y;
+    SwTile t;
+    t.b = blockIdx.x / tpp;
+    const int r = blockIdx.x - t.b * tpp, ty = r / tiles_x, tx = r - ty * tiles_x;
+    t.x0 = tx * SW_TILE_W; t.y0 = ty * SW_TILE_H;
+    t.lx = threadIdx.x & (SW_TILE_W - 1); t.ly = threadIdx.x / SW_TILE_W;        // pixel j of a thread: row ly + 4 j
+    return t;
+}
+
+// one int32 add into the window; an overflow of the cell (possible only after more than two maximal contributions)
+// is repaired exactly by moving 2^32 into the 64-bit global cell
+__device__ __forceinline__ void sw_add(int* cell, int q, long long* gcell) {
+    const int old = atomicAdd(cell, q);
+    const int nw = (int)((unsigned)old + (unsigned)q);
+    if (((old ^ nw) & (q ^ nw)) < 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(gcell), (unsigned long long)(q > 0 ? (1ll << 32) : -(1ll << 32)));
+}
+
+// the contributions of one source pixel (taps t, three channel values gv) to planes plane0 + c * npx
+__device__ __forceinline__ void sw_splat3(int* win, int ox, int oy, const Taps& t, const float (&gv)[3], float scale,
+                                          long long* __restrict__ plane0, long long npx, int W) {
+    const int x0 = (int)t.fx, y0 = (int)t.fy;
+    const int cx = x0 - ox, cy = y0 - oy;
+    const float w[4] = {t.wnw, t.wne, t.wsw, t.wse};
+    const bool in[4] = {t.nw, t.ne, t.sw, t.se};
+    if (in[0] && in[1] && in[2] && in[3] && (unsigned)cx < (unsigned)(SW_W - 1) && (unsigned)cy < (unsigned)(SW_H - 1)) {
+        // the common case: the 2 x 2 footprint lies inside the image and inside the window.  All twelve atomics are
+        // issued before any of their results is looked at (they overlap), and one combined test decides whether some
+        // cell may have overflowed
+        int* c0 = win + cy * SW_W + cx;
+        int q[12], old[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[4 * c + k] = __float2int_rn(w[k] * gv[c] * scale);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) old[4 * c + k] = atomicAdd(c0 + c * SW_PLANE + (k & 1) + (k >> 1) * SW_W, q[4 * c + k]);
+        // |q| < 2^30: a cell can only wrap if it held 2^30 or more in magnitude -- one add + one or per atomic
+        unsigned flag = 0u;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) flag |= (unsigned)old[i] + 0x40000000u;
+        if (flag & 0x80000000u) {            // rare: repair the cells that wrapped by moving 2^32 into the global cell
+            long long* g0 = plane0 + t.off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * c + k, nw = (int)((unsigned)old[i] + (unsigned)q[i]);
+                    if (((old[i] ^ nw) & (q[i] ^ nw)) < 0)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx + (k & 1) + (k >> 1) * W),
+                                  (unsigned long long)(q[i] > 0 ? (1ll << 32) : -(1ll << 32)));
+                }
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!in[k]) continue;
+        const int kx = cx + (k & 1), ky = cy + (k >> 1);
+        const bool inside = (unsigned)kx < (unsigned)SW_W && (unsigned)ky < (unsigned)SW_H;
+        long long* g0 = plane0 + t.off + (k & 1) + (k >> 1) * W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int q = __float2int_rn(w[k] * gv[c] * scale);
+            if (!q) continue;
+            if (inside) sw_add(win + c * SW_PLANE + ky * SW_W + kx, q, g0 + c * npx);
+            else atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx), (unsigned long long)(long long)q);
+        }
+    }
+}
+
+// non-zero cells -> one 64-bit global atomic each; the window is left zeroed for the next phase
+__device__ __forceinline__ void sw_flush(int* win, int ox, int oy, long long* __restrict__ plane0, long long npx, int H, int W) {
+    for (int i = threadIdx.x; i < 3 * SW_PLANE; i += SW_THREADS) {
+        const int q = win[i];
+        if (!q) continue;
+        win[i] = 0;
+        const int c = i / SW_PLANE, r = i - c * SW_PLANE, cy = r / SW_W, cx = r - cy * SW_W;
+        // only taps inside the image were added: (ox + cx, oy + cy) is a valid pixel
+        atomicAdd(reinterpret_cast<unsigned long long*>(plane0 + c * npx + (long long)(oy + cy) * W + (ox + cx)), (unsigned long long)(long long)q);
+    }
+}
+
+// One phase = the contributions of the CTA's 64 x 16 source pixels to one frame's three planes.
+// (win and s_org are deliberately NOT __restrict__: with it the compiler hoists the s_org load above the barrier.)
+// pixel(x, y, t, gv) fills the taps and the three channel values of source pixel (x, y) of this phase.
+template <typename PixelFn>
+__device__ __forceinline__ void sw_phase(int* win, volatile int* s_org, const SwTile& ti, const Geom& g, float scale,
+                                         long long* __restrict__ plane0, long long npx, PixelFn&& pixel) {
+    // window origin: the tile shifted by the displacement of its centre pixel (any origin is correct; this one
+    // captures the most)
+    if (ti.lx == SW_CENTRE_LX && ti.ly == (SW_CENTRE_ROW & 3)) {
+        const int x = min(ti.x0 + SW_CENTRE_LX, g.W - 1), y = min(ti.y0 + SW_CENTRE_ROW, g.H - 1);
+        Taps t; float gv[3];
+        pixel(x, y, t, gv);
+        s_org[0] = (int)t.fx - (x - ti.x0) - SW_HALO;
+        s_org[1] = (int)t.fy - (y - ti.y0) - SW_HALO;
+    }
+    __syncthreads();                         // origin visible; the previous phase's flush is complete
+    const int ox = s_org[0], oy = s_org[1];
+#pragma unroll 1
+    for (int j = 0; j < SW_TILE_H / 4; ++j) {
+        const int x = ti.x0 + ti.lx, y = ti.y0 + ti.ly + 4 * j;
+        if (x < g.W && y < g.H) {
+            Taps t; float gv[3];
+            pixel(x, y, t, gv);
+            sw_splat3(win, ox, oy, t, gv, scale, plane0, npx, g.W);
+        }
+    }
+    __syncthreads();
+    sw_flush(win, ox, oy, plane0, npx, g.H, g.W);
+    // no barrier here: the next phase's first barrier orders this flush before its adds, and every thread has read
+    // s_org before the barrier above
+}
+
+__device__ __forceinline__ void sw_clear(int* win) {
+    for (int i = threadIdx.x; i < 3 * SW_PLANE; i += SW_THREADS) win[i] = 0;
 }
 
 __device__ __forceinline__ void scatter_quad(long long* plane, const Taps& t, int W, float gv, float scale) {
@@ -60,6 +202,7 @@ absmax_kernel(View<const T> v, int C, Geom g, ScatterHdr* hdr) {
 }
 
 // ---- a1: scatter of grad_out through the flow ---------------------------------------------------
+// any channel count: global atomics only (the window scheme below is built for the three colour planes)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(TILE_THREADS)
 warp_scatter_kernel(View<const T> gout, View<const T> flow, long long* __restrict__ acc, int C, Geom g,
@@ -76,73 +219,99 @@ warp_scatter_kernel(View<const T> gout, View<const T> flow, long long* __restric
         scatter_quad(acc + ((long long)ti.b * C + c) * npx, t, g.W, lds_(gp + c * gout.sc), scale);
 }
 
+// C = 3: windowed
+template <typename T, int MODE>
+__global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
+warp_scatter_win_kernel(View<const T> gout, View<const T> flow, long long* __restrict__ acc, Geom g,
+                        const ScatterHdr* __restrict__ hdr) {
+    __shared__ int win[3 * SW_PLANE];
+    __shared__ int s_org[2];
+    const SwTile ti = sw_tile(g.H, g.W);
+    const float scale = scatter_scale(hdr, 0);
+    const long long npx = (long long)g.H * g.W;
+    sw_clear(win);
+    const T* fl = flow.p + ti.b * flow.sb;
+    const T* gp = gout.p + ti.b * gout.sb;
+    const int fsc = (int)flow.sc, gsc = (int)gout.sc;
+    sw_phase(win, s_org, ti, g, scale, acc + (long long)ti.b * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
+        const int p = y * g.W + x;
+        t = make_taps<MODE>(x, y, lds_(fl + p), lds_(fl + fsc + p), g);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gv[c] = lds_(gp + c * gsc + p);
+    });
+}
+
 // ---- a2: scatter of grad16[:, 3:6] through F_t1 into I1 and grad16[:, 10:13] through F_t0 into I0
 template <typename T, int MODE>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
 flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __restrict__ tv,
                          long long* __restrict__ acc, int N, Geom g,
                          const ScatterHdr* __restrict__ hdr, int count_bits) {
-    TileIdx ti = tile_index(g.H, g.W);
-    if (!ti.valid) return;
+    __shared__ int win[3 * SW_PLANE];
+    __shared__ int s_org[2];
+    const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);
-    const int p = ti.y * g.W + ti.x;
     const long long npx = (long long)g.H * g.W;
-    const T* F = flow4.p + ti.b * flow4.sb + p;
-    const float f01x = lds_(F), f01y = lds_(F + flow4.sc);
-    const float f10x = lds_(F + 2 * flow4.sc), f10y = lds_(F + 3 * flow4.sc);
+    sw_clear(win);
+    const T* F = flow4.p + ti.b * flow4.sb;
+    const int fsc = (int)flow4.sc, gsc = (int)g16.sc;
     long long* a0 = acc + (long long)ti.b * 6 * npx;      // I0 planes 0-2, I1 planes 3-5
     for (int n = 0; n < N; ++n) {
         const Coef k = make_coef(__ldg(tv + ti.b * N + n));
-        const Taps t1 = make_taps<MODE>(ti.x, ti.y, storage_round<T>(est_t1(k, f01x, f10x)), storage_round<T>(est_t1(k, f01y, f10y)), g);
-        const Taps t0 = make_taps<MODE>(ti.x, ti.y, storage_round<T>(est_t0(k, f01x, f10x)), storage_round<T>(est_t0(k, f01y, f10y)), g);
-        const T* G = g16.p + ti.b * g16.sb + n * g16.sn + p;
+        const T* G = g16.p + ti.b * g16.sb + n * g16.sn;
+        for (int frame = 0; frame < 2; ++frame) {
+            sw_phase(win, s_org, ti, g, scale, a0 + frame * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
+                const int p = y * g.W + x;
+                const float f01x = ldg_(F + p), f01y = ldg_(F + fsc + p), f10x = ldg_(F + 2 * fsc + p), f10y = ldg_(F + 3 * fsc + p);
+                if (frame) t = make_taps<MODE>(x, y, storage_round<T>(est_t1(k, f01x, f10x)), storage_round<T>(est_t1(k, f01y, f10y)), g);
+                else t = make_taps<MODE>(x, y, storage_round<T>(est_t0(k, f01x, f10x)), storage_round<T>(est_t0(k, f01y, f10y)), g);
+                const T* gp = G + (frame ? 3 : 10) * gsc + p;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            scatter_quad(a0 + (3 + c) * npx, t1, g.W, lds_(G + (3 + c) * g16.sc), scale);
-            scatter_quad(a0 + c * npx, t0, g.W, lds_(G + (10 + c) * g16.sc), scale);
+                for (int c = 0; c < 3; ++c) gv[c] = lds_(gp + c * gsc);
+            });
         }
     }
 }
 
 // ---- a4: scatter of the staged d/d(warped I0), d/d(warped I1) through the refined flows ---------
 template <typename T, int MODE, bool RECOMP>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
 fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<const T> out5,
                     const float* __restrict__ tv, long long* __restrict__ acc, int N, Geom g,
                     const ScatterHdr* __restrict__ hdr, int count_bits) {
-    TileIdx ti = tile_index(g.H, g.W);
-    if (!ti.valid) return;
+    __shared__ int win[3 * SW_PLANE];
+    __shared__ int s_org[2];
+    const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);
-    const int p = ti.y * g.W + ti.x;
     const long long npx = (long long)g.H * g.W;
+    sw_clear(win);
     long long* a0 = acc + (long long)ti.b * 6 * npx;
-    float f[4] = {0.f, 0.f, 0.f, 0.f};
-    if (RECOMP) {
-        const T* F = flows4.p + ti.b * flows4.sb + p;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = lds_(F + k * flows4.sc);
-    }
+    const int fsc = (int)flows4.sc, ysc = (int)out5.sc;
     for (int n = 0; n < N; ++n) {
-        float xs[4];
-        if (RECOMP) {
-            est_flows<T>(__ldg(tv + ti.b * N + n), f, xs);
-        } else {
-            const T* X = flows4.p + ti.b * flows4.sb + n * flows4.sn + p;
+        const float tt = __ldg(tv + ti.b * N + n);
+        const T* X = flows4.p + ti.b * flows4.sb + (RECOMP ? 0 : n * flows4.sn);
+        const T* Y = out5.p + ti.b * out5.sb + n * out5.sn;
+        const float* st = stage + ((long long)(ti.b * N + n) * 6) * npx;
+        for (int frame = 0; frame < 2; ++frame) {
+            sw_phase(win, s_org, ti, g, scale, a0 + frame * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
+                const int p = y * g.W + x;
+                float xs[4];
+                if (RECOMP) {
+                    const float f[4] = {ldg_(X + p), ldg_(X + fsc + p), ldg_(X + 2 * fsc + p), ldg_(X + 3 * fsc + p)};
+                    est_flows<T>(tt, f, xs);
+                } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) xs[k] = lds_(X + k * flows4.sc);
-        }
-        const T* Y = out5.p + ti.b * out5.sb + n * out5.sn + p;
-        const float f1x = __fadd_rn(xs[0], lds_(Y + out5.sc));
-        const float f1y = __fadd_rn(xs[1], lds_(Y + 2 * out5.sc));
-        const float f0x = __fadd_rn(xs[2], lds_(Y + 3 * out5.sc));
-        const float f0y = __fadd_rn(xs[3], lds_(Y + 4 * out5.sc));
-        const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
-        const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
-        const float* st = stage + ((long long)(ti.b * N + n) * 6) * npx + p;
+                    for (int k = 0; k < 4; ++k) xs[k] = ldg_(X + k * fsc + p);
+                }
+                // xs: F_t1.x, F_t1.y, F_t0.x, F_t0.y; out5 channels 1:3 refine F_t1, 3:5 refine F_t0 (:412-413)
+                const int o = frame ? 0 : 2;
+                const float fx = __fadd_rn(xs[o], ldg_(Y + (1 + o) * ysc + p));
+                const float fy = __fadd_rn(xs[o + 1], ldg_(Y + (2 + o) * ysc + p));
+                t = make_taps<MODE>(x, y, fx, fy, g);
+                const float* sp = st + (frame ? 3 : 0) * npx + p;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            scatter_quad(a0 + c * npx, t0, g.W, __ldcs(st + c * npx), scale);
-            scatter_quad(a0 + (3 + c) * npx, t1, g.W, __ldcs(st + (3 + c) * npx), scale);
+                for (int c = 0; c < 3; ++c) gv[c] = __ldcs(sp + c * npx);
+            });
         }
     }
 }

@@ -8,6 +8,7 @@ except t, which is what autograd derives for the reference.
 All functions require CUDA tensors; nothing here computes on the CPU.
 """
 import ctypes
+import os
 
 import torch
 
@@ -74,15 +75,51 @@ def _no_grad_for_out(out, what, *inputs):
         raise RuntimeError("%s: out= is for inference; it cannot be combined with inputs that require grad" % what)
 
 
+# How a DEVICE-side t is range-checked (the reference asserts 0 < t < 1, scripts/utils/validators.py:9-11; a host-side
+# t is always checked).  Reading a device tensor would synchronise every call, so the default is "off"; "flag" counts
+# violations in a device counter (one tiny kernel per call, read with t_violations() whenever the caller synchronises
+# anyway); "assert" uses torch._assert_async (a violation traps the kernel: for debugging).  SSM_B200_CHECK_T=flag|assert.
+_T_CHECK = os.environ.get("SSM_B200_CHECK_T", "off")
+_t_violations = {}
+
+
+def set_device_t_check(mode):
+    """mode: "off" | "flag" | "assert".  Returns the previous mode."""
+    global _T_CHECK
+    if mode not in ("off", "flag", "assert"):
+        raise ValueError("set_device_t_check: mode must be off, flag or assert")
+    previous, _T_CHECK = _T_CHECK, mode
+    return previous
+
+
+def t_violations(device=None, reset=True):
+    """number of device-side t values outside (0, 1) seen since the last reset (synchronises)"""
+    total = 0
+    for dev, counter in list(_t_violations.items()):
+        if device is None or torch.device(device) == dev:
+            total += int(counter.item())
+            if reset:
+                counter.zero_()
+    return total
+
+
 def _t_vector(t, count, device):
     """t as `count` contiguous fp32 values on `device` (t is never differentiated)."""
     t = torch.as_tensor(t).detach()
     if not t.is_cuda and t.numel() > 0:
-        # the reference asserts 0 < t < 1 (scripts/utils/validators.py:9-11); a host-side t is checked
-        # here, a device-side t is not (that would force a synchronisation on every call)
+        # the reference asserts 0 < t < 1 (scripts/utils/validators.py:9-11); a host-side t is checked here
         lo, hi = float(t.min()), float(t.max())
         if not (0.0 < lo and hi < 1.0):
             raise AssertionError("t must satisfy 0 < t < 1 (got values in [%g, %g])" % (lo, hi))
+    elif t.is_cuda and t.numel() > 0 and _T_CHECK != "off" and not torch.cuda.is_current_stream_capturing():
+        inside = (t > 0) & (t < 1)
+        if _T_CHECK == "assert":
+            torch._assert_async(inside.all(), "t must satisfy 0 < t < 1")
+        else:
+            counter = _t_violations.get(t.device)
+            if counter is None:
+                counter = _t_violations[t.device] = torch.zeros((), dtype=torch.int64, device=t.device)
+            counter += (~inside).sum()
     t = t.to(device=device, dtype=torch.float32).reshape(-1)
     if t.numel() == 1 and count > 1:
         t = t.expand(count)
@@ -103,29 +140,39 @@ class _Warp(torch.autograd.Function):
     """layers.warp(x, flo) -- reference scripts/models/layers.py:73-120"""
 
     @staticmethod
-    def forward(ctx, x, flo, mode):
+    def forward(ctx, x, flo, mode, packed):
         _same(x, flo)
         x, flo = _abi.dense_planes(x), _abi.dense_planes(flo)
         B, C, H, W = x.shape
         if flo.shape != (B, 2, H, W):
             raise RuntimeError("warp: flo must be B x 2 x H x W, got %s for x %s" % (tuple(flo.shape), tuple(x.shape)))
+        if packed is not None and (C != 3 or packed.shape != (B, H, W, 4) or packed.dtype != x.dtype
+                                   or packed.device != x.device or not packed.is_contiguous()):
+            raise RuntimeError("warp: packed= must be the contiguous %s %s RGBx copy of a 3-channel x (pack_image)"
+                               % ((B, H, W, 4), x.dtype))
         out = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device)
+        L = _abi.lib()
         with torch.cuda.device(x.device):
-            rc = _abi.lib().ssm_warp_fwd(_abi.ref(_abi.desc(x, False)), _abi.ref(_abi.desc(flo, False)),
-                                         _abi.ref(_abi.desc(out, False)), B, C, H, W, _abi.dtype_code(x), mode,
-                                         _abi.stream_ptr(x.device))
+            if packed is not None:
+                rc = L.ssm_warp_fwd_packed(ctypes.c_void_p(packed.data_ptr()), _abi.ref(_abi.desc(flo, False)),
+                                           _abi.ref(_abi.desc(out, False)), B, H, W, _abi.dtype_code(x), mode,
+                                           _abi.stream_ptr(x.device))
+            else:
+                rc = L.ssm_warp_fwd(_abi.ref(_abi.desc(x, False)), _abi.ref(_abi.desc(flo, False)),
+                                    _abi.ref(_abi.desc(out, False)), B, C, H, W, _abi.dtype_code(x), mode,
+                                    _abi.stream_ptr(x.device))
         _abi.check(rc, "ssm_warp_fwd")
-        ctx.save_for_backward(x, flo)
+        ctx.save_for_backward(x, flo, packed)
         ctx.mode = mode
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, flo = ctx.saved_tensors
+        x, flo, packed = ctx.saved_tensors
         B, C, H, W = x.shape
         need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_x or need_f):
-            return None, None, None
+            return None, None, None, None
         gout = _abi.dense_planes(gout.to(x.dtype))
         gx = torch.empty_like(x, memory_format=torch.contiguous_format) if need_x else None
         gf = torch.empty_like(flo, memory_format=torch.contiguous_format) if need_f else None
@@ -136,17 +183,41 @@ class _Warp(torch.autograd.Function):
             ws = _workspace(ws_bytes, x.device)
             ws_ptr = ctypes.c_void_p(ws.data_ptr())
         with torch.cuda.device(x.device):
-            rc = L.ssm_warp_bwd(_abi.ref(_abi.desc(gout, False)), _abi.ref(_abi.desc(x, False)),
-                                _abi.ref(_abi.desc(flo, False)), _abi.ref(_abi.desc(gx, False)),
-                                _abi.ref(_abi.desc(gf, False)), B, C, H, W, _abi.dtype_code(x), ctx.mode,
-                                ws_ptr, ws_bytes, _abi.stream_ptr(x.device))
+            if packed is not None:
+                rc = L.ssm_warp_bwd_packed(_abi.ref(_abi.desc(gout, False)), ctypes.c_void_p(packed.data_ptr()),
+                                           _abi.ref(_abi.desc(flo, False)), _abi.ref(_abi.desc(gx, False)),
+                                           _abi.ref(_abi.desc(gf, False)), B, H, W, _abi.dtype_code(x), ctx.mode,
+                                           ws_ptr, ws_bytes, _abi.stream_ptr(x.device))
+            else:
+                rc = L.ssm_warp_bwd(_abi.ref(_abi.desc(gout, False)), _abi.ref(_abi.desc(x, False)),
+                                    _abi.ref(_abi.desc(flo, False)), _abi.ref(_abi.desc(gx, False)),
+                                    _abi.ref(_abi.desc(gf, False)), B, C, H, W, _abi.dtype_code(x), ctx.mode,
+                                    ws_ptr, ws_bytes, _abi.stream_ptr(x.device))
         _abi.check(rc, "ssm_warp_bwd")
-        return gx, gf, None
+        return gx, gf, None, None
 
 
-def warp(x, flo, coord_mode=None):
-    """Backward-warp image x (B x C x H x W) by flow flo (B x 2 x H x W; channel 0 horizontal)."""
-    return _Warp.apply(x, flo, _resolve_mode(coord_mode))
+def warp(x, flo, coord_mode=None, packed=None):
+    """Backward-warp image x (B x C x H x W) by flow flo (B x 2 x H x W; channel 0 horizontal).  packed: the RGBx
+    copy of a 3-channel x (pack_image), for callers that warp the same image by several flows: one 16-byte gather
+    per bilinear tap instead of three 4-byte ones; gradients still flow to x."""
+    return _Warp.apply(x, flo, _resolve_mode(coord_mode), packed)
+
+
+def pack_image(x, out=None):
+    """RGBx re-layout of B x 3 x H x W images (ssm_pack_image) -> B x H x W x 4, for warp(..., packed=).  Not
+    differentiable (a staging copy; the gradient of warp reaches x itself)."""
+    _same(x)
+    x = _abi.dense_planes(x.detach())
+    B, C, H, W = x.shape
+    if C != 3:
+        raise RuntimeError("pack_image: expected B x 3 x H x W, got %s" % (tuple(x.shape),))
+    packed = _out_buffer(out, (B, H, W, 4), x, "pack_image")
+    with torch.cuda.device(x.device):
+        rc = _abi.lib().ssm_pack_image(_abi.ref(_abi.desc(x, False)), ctypes.c_void_p(packed.data_ptr()),
+                                       B, H, W, _abi.dtype_code(x), _abi.stream_ptr(x.device))
+    _abi.check(rc, "ssm_pack_image")
+    return packed
 
 
 # ---------------------------------------------------------------------------------------------

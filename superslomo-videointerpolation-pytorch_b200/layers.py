@@ -10,11 +10,12 @@ import torch.nn as nn
 from . import functional as F_ssm
 
 
-def warp(x, flo):
+def warp(x, flo, packed=None):
     """Backward warp of x (B x C x H x W) by flow flo (B x 2 x H x W), bilinear, zeros outside,
     corners aligned -- same results as reference layers.warp (layers.py:73-120), differentiable
-    in x and flo.  CUDA tensors only."""
-    return F_ssm.warp(x, flo)
+    in x and flo.  CUDA tensors only.  packed: optional RGBx copy of a 3-channel x (ssm_b200.pack_image) shared by
+    several warps of the same image."""
+    return F_ssm.warp(x, flo, packed=packed)
 
 
 def conv(in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1):

@@ -125,22 +125,20 @@ def test_frames_host_helpers():
         ssm_b200.frames_from_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))     # CPU tensor: refused
 
 
-def test_sliding_window_matches_reference_rule():
-    """visualize_interpolation.py:270-288: windows of n_frames indices centred on each adjacent pair,
-    clamped at the ends; the 240-fps mode keeps every 8th image."""
+def test_sliding_window_matches_reference_fixture():
+    """formats.sliding_window against the windows the reference's own Interpolator.sliding_window
+    (scripts/visualize_interpolation.py:270-288) produced for 48 (n_images, n_frames, 240-fps) combinations
+    (tests/golden/sliding_window.json, written by tests/golden/make_golden_large.py from the imported reference)."""
+    import json
+    import os
     from ssm_b200 import formats
-
-    def reference_rule(n_images, n_frames, fps240):
-        paths = list(range(n_images))[::8] if fps240 else list(range(n_images))
-        out = []
-        for s, e in zip(range(len(paths))[:-1], range(len(paths))[1:]):
-            left, right = s - ((n_frames - 1) // 2), e + ((n_frames - 1) // 2)
-            locs = [min(max(i, 0), len(paths) - 1) for i in range(left, right + 1)]
-            out.append([paths[i] for i in locs])
-        return out
-
-    for n_images, n_frames, fps in [(5, 2, False), (5, 4, False), (3, 6, False), (20, 4, True), (2, 2, False), (1, 2, False)]:
-        assert list(formats.sliding_window(n_images, n_frames, 8 if fps else 1)) == reference_rule(n_images, n_frames, fps)
+    from util import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "sliding_window.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 48
+    for c in cases:
+        got = list(formats.sliding_window(c["n_images"], c["n_frames"], 8 if c["is_fps_240"] else 1))
+        assert got == c["windows"], (c["n_images"], c["n_frames"], c["is_fps_240"])
     assert list(formats.sliding_window(4, 4)) == [[0, 0, 1, 2], [0, 1, 2, 3], [1, 2, 3, 3]]
     assert formats.output_name("d", 7) == "d/img_00007.png"
 
@@ -343,3 +341,75 @@ def test_perceptual_term_is_never_dropped_silently():
     assert any("DROPPED" in str(x.message) for x in w)
     rnd = SSMLosses(perceptual_features="random")
     assert len(rnd.perceptual_features) == 23 and not any(p.requires_grad for p in rnd.perceptual_features.parameters())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/scripts"), reason="needs the reference tree (build container only)")
+def test_patch_reference_rebinds_the_reference_modules():
+    """ssm_b200.patch_reference on the REAL reference modules: the six rebindings INTEGRATION.md section 1 promises
+    (three methods of FlowInterpolationModel, `warp` in flow_interpolation / layers / losses), idempotence, and that CPU
+    tensors still reach the reference's own functions bit for bit (the patched names route by device)."""
+    import importlib
+    import sys
+    import ssm_b200
+    from ssm_b200 import synthetic
+    sys.path.insert(0, "/root/reference/scripts")
+    saved = {k: sys.modules.get(k) for k in ("models", "models.flow_interpolation", "models.layers", "models.losses")}
+    try:
+        fi = importlib.import_module("models.flow_interpolation")
+        layers = importlib.import_module("models.layers")
+        try:
+            losses = importlib.import_module("models.losses")
+        except Exception:                      # torchvision / VGG import problems are not what this test is about
+            losses = None
+        cls = fi.FlowInterpolationModel
+        originals = {n: getattr(cls, n) for n in ("compute_inputs", "extract_outputs", "compute_output_image")}
+        ref_warp = layers.warp
+        assert fi.warp is ref_warp
+        ssm_b200.patch_reference(fi, layers, losses)
+        rebound = 0
+        for n, orig in originals.items():
+            assert getattr(cls, n) is not orig and getattr(getattr(cls, n), "_ssm_b200", False), n
+            assert getattr(cls, "_ssm_ref_" + n) is orig
+            rebound += 1
+        for mod in (fi, layers, losses):
+            if mod is None:
+                continue
+            assert mod.warp is not ref_warp and mod.warp._ssm_b200 and mod.warp._ssm_ref is ref_warp
+            rebound += 1
+        assert rebound == (6 if losses is not None else 5)
+        for n in ("compute_inputs_batched", "compute_output_image_batched", "compute_output_image_from_flow"):
+            assert hasattr(cls, n)
+        before = {n: getattr(cls, n) for n in originals}
+        ssm_b200.patch_reference(fi, layers, losses)                  # idempotent: no wrapper around a wrapper
+        assert all(getattr(cls, n) is before[n] for n in originals) and layers.warp._ssm_ref is ref_warp
+
+        # CPU tensors: the reference's own code path, unchanged
+        class Bare:
+            verbose = False
+        bare = Bare()
+        img6 = synthetic.frames(1, 16, 24, seed=11)
+        flow4 = synthetic.flows(1, 16, 24, 4, flow_px=3.0, seed=12)
+        out5 = synthetic.unet_out5(1, 1, 16, 24, seed=13)[:, 0].contiguous()
+        t = torch.tensor([0.25]).view(1, 1, 1, 1)
+        bare.extract_outputs = lambda y: cls.extract_outputs(bare, y)
+        want16 = originals["compute_inputs"](bare, img6, flow4, t)
+        assert torch.equal(cls.compute_inputs(bare, img6, flow4, t), want16)
+        want3 = originals["compute_output_image"](bare, img6, want16, out5, t)
+        assert torch.equal(cls.compute_output_image(bare, img6, want16, out5, t), want3)
+        assert torch.equal(layers.warp(img6[:, :3], flow4[:, :2]), ref_warp(img6[:, :3], flow4[:, :2]))
+    finally:
+        for k in ("models.flow_interpolation", "models.layers", "models.losses", "models"):
+            if saved[k] is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = saved[k]
+        sys.path.remove("/root/reference/scripts")
+
+
+def test_device_t_check_modes():
+    import ssm_b200
+    assert ssm_b200.set_device_t_check("flag") in ("off", "flag", "assert")
+    assert ssm_b200.set_device_t_check("off") == "flag"
+    with pytest.raises(ValueError):
+        ssm_b200.set_device_t_check("sometimes")
+    assert ssm_b200.t_violations() == 0

@@ -40,6 +40,25 @@ def test_c_oracle_matches_reference(name):
     assert_close_fp32(gy, d["fuse_gout5"], "compute_output_image grad out5")
 
 
+def test_c_oracle_matches_reference_large_flows():
+    """352 x 352 with flows of up to 82 px (tests/golden/make_golden_large.py): the C restatement against the
+    reference's own outputs and autograd gradients on the stored band of rows."""
+    from util import load_large_golden
+    d = load_large_golden()
+    assert d["flow_absmax"].item() > 60.0
+    rows = d["rows"]
+    in16 = c_oracle.compute_inputs(d["img6"], d["flow4"], d["t"])
+    warped = torch.cat([in16[:, 3:6], in16[:, 10:13]], 1)[:, :, rows]
+    assert_close_fp32(warped, d["in16_warped"], "compute_inputs warped images, large flows")
+    _, gf = c_oracle.compute_inputs_backward(d["g16"], d["img6"], d["flow4"], d["t"])
+    assert_close_fp32(gf[:, :, rows], d["pack_gflow"], "compute_inputs grad flow, large flows")
+    frame = c_oracle.compute_output_image(d["img6"], in16, d["out5"], d["t"])
+    assert_close_fp32(frame[:, :, rows], d["frame"], "compute_output_image, large flows")
+    _, gx, gy = c_oracle.compute_output_image_backward(d["g3"], d["img6"], in16, d["out5"], d["t"])
+    assert_close_fp32(gx[:, 6:10, rows], d["fuse_gflows"], "compute_output_image grad in16[6:10], large flows")
+    assert_close_fp32(gy[:, :, rows], d["fuse_gout5"], "compute_output_image grad out5, large flows")
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_torch_oracle_matches_reference(name):
     """The torch restatement issues the reference's torch ops: same bits on the same torch build."""

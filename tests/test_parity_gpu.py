@@ -639,3 +639,137 @@ def test_constant_divisor_division_is_ieee_exact(size):
           % (size, bad_n, bad_q, example))
     assert bad_n == 0, "%d coordinate mismatches for size %d" % (bad_n, size)
     assert bad_q <= 2 ** 25, "raw quotient mismatches beyond the denormal range for size %d" % size
+
+
+# ---------------------------------------------------------------------------------------------
+def test_large_flow_reference_fixture():
+    """352 x 352 with flows of up to 82 px: the CUDA path against outputs and autograd gradients of the reference itself
+    (tests/golden/make_golden_large.py), 1e-5, on the stored band of rows -- fp32 frames (RGBx gathers) and the 8-bit-frame
+    kernels (the fixture's frames are uint8 images normalised with the reference's expression)."""
+    from ssm_b200 import q8
+    from util import load_large_golden
+    d = load_large_golden()
+    rows = d["rows"]
+    B = d["img6"].shape[0]
+    t = d["t"].view(B, 1)
+    a, f = _dev(d["img6"]), _dev(d["flow4"], True)
+    in16 = ssm_b200.flow_pack(a, f, _dev(t), n_timesteps=1)
+    in16.backward(_dev(d["g16"]).unsqueeze(1))
+    warped = torch.cat([in16[:, 0, 3:6], in16[:, 0, 10:13]], 1)[:, :, rows]
+    assert_close_fp32(warped, d["in16_warped"], "compute_inputs warped images, large flows")
+    assert_close_fp32(f.grad[:, :, rows], d["pack_gflow"], "compute_inputs grad flow, large flows")
+    xin, yo = _dev(in16.detach()[:, 0], True), _dev(d["out5"], True)
+    frame = ssm_b200.SynthesisMixin().compute_output_image(a, xin, yo, _dev(t.view(B, 1, 1, 1)))
+    frame.backward(_dev(d["g3"]))
+    assert_close_fp32(frame[:, :, rows], d["frame"], "compute_output_image, large flows")
+    assert_close_fp32(xin.grad[:, 6:10, rows], d["fuse_gflows"], "compute_output_image grad in16[6:10], large flows")
+    assert_close_fp32(yo.grad[:, :, rows], d["fuse_gout5"], "compute_output_image grad out5, large flows")
+    # the 8-bit-frame kernels on the same uint8 images
+    planar, quads, norm, _ = q8.prepare(d["u8"].to(DEV), order="rgb", lut=ssm_b200.normalisation_lut(device="cpu"))
+    H, W = planar.shape[-2:]
+    img6_q = planar.view(B, 6, H, W)
+    assert torch.equal(img6_q.cpu(), d["img6"]), "normalised frames are not bit-identical to the reference's"
+    in16_q = q8.flow_pack(img6_q, quads, _dev(d["flow4"]), _dev(t), norm, n_timesteps=1)
+    warped_q = torch.cat([in16_q[:, 0, 3:6], in16_q[:, 0, 10:13]], 1)[:, :, rows]
+    assert_close_fp32(warped_q, d["in16_warped"], "compute_inputs from uint8 frames, large flows")
+    frame_q = q8.fuse_from_flow(quads, _dev(d["flow4"]), _dev(d["out5"]).unsqueeze(1), _dev(t), norm)
+    assert_close_fp32(frame_q[:, 0, :, rows], d["frame"], "compute_output_image from uint8 frames, large flows")
+
+
+def test_patch_reference_on_a_reference_style_module():
+    """patch_reference as INTEGRATION.md section 1 uses it, on a stand-in for the reference's `models` modules (the
+    reference tree does not travel to the GPU box): a FlowInterpolationModel class whose three methods and whose
+    module-level warp are the reference's op sequence (oracle/torch_oracle.py).  After patching, CUDA tensors run the
+    B200 path and reproduce the reference's golden outputs and gradients; CPU tensors still reach the stand-in's own code."""
+    import types
+
+    class FlowInterpolationModel:
+        verbose = False
+
+        def compute_inputs(self, img_tensor, flow_pred_tensor, t):
+            return torch_oracle.compute_inputs(img_tensor, flow_pred_tensor, t)
+
+        def extract_outputs(self, output_tensor):
+            return torch_oracle.extract_outputs(output_tensor)
+
+        def compute_output_image(self, img_tensor, input_tensor, output_tensor, t):
+            return torch_oracle.compute_output_image(img_tensor, input_tensor, output_tensor, t)
+
+    fi = types.SimpleNamespace(FlowInterpolationModel=FlowInterpolationModel, warp=torch_oracle.warp)
+    layers = types.SimpleNamespace(warp=torch_oracle.warp)
+    losses = types.SimpleNamespace(warp=torch_oracle.warp)
+    ssm_b200.patch_reference(fi, layers, losses)
+    model = fi.FlowInterpolationModel()
+    for name in ("small_smooth", "border"):
+        d = load_golden(name)
+        B = d["img6"].shape[0]
+        t = d["t"].view(B, 1, 1, 1)
+        a, b = _dev(d["img6"], True), _dev(d["flow4"], True)
+        in16 = model.compute_inputs(a, b, _dev(t))
+        in16.backward(_dev(d["pack_g16"]))
+        assert_close_fp32(in16, d["in16"], "patched compute_inputs")
+        assert_close_fp32(b.grad, d["pack_gflow"], "patched compute_inputs grad flow")
+        xin, yo = _dev(d["in16"], True), _dev(d["out5"], True)
+        frame = model.compute_output_image(_dev(d["img6"]), xin, yo, _dev(t))
+        frame.backward(_dev(d["fuse_g3"]))
+        assert_close_fp32(frame, d["frame"], "patched compute_output_image")
+        assert_close_fp32(yo.grad, d["fuse_gout5"], "patched compute_output_image grad out5")
+        v1, df1, df0, v0 = model.extract_outputs(_dev(d["out5"]))
+        assert_close_fp32(v1 + v0, torch.ones_like(v1), "patched extract_outputs")
+        x, f = _dev(d["img6"][:, 0:3], True), _dev(d["flow4"][:, 0:2], True)
+        y = losses.warp(x, f)                                  # losses.py:152-161 calls the module-level name
+        y.backward(_dev(d["warp_gout"]))
+        assert_close_fp32(y, d["warp_out"], "patched losses.warp")
+        assert_close_fp32(x.grad, d["warp_gimg"], "patched losses.warp grad img")
+        assert_close_fp32(f.grad, d["warp_gflow"], "patched losses.warp grad flow")
+        assert torch.equal(layers.warp(d["img6"][:, 0:3], d["flow4"][:, 0:2]), d["warp_out"]), "CPU tensors: the module's own warp"
+        assert torch.equal(model.compute_inputs(d["img6"], d["flow4"], t), d["in16"])
+    # autocast hands over a bf16 U-Net output next to fp32 frames (ADVICE r1): promoted, as the reference's torch ops do
+    d = load_golden("small_smooth")
+    t = _dev(d["t"].view(-1, 1, 1, 1))
+    mixed = model.compute_output_image(_dev(d["img6"]), _dev(d["in16"]), _dev(d["out5"]).bfloat16(), t)
+    want = model.compute_output_image(_dev(d["img6"]), _dev(d["in16"]), _dev(d["out5"]).bfloat16().float(), t)
+    assert mixed.dtype == torch.float32 and torch.equal(mixed, want)
+
+
+def test_device_side_t_is_range_checked_on_request():
+    """validators.py:9-11 asserts 0 < t < 1.  A device-side t is checked without a synchronisation in "flag" mode."""
+    B, N, H, W = 2, 3, 16, 32
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=77)
+    previous = ssm_b200.set_device_t_check("flag")
+    try:
+        ssm_b200.t_violations()
+        ssm_b200.flow_pack(_dev(img6), _dev(flow4), _dev(t), n_timesteps=N)
+        assert ssm_b200.t_violations() == 0
+        bad = t.clone()
+        bad[0, 1], bad[1, 2] = 1.0, -0.25
+        ssm_b200.flow_pack(_dev(img6), _dev(flow4), _dev(bad), n_timesteps=N)
+        assert ssm_b200.t_violations() == 2
+        assert ssm_b200.t_violations() == 0            # reading resets the counter
+    finally:
+        ssm_b200.set_device_t_check(previous)
+    with pytest.raises(AssertionError):                # a host-side t is always checked
+        ssm_b200.flow_pack(_dev(img6), _dev(flow4), bad, n_timesteps=N)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_warp_from_packed_image_is_bit_identical(dtype):
+    """warp(x, flo, packed=pack_image(x)): the RGBx gathers read the same values as the planar ones, so output, flow
+    gradient and (deterministic) image gradient are the same bits; one packed copy serves several warps of an image."""
+    B, H, W = 2, 45, 77
+    img6, flow4, _, _ = _inputs(B, 1, H, W, seed=4100, kind="border")
+    g = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(9)).to(DEV).to(dtype)
+    x1, x2 = _dev(img6[:, 0:3].to(dtype), True), _dev(img6[:, 0:3].to(dtype), True)
+    packed = ssm_b200.pack_image(x2)
+    assert packed.shape == (B, H, W, 4) and torch.equal(packed[..., :3].permute(0, 3, 1, 2), x2.detach())
+    for k in (0, 2):                                  # two different flows, one packed copy
+        f1, f2 = _dev(flow4[:, k:k + 2].to(dtype), True), _dev(flow4[:, k:k + 2].to(dtype), True)
+        y1 = ssm_b200.warp(x1, f1)
+        y2 = ssm_b200.warp(x2, f2, packed=packed)
+        assert torch.equal(y1, y2)
+        x1.grad = x2.grad = None
+        y1.backward(g)
+        y2.backward(g)
+        assert torch.equal(f1.grad, f2.grad) and torch.equal(x1.grad, x2.grad)
+    with pytest.raises(RuntimeError):
+        ssm_b200.warp(x1, _dev(flow4[:, 0:2].to(dtype)), packed=packed[:, :, :, :3].contiguous())

@@ -47,6 +47,26 @@ def seeded_unets(seed, device="cpu", bottleneck="CONV"):
     return s1.to(device), s2.to(device)
 
 
+def load_large_golden(name="large_352_flow100"):
+    """the large-flow fixture (tests/golden/make_golden_large.py): exact fp32 inputs rebuilt from the stored integers
+    with the generator's own expressions, outputs for the stored band of rows"""
+    d = load_golden(name)
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(1, 3, 1, 1)
+    x = (d["u8"].permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    d["img6"] = torch.cat([x[0::2], x[1::2]], dim=1).contiguous()
+    d["flow4"] = d["flow_i16"].float() / 64.0
+    d["out5"] = d["out5_i16"].float() / 1024.0
+    r0, r1 = (int(v) for v in d["band"])
+    B, _, H, W = d["flow4"].shape
+    d["g16"] = torch.zeros((B, 16, H, W))
+    d["g16"][:, 3:13, r0:r1] = d["g16_band_i16"].float() / 256.0
+    d["g3"] = torch.zeros((B, 3, H, W))
+    d["g3"][:, :, r0:r1] = d["g3_band_i16"].float() / 256.0
+    d["rows"] = slice(r0, r1)
+    return d
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
         return {k: torch.from_numpy(z[k]) for k in z.files}

@@ -216,6 +216,10 @@ __device__ __forceinline__ void sts2(__nv_bfloat16* p, float a, float b) {
 // entry tables from uint8 images: F images (H_in x W_in x 3, RGB or BGR bytes) placed at (top, left) of an
 // H x W frame whose other pixels are byte 0 (visualize_interpolation.py:76-87 pads the raw image with 0 and
 // normalises afterwards, :137)  ->  F x (H+1) x (W+1) entries.  One thread builds 4 consecutive entries of a row.
+// 0.35 ms per 32 frames of 1088x1920 (1.2 GB moved).  Tried and measured slower or equal (profiles/r02s-r02v): the rows
+// read as aligned 32-bit words cut up with funnel shifts (10 loads per thread instead of 30: 0.41 ms), one entry per
+// thread with fully coalesced 16-byte stores (0.43 ms; 0.41 with a 2-D grid and no 64-bit divisions), streaming stores
+// (no change).
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_stride, int src_row_stride, int bgr,

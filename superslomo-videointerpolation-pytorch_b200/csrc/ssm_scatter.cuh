@@ -48,7 +48,10 @@ __device__ __forceinline__ void fx_add(long long* dst, float contrib, float scal
 
 // ---- the shared-memory window -----------------------------------------------------------------------------------
 constexpr int SW_TILE_W = 64, SW_TILE_H = 16;             // source pixels per CTA: 256 threads x 4 rows
-constexpr int SW_HALO = 8;
+#ifndef SSM_SW_HALO
+#define SSM_SW_HALO 8
+#endif
+constexpr int SW_HALO = SSM_SW_HALO;
 constexpr int SW_W = SW_TILE_W + 2 * SW_HALO, SW_H = SW_TILE_H + 2 * SW_HALO, SW_PLANE = SW_W * SW_H;   // 80 x 32 cells
 constexpr int SW_THREADS = 256;
 #ifndef SSM_SW_MIN_BLOCKS

@@ -12,7 +12,8 @@
                   are the unit that shards).
   C5  configs[4]  one 2176x3840 (4K padded to /32) pair x 31 intermediate times (t = k/32,
                   scripts/evaluate_interpolation_results.py:52, 204-211) split 4/4/4/4/4/4/4/3 over the ranks
-                  (sharding.shard_work), INCLUDING the NCCL broadcast of the pair and its stage-1 flows from rank 0.
+                  (sharding.shard_work), INCLUDING the NCCL broadcast of the pair (two 8-bit images) and its stage-1 flows
+                  from rank 0; every rank then runs the 8-bit-frame kernels on its timesteps.
 
 The two flow U-Nets are stock torch/cuDNN modules with random-init weights (out of scope); the
 timed work of C5 is the path alone (stage-2 output = seeded surrogate, as in the headline).  Every number is
@@ -206,23 +207,29 @@ def c4_ssmr_windows(world, rank, dev, steps=2, warmup=1, H=1088, W=1920, n_frame
 
 
 # ---------------------------------------------------------------------------------------------
-def c5_4k_sharded(world, rank, dev, steps=5, warmup=3, H=2176, W=3840, n_t=31, peak_gbs=None):
+def c5_4k_sharded(world, rank, dev, steps=5, warmup=3, H_in=2160, W_in=3840, n_t=31, peak_gbs=None):
     import ssm_b200
-    from ssm_b200 import sharding, synthetic
+    from ssm_b200 import q8, sharding, synthetic
+    H, W = (H_in + 31) // 32 * 32, (W_in + 31) // 32 * 32          # 2176 x 3840 (evaluate_interpolation_results.py:89-90)
     work = sharding.shard_work(1, n_t, rank, world)
     assert len(work) == 1
     _, t0, t1 = work[0]
     n = t1 - t0
+    # the pair lives on rank 0 as the two 8-bit images a video decoder delivers, next to its stage-1 flows
     if rank == 0:
-        img6 = synthetic.frames(1, H, W, seed=500, device=dev)
+        x = synthetic.frames(2, H_in, W_in, n_frames=1, seed=500, smooth=True, device=dev)
+        x = (x - x.amin()) / (x.amax() - x.amin())
+        images = (x.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous()
+        del x
         flow4 = synthetic.flows(1, H, W, 4, flow_px=20.0, seed=501, device=dev)
     else:
-        img6 = torch.empty((1, 6, H, W), device=dev)
+        images = torch.empty((2, H_in, W_in, 3), dtype=torch.uint8, device=dev)
         flow4 = torch.empty((1, 4, H, W), device=dev)
+    lut = ssm_b200.normalisation_lut(device=dev)
+    pads = lut[:, 0].tolist()
     t_all = synthetic.timesteps(1, n_t, device=dev)
     t = t_all[:, t0:t1].contiguous()
     out5 = synthetic.unet_out5(1, n, H, W, seed=502 + rank, device=dev)
-    rgbx = torch.empty((1, 2, H, W, 4), device=dev)
     in16 = torch.empty((1, n, 16, H, W), device=dev)
     frames = torch.empty((1, n, 3, H, W), device=dev)
     ev = []
@@ -231,13 +238,14 @@ def c5_4k_sharded(world, rank, dev, steps=5, warmup=3, H=2176, W=3840, n_t=31, p
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         if world > 1:                         # the pair and its stage-1 flows live on rank 0
-            dist.broadcast(img6, src=0)
+            dist.broadcast(images, src=0)
             dist.broadcast(flow4, src=0)
         e[1].record()
         with torch.no_grad():
-            ssm_b200.pack_frames(img6, out=rgbx)
-            ssm_b200.flow_pack(img6, flow4, t, n_timesteps=n, packed=rgbx, out=in16)
-            ssm_b200.fuse_from_flow(img6, flow4, out5, t, packed=rgbx, out=frames)
+            planar, quads, norm, _ = q8.prepare(images, order="rgb", lut=lut, pad_values=pads)
+            img6 = planar.view(1, 6, H, W)
+            q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=n, out=in16)
+            q8.fuse_from_flow(quads, flow4, out5, t, norm, out=frames)
         e[2].record()
         ev.append(e)
 
@@ -250,19 +258,20 @@ def c5_4k_sharded(world, rank, dev, steps=5, warmup=3, H=2176, W=3840, n_t=31, p
     npx = H * W
     nbytes = ((10 + 16 * n) + (10 + 8 * n)) * 4 * npx          # this rank's algorithmic bytes
     res = {
-        "what": "one %dx%d pair x %d intermediate times (t = k/32), (pair, timestep) work split over the ranks; fp32; "
-                "step = NCCL broadcast of the pair (6 planes) and its stage-1 flows (4 planes) from rank 0 + RGBx staging "
-                "+ compute_inputs + compute_output_image for this rank's timesteps" % (H, W, n_t),
+        "what": "one %dx%d pair (two 8-bit %dx%d images) x %d intermediate times (t = k/32), (pair, timestep) work split over "
+                "the ranks; fp32 tensors; step = NCCL broadcast of the two uint8 images and the stage-1 flows (4 fp32 planes) from "
+                "rank 0 + frame normalisation and entry tables + compute_inputs + compute_output_image for this rank's "
+                "timesteps" % (H, W, H_in, W_in, n_t),
         "parallelism": "timesteps of the single pair split %s, one NCCL broadcast per step" % "/".join(
             str(sharding.frames_of(sharding.shard_work(1, n_t, r, world))) for r in range(world)),
         "scaling": "strong", "n_gpus": world, "timesteps_this_rank": n,
         "ms_per_step": ms, "frames_per_s": n_t / (ms * 1e-3),
-        "broadcast_ms": bcast, "broadcast_bytes": 10 * 4 * npx if world > 1 else 0, "path_kernels_ms": kern,
+        "broadcast_ms": bcast, "broadcast_bytes": (images.numel() + 4 * 4 * npx) if world > 1 else 0, "path_kernels_ms": kern,
         "rank0_path_algorithmic_gbs": nbytes / (kern * 1e-3) / 1e9,
     }
     if peak_gbs:
         res["rank0_path_frac_of_peak"] = res["rank0_path_algorithmic_gbs"] / peak_gbs
-    del img6, flow4, out5, rgbx, in16, frames
+    del images, flow4, out5, in16, frames
     torch.cuda.empty_cache()
     return res
 

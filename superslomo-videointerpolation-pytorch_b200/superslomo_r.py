@@ -176,3 +176,69 @@ class FullModel(nn.Module, SynthesisMixin):
             out5 = out5.view(B, n, 5, *in16.shape[-2:])
             frames.append(F_ssm.fuse_from_flow(pairs[:, mid], flows[:, mid], out5, tn, packed=rgbx[mid]))
         return torch.cat(frames, dim=1)
+
+    @torch.no_grad()
+    def interpolate_u8(self, images_u8, t_values, order="bgr", unet_chunk=None, as_u8=True, saturate=True):
+        """`interpolate` for frames that arrive as 8-bit images, which is how the reference gets them
+        (visualize_interpolation.py:61-88 reads them with cv2): images_u8 B x T x H_in x W_in x 3 uint8 on the GPU,
+        t_values N times in (0,1) -> the N intermediate frames of the middle window, as B x N x H_in x W_in x 3 uint8
+        images in the same channel order (as_u8; de-normalised and cropped as visualize_interpolation.py:221-232,
+        264-268) or as B x N x 3 x H x W normalised fp32 frames of the padded size.
+
+        The frames are normalised and padded to a multiple of 32 on the GPU (ssm_frames_from_u8: bit-identical to the
+        reference's expression) for the U-Nets and the pass-through channels; the warps of compute_inputs and
+        compute_output_image gather from 2 x 2 tables of the raw bytes (ssm_quads_from_u8, one 16-byte request per
+        bilinear sample), and the fused frame is written straight as uint8 (ssm_fuse_flow_fwd_q8_u8)."""
+        from . import q8
+        if images_u8.dim() != 5 or images_u8.shape[-1] != 3 or images_u8.dtype != torch.uint8 or not images_u8.is_cuda:
+            raise RuntimeError("interpolate_u8: expected a CUDA uint8 tensor B x T x H x W x 3, got %s %s"
+                               % (tuple(images_u8.shape), images_u8.dtype))
+        B, T, H_in, W_in, _ = images_u8.shape
+        lut = q8.normalisation_lut(device=images_u8.device)
+        flat = images_u8.reshape(B * T, H_in, W_in, 3)
+        planar, _, (top, left) = q8.frames_from_u8(flat, order=order, pad_mode="before", lut=lut)
+        H, W = planar.shape[-2:]
+        norm = q8.norm6()
+        pairs = self.get_image_pairs(planar.view(B, T, 3, H, W))
+        Wn = T - 1
+        mid = Wn // 2
+        t_values = torch.as_tensor(t_values, dtype=torch.float32, device=images_u8.device).reshape(-1)
+        N = t_values.numel()
+        flows, encs = self._stage1(pairs)
+        t_bn = t_values.view(1, N).expand(B, N).contiguous()
+        step = N if unet_chunk is None else max(1, int(unet_chunk))
+        # entry tables of the two frames of every window (for T = 2 the images are already laid out pair by pair)
+        quads = [q8.quads_from_u8(images_u8[:, w:w + 2].reshape(B * 2, H_in, W_in, 3).contiguous(), order=order)[0]
+                 for w in range(Wn)]
+        nhwc_dtype = None
+        if self.unet_layouts and Wn == 1 and getattr(self.stage2_model, "channels_last", False):
+            nhwc_dtype = torch.float32
+            if torch.is_autocast_enabled("cuda"):
+                nhwc_dtype = torch.bfloat16 if torch.get_autocast_dtype("cuda") == torch.bfloat16 else None
+        out = []
+        for n0 in range(0, N, step):
+            tn = t_bn[:, n0:n0 + step].contiguous()
+            n = tn.shape[1]
+            if nhwc_dtype is not None:
+                in16 = q8.flow_pack(pairs[:, 0], quads[0], flows[:, 0], tn, norm, n_timesteps=n,
+                                    channels_last_dtype=nhwc_dtype).unsqueeze(1)
+            elif Wn > 1:
+                in16 = torch.stack([q8.flow_pack(pairs[:, w], quads[w], flows[:, w], tn, norm, n_timesteps=n)
+                                    for w in range(Wn)], dim=1)
+            else:
+                in16 = q8.flow_pack(pairs[:, 0], quads[0], flows[:, 0], tn, norm, n_timesteps=n).unsqueeze(1)
+            x = in16.permute(0, 2, 1, 3, 4, 5).reshape(B * n, Wn, 16, H, W)
+            e = None
+            if encs[0] is not None:
+                e = [enc.repeat_interleave(n, dim=0) for enc in encs]
+            out5 = self.stage2_model(x, e)[mid]
+            if out5.dtype != torch.bfloat16:
+                out5 = out5.float()
+            out5 = out5.view(B, n, 5, H, W)
+            if as_u8:
+                out.append(q8.fuse_from_flow_to_u8(quads[mid], flows[:, mid], out5, tn, norm, crop=(top, left, H_in, W_in),
+                                                   order=order, saturate=saturate))
+            else:
+                out.append(q8.fuse_from_flow(quads[mid], flows[:, mid], out5, tn, norm))
+        return torch.cat(out, dim=1)
+

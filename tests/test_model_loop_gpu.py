@@ -113,3 +113,29 @@ def test_interpolate_vs_per_timestep_reference_loop(n_frames, n_t, chunk, bottle
     assert out.shape == (B, n_t, 3, H, W)
     # stage 2 runs on a differently shaped batch (B*N instead of B): allow conv rounding
     assert_close_fp32(out, ref, "interpolate vs per-timestep loop", tol=1e-4)
+
+
+@pytest.mark.parametrize("n_frames,n_t,chunk,bottleneck,h,w", [(2, 7, None, "CONV", 60, 90), (2, 3, 2, "CONV", 64, 96),
+                                                               (4, 3, None, "CLSTM", 45, 77)])
+def test_interpolate_u8_matches_interpolate_on_normalised_frames(n_frames, n_t, chunk, bottleneck, h, w):
+    """interpolate_u8 (8-bit images in, the warps gather raw bytes, uint8 images out) against interpolate() on the same
+    images normalised and padded by ssm_frames_from_u8 -- i.e. against the path already pinned to the reference loop
+    above.  Normalised frames within 1e-4 (the stage-2 U-Net sees inputs that differ by <= 3e-6); uint8 images equal
+    to frames_to_u8 of the fp32 result up to one count where that result sits on a rounding boundary."""
+    B = 2
+    m = _model(123, bottleneck)
+    torch.backends.cudnn.enabled = False
+    g = torch.Generator().manual_seed(5)
+    images = torch.randint(0, 256, (B, n_frames, h, w, 3), dtype=torch.uint8, generator=g).to(DEV)
+    tv = torch.arange(1, n_t + 1, dtype=torch.float32) / (n_t + 1)
+    planar, _, (top, left) = ssm_b200.frames_from_u8(images.view(B * n_frames, h, w, 3), order="bgr")
+    H, W = planar.shape[-2:]
+    ref = m.interpolate(planar.view(B, n_frames, 3, H, W), tv, unet_chunk=chunk)
+    got = m.interpolate_u8(images, tv, order="bgr", unet_chunk=chunk, as_u8=False)
+    assert got.shape == (B, n_t, 3, H, W)
+    assert_close_fp32(got, ref, "interpolate_u8 (normalised frames)", tol=1e-4)
+    got8 = m.interpolate_u8(images, tv, order="bgr", unet_chunk=chunk)
+    ref8 = ssm_b200.frames_to_u8(ref.view(B * n_t, 3, H, W), top, left, h, w, order="bgr", saturate=True).view(B, n_t, h, w, 3)
+    assert got8.shape == (B, n_t, h, w, 3) and got8.dtype == torch.uint8
+    diff = (got8.int() - ref8.int()).abs()
+    assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3

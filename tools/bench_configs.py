@@ -178,12 +178,16 @@ def c4_ssmr_windows(world, rank, dev, steps=2, warmup=1, H=1088, W=1920, n_frame
     model.stage1_model.set_channels_last()
     model.stage2_model.set_channels_last()
     B = 1
-    clip = synthetic.frames(B, H, W, n_frames=n_frames, seed=400 + rank, device=dev).view(B, n_frames, 3, H, W)
+    H_in = 1080 if H == 1088 else H                 # 8-bit 1080 x 1920 images, centred in 1088 x 1920 by the library
+    x = synthetic.frames(B * n_frames, H_in, W, n_frames=1, seed=400 + rank, smooth=True, device=dev)
+    x = (x - x.amin()) / (x.amax() - x.amin())
+    clip = (x.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).view(B, n_frames, H_in, W, 3).contiguous()
+    del x
     t_values = torch.tensor([(k + 1) / (n_t + 1) for k in range(n_t)], dtype=torch.float32, device=dev)
 
     def step():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            return model.interpolate(clip, t_values, unet_chunk=1)
+            return model.interpolate_u8(clip, t_values, order="rgb", unet_chunk=1)
 
     for _ in range(warmup):
         step()
@@ -194,8 +198,9 @@ def c4_ssmr_windows(world, rank, dev, steps=2, warmup=1, H=1088, W=1920, n_frame
     path_total = sum(path.values())
     res = {
         "what": "superslomo_recurrent.ini (SSMR): %d-frame windows (%d windows, bidirectional ConvLSTM bottleneck), "
-                "%dx%d, %d intermediate times of the middle window per sequence, inference, bf16-autocast channels-last "
-                "U-Nets (stock torch/cuDNN, random init)" % (n_frames, n_frames - 1, H, W, n_t),
+                "%dx%d (8-bit images in, 8-bit interpolated images out: FullModel.interpolate_u8), %d intermediate times of the "
+                "middle window per sequence, inference, bf16-autocast channels-last U-Nets (stock torch/cuDNN, random init)"
+                % (n_frames, n_frames - 1, H, W, n_t),
         "parallelism": "one sequence per GPU, no collective (the ConvLSTM couples the windows of a sequence)",
         "scaling": "weak", "n_gpus": world, "sequences_per_gpu": B,
         "ms_per_step": ms, "frames_per_s": B * n_t * world / (ms * 1e-3),

@@ -4,9 +4,10 @@
     python tools/interpolate_dir.py --input-dir frames/ --output-dir out/ --upsample-rate 8 [--weights ckpt.pt]
                                     [--n-frames 2] [--fps-240] [--save-flows] [--amp] [--channels-last] [--bottleneck CLSTM]
 
-uint8 images go to the GPU as they are; ssm_frames_from_u8 normalises and pads them, FullModel.interpolate
-runs stage 1 once per window and all intermediate times per launch, ssm_frames_to_u8 crops and converts
-back.  Without --weights the U-Nets are random-init (seed 42): useful only as a smoke run.
+uint8 images go to the GPU as they are; FullModel.interpolate_u8 normalises and pads them for the U-Nets
+(ssm_frames_from_u8), runs stage 1 once per window and all intermediate times per launch with the warps gathering
+the raw bytes (ssm_quads_from_u8, ssm_flow_pack_fwd_q8), and writes the fused frames straight as cropped uint8 images
+(ssm_fuse_flow_fwd_q8_u8).  Without --weights the U-Nets are random-init (seed 42): useful only as a smoke run.
 """
 import argparse
 import glob
@@ -56,16 +57,16 @@ def main():
     for window in formats.sliding_window(len(paths), a.n_frames, stride=8 if a.fps_240 else 1):
         imgs = np.stack([cv2.imread(paths[i]) for i in window])                     # T x H x W x 3, BGR
         T, H, W, _ = imgs.shape
-        planar, _, (top, left) = ssm_b200.frames_from_u8(torch.from_numpy(imgs).to(dev), order="bgr")
+        images = torch.from_numpy(imgs).to(dev)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
-            frames = model.interpolate(planar[None], t_values)                       # 1 x N x 3 x H32 x W32
+            out = model.interpolate_u8(images[None], t_values, order="bgr")[0].cpu().numpy()   # N x H x W x 3 uint8, BGR
         mid = T // 2 - 1
-        out = ssm_b200.frames_to_u8(frames[0], top, left, H, W, order="bgr", saturate=True).cpu().numpy()
         cv2.imwrite(formats.output_name(a.output_dir, count), imgs[mid]); count += 1
         for k in range(out.shape[0]):
             cv2.imwrite(formats.output_name(a.output_dir, count), out[k]); count += 1
         last = imgs[mid + 1]
         if a.save_flows:
+            planar, _, (top, left) = ssm_b200.frames_from_u8(images, order="bgr")
             with torch.no_grad():
                 flows, _ = model._stage1(model.get_image_pairs(planar[None]))
             f = flows[0, T // 2 - 1]

@@ -305,7 +305,8 @@ int ssm_leaky_bwd_nhwc(const void* grad_y, const void* y, void* grad_x, long lon
 int ssm_avgpool2_bwd_nhwc(const void* grad_out, void* grad_in, int M, int H_out, int W_out, int C, int dtype, void* stream);
 
 /* Workspace sizes (bytes) needed when the image gradient is wanted (none is needed otherwise):
- * 64-bit fixed-point accumulators for the deterministic scatter plus fp32 staging. */
+ * 64-bit fixed-point accumulators of the deterministic, segmented scatter (csrc/ssm_scatter.cuh), plus an fp32 buffer
+ * for the direct (non-warped) terms of ssm_flow_pack_bwd. */
 size_t ssm_warp_bwd_workspace_bytes(int B, int C, int H, int W);
 size_t ssm_flow_pack_bwd_workspace_bytes(int B, int N, int H, int W);
 size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W);

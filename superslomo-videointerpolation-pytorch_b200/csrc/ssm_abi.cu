@@ -323,16 +323,15 @@ struct FuseBwd {
         }
         ScatterHdr* hdr = (ScatterHdr*)ws;
         long long* acc = (long long*)((char*)ws + HDR_BYTES);
-        float* stage = (float*)((char*)ws + HDR_BYTES + sizeof(long long) * B * 6 * npx);
         cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * 6 * npx, s);
         if (e != cudaSuccess) return cuda_fail(e, "ssm_fuse_bwd memset");
         fuse_bwd_kernel<T, MODE, PACKED, true, RECOMP><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
             cview<T>(g3), cview<T>(img6), (const T*)packed, cview<T>(flows4), cview<T>(out5), t, mview<T>(gout5),
-            mview<T>(gflows4), stage, hdr, N, g);
+            mview<T>(gflows4), nullptr, hdr, N, g);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd");
         const int cb = count_bits_for((long long)N * npx);
         fuse_scatter_kernel<T, MODE, RECOMP><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(
-            stage, cview<T>(flows4), cview<T>(out5), t, acc, N, g, hdr, cb);
+            cview<T>(g3), cview<T>(flows4), cview<T>(out5), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd (scatter)");
         const long long total = (long long)B * 6 * npx;
         scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg6), 6, npx, total, hdr, cb);
@@ -411,7 +410,7 @@ size_t ssm_flow_pack_bwd_workspace_bytes(int B, int N, int H, int W) {
 }
 size_t ssm_fuse_bwd_workspace_bytes(int B, int N, int H, int W) {
     if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
-    return HDR_BYTES + sizeof(long long) * (size_t)B * 6 * H * W + sizeof(float) * (size_t)B * N * 6 * H * W;
+    return HDR_BYTES + sizeof(long long) * (size_t)B * 6 * H * W;      // (round 1 added a B x N x 6 fp32 staging buffer)
 }
 
 int ssm_selftest_division(int size, unsigned long long* mismatches_device, void* stream) {

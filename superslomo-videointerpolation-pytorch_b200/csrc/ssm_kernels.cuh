@@ -471,9 +471,10 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
 }
 
 // a3 + a4 backward, gather part: gradients w.r.t. the U-Net output (5 ch) and the estimated flows
-// (input_tensor[:, 6:10]).  With STAGE, d/d(warped I0), d/d(warped I1) are written to an fp32
-// staging buffer (B x N x 6 x H x W) and their max magnitude is recorded for the deterministic
-// image-gradient pass (ssm_scatter.cuh).
+// (input_tensor[:, 6:10]).  With STAGE (image gradients wanted) max |G| of the launch is recorded for the
+// deterministic image-gradient pass (ssm_scatter.cuh): it bounds every d/d(warped I_f) = k_f V_f G_c because
+// k_f V_f <= 1.  That pass recomputes d/d(warped I_f) from G and the logit itself; round 1 staged them in a
+// B x N x 6 x H x W fp32 buffer (5.6 GB written and read back at 16 x 1088 x 1920 x 7, and 128 registers here).
 //
 // With G = d/d(out3), S = (1-t) V0 w0 + t V1 w1, Z = (1-t) V0 + t V1 (SURVEY.md section 8 note):
 //   d/d(w_f,c) = k_f V_f G_c,  k_0 = (1-t)/Z, k_1 = t/Z
@@ -494,7 +495,7 @@ __device__ __forceinline__ void fuse_bwd_frame(const T* __restrict__ frame, long
         A = fmaf(gc[c], bilerp(q[c], t), A);
         const float ds = kv * gc[c];                   // d/d(warped frame)
         bilerp_grad(q[c], t, ds, gx, gy);
-        if (STAGE) { st[c * npx] = ds; amax = fmaxf(amax, fabsf(ds)); }
+        if (STAGE) amax = fmaxf(amax, fabsf(gc[c]));
     }
 }
 
@@ -503,7 +504,7 @@ __device__ __forceinline__ void fuse_bwd_frame(const T* __restrict__ frame, long
 // of flow_interpolation.py:353,356 -- no B x N x 4 gradient (nor the 12 zero channels around it in
 // the gradient of input_tensor) is ever materialised.
 template <typename T, int MODE, bool PACKED, bool STAGE, bool RECOMP>
-__global__ void __launch_bounds__(TILE_THREADS, STAGE ? 2 : SSM_FUSE_BWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(TILE_THREADS, SSM_FUSE_BWD_MIN_BLOCKS)
 fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ packed, View<const T> flows4,
                 View<const T> out5, const float* __restrict__ tv, View<T> gout5, View<T> gflows4,
                 float* __restrict__ stage, ScatterHdr* hdr, int N, Geom g) {
@@ -557,15 +558,14 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ pack
             const float rz = __frcp_rn(omt * v0 + tt * v1);
             const float k0 = omt * rz, k1 = tt * rz;
             float A0 = 0, A1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
-            float* st = STAGE ? stage + ((long long)(ti.b * N + n) * 6) * npx + p : nullptr;
+            float* st = nullptr;          // (round 1: the staging buffer of d/d(warped I_f))
             {
                 const Taps t0 = make_taps<MODE>(ti.x, ti.y, f0x, f0y, g);
                 fuse_bwd_frame<T, PACKED, STAGE>(fr.f0, fr.sc, t0, g.W, gc, k0 * v0, A0, g0x, g0y, st, npx, amax);
             }
             {
                 const Taps t1 = make_taps<MODE>(ti.x, ti.y, f1x, f1y, g);
-                fuse_bwd_frame<T, PACKED, STAGE>(fr.f1, fr.sc, t1, g.W, gc, k1 * v1, A1, g1x, g1y,
-                                                 STAGE ? st + 3 * npx : nullptr, npx, amax);
+                fuse_bwd_frame<T, PACKED, STAGE>(fr.f1, fr.sc, t1, g.W, gc, k1 * v1, A1, g1x, g1y, st, npx, amax);
             }
             const float dz = -rz * (k0 * v0 * A0 + k1 * v1 * A1);      // d/d(normalization_factor)
             const float dv0 = k0 * A0 + omt * dz, dv1 = k1 * A1 + tt * dz;

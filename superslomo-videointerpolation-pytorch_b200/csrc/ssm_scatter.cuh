@@ -8,8 +8,8 @@
 //
 //   1. the gather kernels, which read the upstream gradient anyway, record max |grad| of the launch
 //      (integer atomicMax on the bit pattern: order-independent);
-//   2. scale = 2^k puts that maximum in [2^29, 2^30): a contribution rn(weight*grad) * 2^k (exact) is rounded
-//      ONCE to a 32-bit integer, 30 bits below the largest possible one;
+//   2. scale = 2^k puts that maximum in [2^28, 2^29): a contribution rn(weight*grad) * 2^k (exact) is rounded
+//      ONCE to a 32-bit integer, 29 bits below the largest possible one;
 //   3. SEGMENTED accumulation (round 2): a CTA owns a 64 x 16 tile of source pixels and, per frame and
 //      timestep, a shared-memory window of int32 accumulators covering the tile shifted by the displacement of
 //      its centre pixel plus an 8-pixel halo.  Contributions that land in the window -- nearly all of them for
@@ -28,21 +28,21 @@
 
 namespace ssm {
 
-// power-of-two scale: the largest contribution (<= absmax) lands in [2^29, 2^30).  64-bit global sums cannot
-// overflow: the weights of one source pixel sum to 1, so a cell receives at most N*H*W * absmax < 2^25 * 2^30.
+// power-of-two scale: the largest contribution (<= absmax, up to a rounding) lands in [2^28, 2^29].  64-bit global
+// sums cannot overflow: the weights of one source pixel sum to 1, so a cell receives at most N*H*W * absmax < 2^25 * 2^29.
 // count_bits is unused (kept in the signatures of the kernels that predate the windowed scheme).
 __device__ __forceinline__ float scatter_scale(const ScatterHdr* h, int /*count_bits*/) {
     unsigned int bits = h->absmax_bits;
     if (bits == 0u) return 1.0f;
     if (bits >= 0x7f800000u) return __int_as_float(0x7fc00000);   // inf/NaN upstream: poison
     int e = (int)(bits >> 23) - 127;           // floor(log2(absmax)) (denormals: -127, fine)
-    int k = 29 - e;
+    int k = 28 - e;
     k = min(k, 126); k = max(k, -126);
     return __int_as_float((k + 127) << 23);
 }
 
 __device__ __forceinline__ void fx_add(long long* dst, float contrib, float scale) {
-    const int q = __float2int_rn(contrib * scale);       // |contrib * scale| < 2^30; NaN -> 0 (the scale poisons the result)
+    const int q = __float2int_rn(contrib * scale);       // |contrib * scale| <= 2^29; NaN -> 0 (the scale poisons the result)
     if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)(long long)q);
 }
 
@@ -101,7 +101,8 @@ __device__ __forceinline__ void sw_splat3(int* win, int ox, int oy, const Taps& 
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int k = 0; k < 4; ++k) old[4 * c + k] = atomicAdd(c0 + c * SW_PLANE + (k & 1) + (k >> 1) * SW_W, q[4 * c + k]);
-        // |q| < 2^30: a cell can only wrap if it held 2^30 or more in magnitude -- one add + one or per atomic
+        // |q| <= 2^29 (+ a rounding): a cell can only wrap if it held more than 2^30 in magnitude -- one add + one or
+        // per atomic, with a wide margin
         unsigned flag = 0u;
 #pragma unroll
         for (int i = 0; i < 12; ++i) flag |= (unsigned)old[i] + 0x40000000u;
@@ -276,10 +277,12 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
     }
 }
 
-// ---- a4: scatter of the staged d/d(warped I0), d/d(warped I1) through the refined flows ---------
+// ---- a4: scatter of d/d(warped I0), d/d(warped I1) through the refined flows --------------------
+// d/d(warped I_f)_c = k_f V_f G_c (see fuse_bwd_kernel) is recomputed here from G = grad of the fused frame and the
+// visibility logit with the arithmetic of fuse_bwd_kernel, instead of being staged by that kernel.
 template <typename T, int MODE, bool RECOMP>
 __global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
-fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<const T> out5,
+fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
                     const float* __restrict__ tv, long long* __restrict__ acc, int N, Geom g,
                     const ScatterHdr* __restrict__ hdr, int count_bits) {
     __shared__ int win[3 * SW_PLANE];
@@ -289,12 +292,13 @@ fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<
     const long long npx = (long long)g.H * g.W;
     sw_clear(win);
     long long* a0 = acc + (long long)ti.b * 6 * npx;
-    const int fsc = (int)flows4.sc, ysc = (int)out5.sc;
+    const int fsc = (int)flows4.sc, ysc = (int)out5.sc, gsc = (int)g3.sc;
     for (int n = 0; n < N; ++n) {
         const float tt = __ldg(tv + ti.b * N + n);
+        const float omt = __fsub_rn(1.0f, tt);
         const T* X = flows4.p + ti.b * flows4.sb + (RECOMP ? 0 : n * flows4.sn);
         const T* Y = out5.p + ti.b * out5.sb + n * out5.sn;
-        const float* st = stage + ((long long)(ti.b * N + n) * 6) * npx;
+        const T* G = g3.p + ti.b * g3.sb + n * g3.sn;
         for (int frame = 0; frame < 2; ++frame) {
             sw_phase(win, s_org, ti, g, scale, a0 + frame * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
                 const int p = y * g.W + x;
@@ -311,9 +315,12 @@ fuse_scatter_kernel(const float* __restrict__ stage, View<const T> flows4, View<
                 const float fx = __fadd_rn(xs[o], ldg_(Y + (1 + o) * ysc + p));
                 const float fy = __fadd_rn(xs[o + 1], ldg_(Y + (2 + o) * ysc + p));
                 t = make_taps<MODE>(x, y, fx, fy, g);
-                const float* sp = st + (frame ? 3 : 0) * npx + p;
+                const float v1 = sigmoid_(ldg_(Y + p));
+                const float v0 = 1.0f - v1;
+                const float rz = __frcp_rn(omt * v0 + tt * v1);
+                const float kv = frame ? (tt * rz) * v1 : (omt * rz) * v0;            // k_f V_f
 #pragma unroll
-                for (int c = 0; c < 3; ++c) gv[c] = __ldcs(sp + c * npx);
+                for (int c = 0; c < 3; ++c) gv[c] = kv * ldg_(G + c * gsc + p);
             });
         }
     }

@@ -128,3 +128,27 @@ def test_interpolate_uses_the_unet_layouts(monkeypatch):
     m.unet_layouts = False
     b = m.interpolate(frames, tv)
     assert (a - b).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("mode_name", ["cpu", "cuda"])
+def test_layout_entry_points_against_the_c_oracle(mode_name):
+    """The channels-last compute_inputs and the mixed-dtype compute_output_image DIRECTLY against the C restatement of
+    the reference (oracle/ssm_oracle.c), not only against this library's planar kernels: fp32 channels-last within
+    1e-5 with bit-identical estimated flows, bf16 channels-last = the oracle rounded once to bf16 up to one bf16 ulp,
+    bf16 U-Net output = the oracle run on the widened values."""
+    from oracle import c_oracle
+    from util import assert_close_bf16, assert_close_fp32
+    mode = {"cpu": c_oracle.COORD_DIV, "cuda": c_oracle.COORD_RCP}[mode_name]
+    B, N, H, W = 2, 3, 40, 72
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=990)
+    nhwc32 = ssm_b200.flow_pack_channels_last(img6, flow4, t, n_timesteps=N, dtype=torch.float32, coord_mode=mode_name)
+    nhwc16 = ssm_b200.flow_pack_channels_last(img6, flow4, t, n_timesteps=N, dtype=torch.bfloat16, coord_mode=mode_name)
+    y16 = out5.bfloat16()
+    mixed = ssm_b200.fuse_from_flow(img6, flow4, y16, t, coord_mode=mode_name)
+    for n in range(N):
+        r16 = c_oracle.compute_inputs(img6.cpu(), flow4.cpu(), t[:, n].cpu(), coord_mode=mode)
+        assert torch.equal(nhwc32[:, n, 6:10].cpu(), r16[:, 6:10]), "estimated flows not bit-identical"
+        assert_close_fp32(nhwc32[:, n], r16, "channels-last compute_inputs vs C oracle")
+        assert_close_bf16(nhwc16[:, n], r16, "channels-last bf16 compute_inputs vs C oracle")
+        r3 = c_oracle.compute_output_image(img6.cpu(), r16, y16[:, n].float().cpu().contiguous(), t[:, n].cpu(), coord_mode=mode)
+        assert_close_fp32(mixed[:, n], r3, "compute_output_image with a bf16 U-Net output vs C oracle")

@@ -194,9 +194,15 @@ class FullModel(nn.Module, SynthesisMixin):
             raise RuntimeError("interpolate_u8: expected a CUDA uint8 tensor B x T x H x W x 3, got %s %s"
                                % (tuple(images_u8.shape), images_u8.dtype))
         B, T, H_in, W_in, _ = images_u8.shape
-        lut = q8.normalisation_lut(device=images_u8.device)
+        # normalisation table and padding values: built once per device (reading the padding values back synchronises,
+        # which must not happen inside a captured or pipelined step)
+        cache = self.__dict__.setdefault("_u8_tables", {})
+        if images_u8.device not in cache:
+            lut = q8.normalisation_lut(device=images_u8.device)
+            cache[images_u8.device] = (lut, lut[:, 0].tolist())
+        lut, pads = cache[images_u8.device]
         flat = images_u8.reshape(B * T, H_in, W_in, 3)
-        planar, _, (top, left) = q8.frames_from_u8(flat, order=order, pad_mode="before", lut=lut)
+        planar, _, (top, left) = q8.frames_from_u8(flat, order=order, pad_mode="before", lut=lut, pad_values=pads)
         H, W = planar.shape[-2:]
         norm = q8.norm6()
         pairs = self.get_image_pairs(planar.view(B, T, 3, H, W))

@@ -44,6 +44,8 @@ def main():
                     help="planar fp32 tensors either side of the stage-2 U-Net even when it runs channels-last / autocast "
                          "(default: compute_inputs writes the channels-last [bf16] tensor conv1a consumes)")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN time its algorithms per shape")
+    ap.add_argument("--fp32-frames", action="store_true",
+                    help="round-1 form: normalise to fp32 planes, FullModel.interpolate (RGBx gathers), frames_to_u8")
     ap.add_argument("--profile", default=None, help="write the kernel table of one step (torch.profiler) to this file")
     a = ap.parse_args()
     torch.backends.cudnn.benchmark = a.cudnn_benchmark
@@ -68,6 +70,10 @@ def main():
     pad_values = lut[:, 0].tolist()           # read back once, outside the step
 
     def device_part():
+        if not a.fp32_frames:       # 8-bit images straight through: byte-table warps, uint8 frames written by the fusion kernel
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
+                out = model.interpolate_u8(d_u8.view(B, 2, h_in, w_in, 3), t_values, order="bgr", unet_chunk=a.unet_chunk)
+            return out.view(B * N, h_in, w_in, 3)
         planar, _, (top, left) = ssm_b200.frames_from_u8(d_u8, order="bgr", pad_mode="before", lut=lut,
                                                            pad_values=pad_values)
         H, W = planar.shape[-2:]
@@ -120,7 +126,8 @@ def main():
     # share of the step in this repo's kernels: events around every C-ABI call, eager pass
     spans, lib = [], ssm_b200._abi.lib()
     names = ["ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_fuse_flow_fwd",
-             "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed"]
+             "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed", "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8",
+             "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8", "ssm_fuse_flow_fwd_q8_u8"]
     originals = {n: getattr(lib, n) for n in names}
 
     def timed(n, fn):

@@ -215,9 +215,13 @@ __device__ __forceinline__ float est_t1(const Coef& c, float f01, float f10) {
     return __fsub_rn(__fmul_rn(c.c10, f01), __fmul_rn(c.c11, f10));
 }
 
-// sigmoid and the final normalisation are not coordinate arithmetic: a correctly rounded reciprocal
-// (1 ulp off an IEEE division at worst) is far inside the 1e-5 bar
-__device__ __forceinline__ float sigmoid_(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
+// sigmoid and the final normalisation 1/Z are not coordinate arithmetic: the hardware approximations (MUFU.EX2,
+// MUFU.RCP: relative error ~1e-7) are far inside the 1e-5 bar.  Round 1 used expf + __frcp_rn, which cost two
+// subroutine calls and ~40 instructions per pixel and timestep in kernels that are bound by instruction issue.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// 1 / (1 + 2^(-x log2 e)): two MUFU + two FP32 operations
+__device__ __forceinline__ float sigmoid_(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 // ---- bookkeeping of the deterministic image-gradient accumulation (see ssm_scatter.cuh) --------
 struct ScatterHdr {          // lives at the start of the workspace, zeroed before every launch

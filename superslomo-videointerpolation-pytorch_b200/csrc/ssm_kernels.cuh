@@ -459,7 +459,7 @@ fuse_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<const T> 
         Quad q0[3], q1[3];
         gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
         gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
-        const float rz = __frcp_rn(omt * v0 + tt * v1);                              // 1/Z  :425
+        const float rz = rcp_approx(omt * v0 + tt * v1);                              // 1/Z  :425
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float w0 = v0 * bilerp(q0[c], t0);                                 // :420
@@ -555,7 +555,7 @@ fuse_bwd_kernel(View<const T> g3, View<const T> img6, const T* __restrict__ pack
             }
             const float v1 = sigmoid_(logit);
             const float v0 = 1.0f - v1;
-            const float rz = __frcp_rn(omt * v0 + tt * v1);
+            const float rz = rcp_approx(omt * v0 + tt * v1);
             const float k0 = omt * rz, k1 = tt * rz;
             float A0 = 0, A1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
             float* st = nullptr;          // (round 1: the staging buffer of d/d(warped I_f))
@@ -685,7 +685,7 @@ fuse_loss_fwd_kernel(View<const T> img6, const T* __restrict__ packed, View<cons
             Quad q0[3], q1[3];
             gather3<T, PACKED>(fr.f0, fr.sc, t0, g.W, q0);
             gather3<T, PACKED>(fr.f1, fr.sc, t1, g.W, q1);
-            const float rz = __frcp_rn(omt * v0 + tt * v1);
+            const float rz = rcp_approx(omt * v0 + tt * v1);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float s0 = bilerp(q0[c], t0), s1 = bilerp(q1[c], t1);
@@ -800,7 +800,7 @@ fuse_loss_bwd_kernel(View<const T> g3, const float* __restrict__ gsum, View<cons
         }
         const float v1 = sigmoid_(logit);
         const float v0 = 1.0f - v1;
-        const float rz = __frcp_rn(omt * v0 + tt * v1);
+        const float rz = rcp_approx(omt * v0 + tt * v1);
         const float k0 = omt * rz, k1 = tt * rz;
         float A0 = 0, A1 = 0, g0x = 0, g0y = 0, g1x = 0, g1y = 0;
         {

@@ -31,10 +31,6 @@ constexpr int Q8_TILE_W = 64;              // 32 lanes x 2 pixels
 constexpr int Q8_TILE_H = 8;
 constexpr int Q8_THREADS = 256;
 
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// 1 / (1 + 2^(-x log2 e)): two MUFU + two FP32 ops; |error| < 1e-7 (not coordinate arithmetic)
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 // ---- two pixels at a time: packed fp32 arithmetic ------------------------------------------------
 // sm_100 issues one instruction for two independent fp32 operations on a register pair (FADD2 / FMUL2 /

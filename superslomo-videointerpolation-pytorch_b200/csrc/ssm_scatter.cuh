@@ -317,7 +317,7 @@ fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
                 t = make_taps<MODE>(x, y, fx, fy, g);
                 const float v1 = sigmoid_(ldg_(Y + p));
                 const float v0 = 1.0f - v1;
-                const float rz = __frcp_rn(omt * v0 + tt * v1);
+                const float rz = rcp_approx(omt * v0 + tt * v1);
                 const float kv = frame ? (tt * rz) * v1 : (omt * rz) * v0;            // k_f V_f
 #pragma unroll
                 for (int c = 0; c < 3; ++c) gv[c] = kv * ldg_(G + c * gsc + p);

@@ -274,6 +274,10 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #ifndef SSM_Q8_FUSE_BF16_MIN_BLOCKS
 #define SSM_Q8_FUSE_BF16_MIN_BLOCKS 4
 #endif
+#ifndef SSM_Q8_FUSE_PREFETCH
+#define SSM_Q8_FUSE_PREFETCH 1     // U-Net output of timestep n+1 loaded during the gathers of timestep n: 1.85 ms; without it
+                                   // 2.10 ms at 3 CTAs/SM and 1.99 ms at 4 (profiles/r03c_q8_timing_fuse_prefetch_*.json)
+#endif
 #ifndef SSM_Q8_FUSE_U8_MIN_BLOCKS
 #define SSM_Q8_FUSE_U8_MIN_BLOCKS 3
 #endif
@@ -367,17 +371,26 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<co
     T* __restrict__ O = OUT_U8 ? nullptr : out3.p + ti.b * out3.sb + p;
     const f2 posx = make_float2((float)ti.x, (float)(ti.x + 1)), posy = bc2((float)ti.y);
     f2 ys[5];
+#if SSM_Q8_FUSE_PREFETCH
 #pragma unroll
     for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
+#endif
     for (int n = 0; n < N; ++n) {
         const float tt = __ldg(tp + n);
         const Coef k = make_coef(tt);
+#if SSM_Q8_FUSE_PREFETCH
         const f2 y0 = ys[0], y1 = ys[1], y2 = ys[2], y3 = ys[3], y4 = ys[4];
         if (n + 1 < N) {             // streaming loads of the next timestep, in flight during the gathers
             Y += out5.sn;
 #pragma unroll
             for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
         }
+#else
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
+        Y += out5.sn;
+        const f2 y0 = ys[0], y1 = ys[1], y2 = ys[2], y3 = ys[3], y4 = ys[4];
+#endif
         const f2 f1x = add2x(storage_round2<T>(est2_t1(k, f01x, f10x)), y1);                  // :412
         const f2 f1y = add2x(storage_round2<T>(est2_t1(k, f01y, f10y)), y2);
         const f2 f0x = add2x(storage_round2<T>(est2_t0(k, f01x, f10x)), y3);                  // :413

@@ -293,14 +293,15 @@ def whole_model_step(timeout_s=300):
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
-def host_copy_ceiling(dev, world, nbytes=1 << 30, reps=3):
-    """Plain pinned-memory copies, H2D and D2H at the same time on two streams, all ranks at once: the bandwidth the
-    host side of this box gives `world` GPUs, i.e. the ceiling of any host-buffer entry point."""
+def host_copy_ceiling(dev, world, h2d_bytes, d2h_bytes, reps=3):
+    """Plain pinned-memory copies of the SAME byte volumes one e2e step moves (h2d_bytes up, d2h_bytes down), the two
+    directions concurrently on two streams, all ranks at once: the time the host side of this box needs for the step's
+    transfers alone, i.e. the ceiling of any host-buffer entry point with these buffers."""
     import torch.distributed as dist
-    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def both():
@@ -316,14 +317,15 @@ def host_copy_ceiling(dev, world, nbytes=1 << 30, reps=3):
     for _ in range(reps):
         both()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = (time.perf_counter() - t0) / reps
     if world > 1:
         tt = torch.tensor([dt], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = tt.item()
-    gbs = nbytes * reps / dt / 1e9
-    return {"h2d_gbs_per_gpu": gbs, "d2h_gbs_per_gpu": gbs, "aggregate_each_direction_gbs": gbs * world,
-            "how": "1 GiB pinned H2D and 1 GiB pinned D2H concurrently on two streams, %d rank(s) at once, max time over ranks" % world}
+    return {"ms_per_step_copies_only": 1e3 * dt, "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9, "d2h_gbs_per_gpu": d2h_bytes / dt / 1e9,
+            "aggregate_gbs_both_directions": (h2d_bytes + d2h_bytes) * world / dt / 1e9,
+            "how": "the step's own byte volumes (%.2f GB up, %.2f GB down per rank) as plain pinned copies, both directions "
+                   "concurrently on two streams, %d rank(s) at once, max time over ranks" % (h2d_bytes / 1e9, d2h_bytes / 1e9, world)}
 
 
 def main():
@@ -656,13 +658,15 @@ def main():
     # ---- e2e: host buffers through the C-ABI host entry points --------------------------------
     e2e = e2e_fp32 = ceiling = None
     if not args.no_e2e:
-        ceiling = host_copy_ceiling(dev, world)
         # pinned buffers on the NUMA node the GPU hangs off (each rank binds to its own GPU's node)
         with sharding.numa_local_to_gpu(local_rank) as placement:
             h_images = images.view(B, 2, H_IN, W_IN, 3).cpu().pin_memory()
             h_flow, h_out5 = flow4.cpu().pin_memory(), out5.bfloat16().cpu().pin_memory()
             h_t = t.cpu()
             h_out = torch.empty((B, NT, H_IN, W_IN, 3), dtype=torch.uint8, pin_memory=True)
+        h2d = h_images.numel() + h_flow.numel() * 4 + h_out5.numel() * 2 + h_t.numel() * 4
+        d2h = h_out.numel()
+        ceiling = host_copy_ceiling(dev, world, h2d, d2h)
         scratch = torch.empty(q8.synthesize_host_scratch_bytes(B, NT, H_IN, W_IN, torch.bfloat16), dtype=torch.uint8, device=dev)
         q8.synthesize_host(h_images, h_flow, h_out5, h_t, order="rgb", out=h_out, scratch=scratch)          # warm-up
         barrier()
@@ -675,10 +679,9 @@ def main():
             tt = torch.tensor([dt], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = tt.item()
-        h2d = h_images.numel() + h_flow.numel() * 4 + h_out5.numel() * 2 + h_t.numel() * 4
-        d2h = res.numel()
+        assert d2h == res.numel()
         e2e_value = frames_per_step * args.e2e_steps / dt
-        bound = min(ceiling["h2d_gbs_per_gpu"] * 1e9 / (h2d / (B * NT)), ceiling["d2h_gbs_per_gpu"] * 1e9 / (d2h / (B * NT))) * world
+        bound = frames_per_step / (ceiling["ms_per_step_copies_only"] * 1e-3)
         e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": "ssm_synthesize_host_u8 (pinned host buffers: uint8 frames, fp32 stage-1 flows, bf16 U-Net output in; uint8 "

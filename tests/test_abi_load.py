@@ -60,7 +60,8 @@ def test_workspace_sizes():
     npx = 32 * 48
     assert L.ssm_warp_bwd_workspace_bytes(2, 3, 32, 48) == 256 + 8 * 2 * 3 * npx
     assert L.ssm_flow_pack_bwd_workspace_bytes(2, 7, 32, 48) == 256 + 12 * 2 * 6 * npx
-    assert L.ssm_fuse_bwd_workspace_bytes(2, 7, 32, 48) == 256 + 8 * 2 * 6 * npx + 4 * 2 * 7 * 6 * npx
+    # round 2: no B x N x 6 staging buffer any more (the scatter pass recomputes d/d(warped frame))
+    assert L.ssm_fuse_bwd_workspace_bytes(2, 7, 32, 48) == 256 + 8 * 2 * 6 * npx
     assert L.ssm_warp_bwd_workspace_bytes(0, 3, 32, 48) == 0
     assert L.ssm_packed_frames_bytes(2, 32, 48, 0) == 2 * 2 * npx * 16
     assert L.ssm_packed_frames_bytes(2, 32, 48, 1) == 2 * 2 * npx * 8

@@ -202,6 +202,11 @@ __device__ __forceinline__ float2 lds2(const __nv_bfloat16* p) {
     const unsigned w = __ldcs(reinterpret_cast<const unsigned*>(p));
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ldg2(const __nv_bfloat16* p) {
+    const unsigned w = __ldg(reinterpret_cast<const unsigned*>(p));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
 __device__ __forceinline__ void sts2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
 __device__ __forceinline__ void sts2(__nv_bfloat16* p, float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = low half = the first pixel
@@ -274,6 +279,13 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #ifndef SSM_Q8_FUSE_BF16_MIN_BLOCKS
 #define SSM_Q8_FUSE_BF16_MIN_BLOCKS 4
 #endif
+// channels-last output only: the six pass-through channels are re-read every timestep (L1 / L2 hits) instead of living
+// in 12 registers, which lets 4 CTAs fit per SM: 2.05 -> 1.98 ms (rough flow) / 1.98 -> 1.84 ms (smooth) for the bf16
+// channels-last tensor; the planar fp32 kernel is DRAM-bound and gets slower that way (2.90 -> 2.99 ms)
+// (profiles/r03h_q8_timing_pack_*.json)
+#ifndef SSM_Q8_PACK_NHWC_MIN_BLOCKS
+#define SSM_Q8_PACK_NHWC_MIN_BLOCKS 4
+#endif
 #ifndef SSM_Q8_FUSE_PREFETCH
 #define SSM_Q8_FUSE_PREFETCH 1     // U-Net output of timestep n+1 loaded during the gathers of timestep n: 1.85 ms; without it
                                    // 2.10 ms at 3 CTAs/SM and 1.99 ms at 4 (profiles/r03c_q8_timing_fuse_prefetch_*.json)
@@ -283,7 +295,7 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #endif
 // T: storage type of img6 / flow4 (and of out16 in the planar layout): fp32, or bf16 with fp32 arithmetic
 template <typename T, int MODE, typename TO, bool NHWC>
-__global__ void __launch_bounds__(Q8_THREADS, SSM_Q8_PACK_MIN_BLOCKS)
+__global__ void __launch_bounds__(Q8_THREADS, NHWC ? SSM_Q8_PACK_NHWC_MIN_BLOCKS : SSM_Q8_PACK_MIN_BLOCKS)
 flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, View<const T> flow4,
                         const float* __restrict__ tv, View<TO> out16, int N, Geom g, Norm3 nm) {
     const Q8Idx ti = q8_index(g.H, g.W);
@@ -297,15 +309,22 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
     const int fsc = (int)flow4.sc, isc = (int)img6.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
     const T* I = img6.p + ti.b * img6.sb + p;
+    constexpr bool RELOAD = NHWC;
     float2 c0[3], c1[3];
+    if constexpr (!RELOAD) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { c0[c] = lds2(I + c * isc); c1[c] = lds2(I + (3 + c) * isc); }
+        for (int c = 0; c < 3; ++c) { c0[c] = lds2(I + c * isc); c1[c] = lds2(I + (3 + c) * isc); }
+    }
     const float* tp = tv + ti.b * N;
     TO* __restrict__ O = out16.p + ti.b * out16.sb + (NHWC ? (long long)p * 16 : (long long)p);
     const int osc = (int)out16.sc;
     const f2 posx = make_float2((float)ti.x, (float)(ti.x + 1)), posy = bc2((float)ti.y);
     for (int n = 0; n < N; ++n, O += out16.sn) {
         const Coef k = make_coef(__ldg(tp + n));
+        if constexpr (RELOAD) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { c0[c] = ldg2(I + c * isc); c1[c] = ldg2(I + (3 + c) * isc); }
+        }
         const f2 e0x = storage_round2<T>(est2_t0(k, f01x, f10x)), e0y = storage_round2<T>(est2_t0(k, f01y, f10y));   // F_t0  :353
         const f2 e1x = storage_round2<T>(est2_t1(k, f01x, f10x)), e1y = storage_round2<T>(est2_t1(k, f01y, f10y));   // F_t1  :356
         const QTap2 t1 = make_qtap2<MODE>(posx, posy, e1x, e1y, g, xb1);                             // warp(img_1, F_t1) :361

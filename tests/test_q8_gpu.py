@@ -200,3 +200,66 @@ def test_q8_bf16_storage():
         x16[:, 6:10] = e
         r3 = c_oracle.compute_output_image(img6_c, x16, out5[:, n].float().contiguous(), t[:, n])
         assert_close_bf16(frames[:, n], r3, "q8 bf16 fused n=%d" % n)
+
+
+def test_q8_4k_31_timesteps_against_fp32_kernels():
+    """BASELINE.json configs[4] size: one 2160x3840 pair (padded to 2176x3840), t = k/32 -- the timesteps one rank of
+    eight gets (4) plus the last one -- against the fp32 kernels, and the oracle on a band of rows."""
+    h, w = 2160, 3840
+    images = _u8_images(2, h, w, seed=21, smooth=True)
+    planar, quads, norm, _ = q8.prepare(images.to(DEV))
+    H, W = planar.shape[-2:]
+    assert (H, W) == (2176, 3840)
+    img6 = planar.view(1, 6, H, W)
+    flow4 = synthetic.flows(1, H, W, 4, flow_px=20.0, seed=22, device=DEV)
+    t = torch.tensor([[1 / 32, 2 / 32, 3 / 32, 4 / 32, 31 / 32]], device=DEV)
+    N = t.shape[1]
+    out5 = synthetic.unet_out5(1, N, H, W, seed=23, device=DEV)
+    in16 = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N)
+    frames = q8.fuse_from_flow(quads, flow4, out5, t, norm)
+    ref16 = ssm_b200.flow_pack(img6, flow4, t, n_timesteps=N)
+    ref3 = ssm_b200.fuse_from_flow(img6, flow4, out5, t)
+    assert torch.equal(in16[:, :, 6:10], ref16[:, :, 6:10])
+    assert max_err(in16, ref16) <= 1e-5 and max_err(frames, ref3) <= 1e-5
+    assert torch.isfinite(frames).all()
+    r16 = c_oracle.compute_inputs(img6.cpu(), flow4.cpu(), t[:, 4].cpu())
+    assert_close_fp32(in16[0, 4, :, 2000:2008], r16[0, :, 2000:2008], "q8 flow_pack vs C oracle at 4K")
+
+
+def test_q8_non_finite_flows_and_argument_errors():
+    """Samples with non-finite or absurd coordinates read nothing and give zeros (the fp32 kernels and, in practice, the
+    reference do the same); wrong arguments are refused loudly -- there is no fallback path."""
+    B, N, h, w = 1, 2, 40, 72
+    images = _u8_images(2 * B, h, w, seed=31, smooth=False)
+    planar, quads, norm, _ = q8.prepare(images.to(DEV))
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=4.0, seed=32, device=DEV)
+    out5 = synthetic.unet_out5(B, N, H, W, seed=33, device=DEV)
+    t = synthetic.timesteps(B, N, device=DEV)
+    bad = flow4.clone()
+    bad[0, :, 5, 7] = float("inf")
+    bad[0, :, 6, 8] = float("nan")
+    bad[0, :, 7, 9] = 3.0e30
+    bad[0, :, 8, 10] = -1.0e9
+    in16 = q8.flow_pack(img6, quads, bad, t, norm, n_timesteps=N)
+    assert torch.isfinite(in16[:, :, 3:6]).all() and torch.isfinite(in16[:, :, 10:13]).all()
+    for (y, x) in ((5, 7), (6, 8), (7, 9), (8, 10)):
+        assert in16[0, :, 3:6, y, x].abs().max() == 0 and in16[0, :, 10:13, y, x].abs().max() == 0
+    good = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N)
+    mask = torch.ones((H, W), dtype=torch.bool, device=DEV)
+    for (y, x) in ((5, 7), (6, 8), (7, 9), (8, 10)):
+        mask[y, x] = False
+    assert torch.equal(in16[:, :, 3:6][..., mask], good[:, :, 3:6][..., mask])          # every other pixel untouched
+    frames = q8.fuse_from_flow(quads, bad, out5, t, norm)
+    assert torch.isfinite(frames).all()
+    with pytest.raises(RuntimeError):                     # tables of another size
+        q8.flow_pack(img6, quads[:, :-1].contiguous(), flow4, t, norm, n_timesteps=N)
+    with pytest.raises(RuntimeError):                     # CPU tensors: no fallback
+        q8.flow_pack(img6.cpu(), quads, flow4.cpu(), t.cpu(), norm, n_timesteps=N)
+    with pytest.raises(RuntimeError):                     # inference only
+        q8.flow_pack(img6, quads, flow4.clone().requires_grad_(True), t, norm, n_timesteps=N)
+    with pytest.raises(RuntimeError):                     # t count (a single value would be broadcast; three for two is an error)
+        q8.fuse_from_flow(quads, flow4, out5, torch.tensor([[0.25, 0.5, 0.75]], device=DEV), norm)
+    with pytest.raises(AssertionError):                   # validators.py:9-11 on a host-side t
+        q8.flow_pack(img6, quads, flow4, torch.tensor([[0.5, 1.0]]), norm, n_timesteps=N)

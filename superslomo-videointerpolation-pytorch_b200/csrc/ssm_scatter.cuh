@@ -80,71 +80,86 @@ __device__ __forceinline__ void sw_add(int* cell, int q, long long* gcell) {
         atomicAdd(reinterpret_cast<unsigned long long*>(gcell), (unsigned long long)(q > 0 ? (1ll << 32) : -(1ll << 32)));
 }
 
-// the contributions of one source pixel (taps t, three channel values gv) to planes plane0 + c * npx
+// the contributions of one source pixel (taps t, three channel values gv) to planes plane0 + c * npx.
+// ONE code path for every pixel: a tap inside the image goes to the window when its cell is inside it and to the global
+// accumulator otherwise, by predication.  (The first version had a fast path for footprints entirely inside image and
+// window and a per-tap slow path; with a rough flow field most warps hold both kinds of lanes and executed both paths,
+// 550 instructions per pixel and phase.)  All twelve shared-memory atomics are issued before any of their results is
+// looked at, and one combined test decides whether some cell may have wrapped.
 __device__ __forceinline__ void sw_splat3(int* win, int ox, int oy, const Taps& t, const float (&gv)[3], float scale,
                                           long long* __restrict__ plane0, long long npx, int W) {
-    const int x0 = (int)t.fx, y0 = (int)t.fy;
-    const int cx = x0 - ox, cy = y0 - oy;
+    const int cx = (int)t.fx - ox, cy = (int)t.fy - oy;
     const float w[4] = {t.wnw, t.wne, t.wsw, t.wse};
     const bool in[4] = {t.nw, t.ne, t.sw, t.se};
-    if (in[0] && in[1] && in[2] && in[3] && (unsigned)cx < (unsigned)(SW_W - 1) && (unsigned)cy < (unsigned)(SW_H - 1)) {
-        // the common case: the 2 x 2 footprint lies inside the image and inside the window.  All twelve atomics are
-        // issued before any of their results is looked at (they overlap), and one combined test decides whether some
-        // cell may have overflowed
-        int* c0 = win + cy * SW_W + cx;
-        int q[12], old[12];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) q[4 * c + k] = __float2int_rn(w[k] * gv[c] * scale);
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) old[4 * c + k] = atomicAdd(c0 + c * SW_PLANE + (k & 1) + (k >> 1) * SW_W, q[4 * c + k]);
-        // |q| <= 2^29 (+ a rounding): a cell can only wrap if it held more than 2^30 in magnitude -- one add + one or
-        // per atomic, with a wide margin
-        unsigned flag = 0u;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) flag |= (unsigned)old[i] + 0x40000000u;
-        if (flag & 0x80000000u) {            // rare: repair the cells that wrapped by moving 2^32 into the global cell
-            long long* g0 = plane0 + t.off;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = 4 * c + k, nw = (int)((unsigned)old[i] + (unsigned)q[i]);
-                    if (((old[i] ^ nw) & (q[i] ^ nw)) < 0)
-                        atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx + (k & 1) + (k >> 1) * W),
-                                  (unsigned long long)(q[i] > 0 ? (1ll << 32) : -(1ll << 32)));
-                }
-        }
-        return;
-    }
+    const bool xin[2] = {(unsigned)cx < (unsigned)SW_W, (unsigned)(cx + 1) < (unsigned)SW_W};
+    const bool yin[2] = {(unsigned)cy < (unsigned)SW_H, (unsigned)(cy + 1) < (unsigned)SW_H};
+    bool smem[4], glob[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (!in[k]) continue;
-        const int kx = cx + (k & 1), ky = cy + (k >> 1);
-        const bool inside = (unsigned)kx < (unsigned)SW_W && (unsigned)ky < (unsigned)SW_H;
-        long long* g0 = plane0 + t.off + (k & 1) + (k >> 1) * W;
+        const bool inside = xin[k & 1] && yin[k >> 1];
+        smem[k] = in[k] && inside;
+        glob[k] = in[k] && !inside;
+    }
+    int* c0 = win + cy * SW_W + cx;                 // dereferenced under smem[k] only
+    long long* g0 = plane0 + t.off;                 // dereferenced under in[k] only
+    const float gs[3] = {gv[0] * scale, gv[1] * scale, gv[2] * scale};      // scale is a power of two: exact
+    int q[12], old[12];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int q = __float2int_rn(w[k] * gv[c] * scale);
-            if (!q) continue;
-            if (inside) sw_add(win + c * SW_PLANE + ky * SW_W + kx, q, g0 + c * npx);
-            else atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx), (unsigned long long)(long long)q);
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[4 * c + k] = __float2int_rn(w[k] * gs[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * c + k;
+            old[i] = 0;
+            if (smem[k]) old[i] = atomicAdd(c0 + c * SW_PLANE + (k & 1) + (k >> 1) * SW_W, q[i]);
         }
+    if (glob[0] || glob[1] || glob[2] || glob[3]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!glob[k]) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (q[4 * c + k])
+                    atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx + (k & 1) + (k >> 1) * W), (unsigned long long)(long long)q[4 * c + k]);
+        }
+    }
+    // |q| <= 2^29 (+ a rounding): a cell can only wrap if it held more than 2^30 in magnitude -- one add + one or per
+    // atomic, with a wide margin
+    unsigned flag = 0u;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) flag |= (unsigned)old[i] + 0x40000000u;
+    if (flag & 0x80000000u) {            // rare: repair the cells that wrapped by moving 2^32 into the global cell
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * c + k, nw = (int)((unsigned)old[i] + (unsigned)q[i]);
+                if (smem[k] && ((old[i] ^ nw) & (q[i] ^ nw)) < 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(g0 + c * npx + (k & 1) + (k >> 1) * W),
+                              (unsigned long long)(q[i] > 0 ? (1ll << 32) : -(1ll << 32)));
+            }
     }
 }
 
-// non-zero cells -> one 64-bit global atomic each; the window is left zeroed for the next phase
+// non-zero cells -> one 64-bit global atomic each; the window is left zeroed for the next phase.  Four cells per
+// 16-byte shared-memory load; an all-zero quadruple (half the window on average) costs three instructions.
 __device__ __forceinline__ void sw_flush(int* win, int ox, int oy, long long* __restrict__ plane0, long long npx, int H, int W) {
-    for (int i = threadIdx.x; i < 3 * SW_PLANE; i += SW_THREADS) {
-        const int q = win[i];
-        if (!q) continue;
-        win[i] = 0;
-        const int c = i / SW_PLANE, r = i - c * SW_PLANE, cy = r / SW_W, cx = r - cy * SW_W;
-        // only taps inside the image were added: (ox + cx, oy + cy) is a valid pixel
-        atomicAdd(reinterpret_cast<unsigned long long*>(plane0 + c * npx + (long long)(oy + cy) * W + (ox + cx)), (unsigned long long)(long long)q);
+    static_assert(SW_W % 4 == 0, "window rows are read four cells at a time");
+    int4* w4 = reinterpret_cast<int4*>(win);
+    for (int i = threadIdx.x; i < 3 * SW_PLANE / 4; i += SW_THREADS) {
+        const int4 v = w4[i];
+        if ((v.x | v.y | v.z | v.w) == 0) continue;
+        w4[i] = make_int4(0, 0, 0, 0);
+        const int cell = 4 * i, c = cell / SW_PLANE, r = cell - c * SW_PLANE, cy = r / SW_W, cx = r - cy * SW_W;
+        // only taps inside the image were added: a non-zero cell (ox + cx + j, oy + cy) is a valid pixel
+        long long* g = plane0 + c * npx + (long long)(oy + cy) * W + (ox + cx);
+        if (v.x) atomicAdd(reinterpret_cast<unsigned long long*>(g), (unsigned long long)(long long)v.x);
+        if (v.y) atomicAdd(reinterpret_cast<unsigned long long*>(g + 1), (unsigned long long)(long long)v.y);
+        if (v.z) atomicAdd(reinterpret_cast<unsigned long long*>(g + 2), (unsigned long long)(long long)v.z);
+        if (v.w) atomicAdd(reinterpret_cast<unsigned long long*>(g + 3), (unsigned long long)(long long)v.w);
     }
 }
 
@@ -181,7 +196,8 @@ __device__ __forceinline__ void sw_phase(int* win, volatile int* s_org, const Sw
 }
 
 __device__ __forceinline__ void sw_clear(int* win) {
-    for (int i = threadIdx.x; i < 3 * SW_PLANE; i += SW_THREADS) win[i] = 0;
+    int4* w4 = reinterpret_cast<int4*>(win);
+    for (int i = threadIdx.x; i < 3 * SW_PLANE / 4; i += SW_THREADS) w4[i] = make_int4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ void scatter_quad(long long* plane, const Taps& t, int W, float gv, float scale) {
@@ -228,7 +244,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
 warp_scatter_win_kernel(View<const T> gout, View<const T> flow, long long* __restrict__ acc, Geom g,
                         const ScatterHdr* __restrict__ hdr) {
-    __shared__ int win[3 * SW_PLANE];
+    __shared__ __align__(16) int win[3 * SW_PLANE];
     __shared__ int s_org[2];
     const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, 0);
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
 flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __restrict__ tv,
                          long long* __restrict__ acc, int N, Geom g,
                          const ScatterHdr* __restrict__ hdr, int count_bits) {
-    __shared__ int win[3 * SW_PLANE];
+    __shared__ __align__(16) int win[3 * SW_PLANE];
     __shared__ int s_org[2];
     const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(SW_THREADS, SW_MIN_BLOCKS)
 fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
                     const float* __restrict__ tv, long long* __restrict__ acc, int N, Geom g,
                     const ScatterHdr* __restrict__ hdr, int count_bits) {
-    __shared__ int win[3 * SW_PLANE];
+    __shared__ __align__(16) int win[3 * SW_PLANE];
     __shared__ int s_org[2];
     const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);

@@ -560,9 +560,7 @@ def main():
                 r = ssm_b200.pack_frames(img_h)
                 a = ssm_b200.flow_pack(img_h, flow_h, t, n_timesteps=NT, packed=r)
                 return a, ssm_b200.fuse_from_flow(img_h, flow_h, out5_h, t, packed=r)
-        bf16 = variant(timed(step_bf16), (pack_bytes + fuse_bytes) // 2)
-        bf16["note"] = ("bf16 storage of every tensor (RGBx bf16 gathers), fp32 arithmetic; not the headline (the reference is fp32); "
-                        "uint8_frames: the same with the gathers reading the uint8 entry tables")
+        bf16_rgbx = variant(timed(step_bf16), (pack_bytes + fuse_bytes) // 2)
         in16_h = torch.empty((B, NT, 16, H, W), dtype=torch.bfloat16, device=dev)
         frames_h = torch.empty((B, NT, 3, H, W), dtype=torch.bfloat16, device=dev)
 
@@ -571,7 +569,12 @@ def main():
                 stage_quads()
                 a = q8.flow_pack(img_h, quads, flow_h, t, norm, n_timesteps=NT, out=in16_h)
                 return a, q8.fuse_from_flow(quads, flow_h, out5_h, t, norm, out=frames_h)
-        bf16["uint8_frames"] = variant(timed(step_bf16_q8), (pack_bytes + fuse_bytes) // 2)
+        bf16 = variant(timed(step_bf16_q8), (pack_bytes + fuse_bytes) // 2)
+        bf16["note"] = ("bf16 storage of every tensor (planar frames, flows, U-Net output, both results), fp32 arithmetic, the warps "
+                        "gathering from the uint8 entry tables as in the headline; not the headline (the reference is fp32). Half the "
+                        "bytes for the same instruction count: the kernels are bound by instruction issue / the FMA pipe, not HBM "
+                        "(DESIGN 5.1b).  bf16_rgbx_frames: the round-1 form (frames as a bf16 RGBx copy, 8-byte gathers)")
+        bf16["bf16_rgbx_frames"] = bf16_rgbx
         del img_h, flow_h, in16_h, frames_h
         # the layouts either side of a channels-last stage-2 U-Net under bf16 autocast:
         # compute_inputs writes B x N x H x W x 16 bf16, compute_output_image reads a bf16 U-Net output

@@ -283,6 +283,9 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 // in 12 registers, which lets 4 CTAs fit per SM: 2.05 -> 1.98 ms (rough flow) / 1.98 -> 1.84 ms (smooth) for the bf16
 // channels-last tensor; the planar fp32 kernel is DRAM-bound and gets slower that way (2.90 -> 2.99 ms)
 // (profiles/r03h_q8_timing_pack_*.json)
+#ifndef SSM_Q8_RELOAD_BF16
+#define SSM_Q8_RELOAD_BF16 1       // the same for bf16 storage (planar): 1.92 -> 1.83 ms (profiles/r03n_bf16_*.json)
+#endif
 #ifndef SSM_Q8_PACK_NHWC_MIN_BLOCKS
 #define SSM_Q8_PACK_NHWC_MIN_BLOCKS 4
 #endif
@@ -295,7 +298,7 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #endif
 // T: storage type of img6 / flow4 (and of out16 in the planar layout): fp32, or bf16 with fp32 arithmetic
 template <typename T, int MODE, typename TO, bool NHWC>
-__global__ void __launch_bounds__(Q8_THREADS, NHWC ? SSM_Q8_PACK_NHWC_MIN_BLOCKS : SSM_Q8_PACK_MIN_BLOCKS)
+__global__ void __launch_bounds__(Q8_THREADS, (NHWC || (SSM_Q8_RELOAD_BF16 && sizeof(T) == 2)) ? SSM_Q8_PACK_NHWC_MIN_BLOCKS : SSM_Q8_PACK_MIN_BLOCKS)
 flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, View<const T> flow4,
                         const float* __restrict__ tv, View<TO> out16, int N, Geom g, Norm3 nm) {
     const Q8Idx ti = q8_index(g.H, g.W);
@@ -309,7 +312,7 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
     const int fsc = (int)flow4.sc, isc = (int)img6.sc;
     const float2 f01x = lds2(F), f01y = lds2(F + fsc), f10x = lds2(F + 2 * fsc), f10y = lds2(F + 3 * fsc);
     const T* I = img6.p + ti.b * img6.sb + p;
-    constexpr bool RELOAD = NHWC;
+    constexpr bool RELOAD = NHWC || (SSM_Q8_RELOAD_BF16 && sizeof(T) == 2);
     float2 c0[3], c1[3];
     if constexpr (!RELOAD) {
 #pragma unroll

@@ -644,12 +644,13 @@ def main():
         pk = ssm_b200.pack_image(xw)
         warp_t = {}
         for name, kw in (("planar", {}), ("rgbx", {"packed": pk})):
-            yw = ssm_b200.warp(xw, fw, **kw)
-            warp_t["warp_fwd_" + name] = (timed(lambda: ssm_b200.warp(xw.detach(), fw.detach(), **{k: v for k, v in kw.items()})), 8)
+            warp_t["warp_fwd_" + name] = (timed(lambda: ssm_b200.warp(xw.detach(), fw.detach(), **kw)), 8)
+            yw = ssm_b200.warp(xw.detach(), fw, **kw)                    # frames are data: flow gradient only (a gather)
             warp_t["warp_bwd_flow_" + name] = (timed(lambda: torch.autograd.grad(yw, (fw,), gw, retain_graph=True)), 10)
-            if name == "planar":
-                warp_t["warp_bwd_flow_and_image"] = (timed(lambda: torch.autograd.grad(yw, (xw, fw), gw, retain_graph=True), reps=3, warm=1), 13)
             del yw
+        yw = ssm_b200.warp(xw, fw)                                        # + image gradient (segmented scatter)
+        warp_t["warp_bwd_flow_and_image"] = (timed(lambda: torch.autograd.grad(yw, (xw, fw), gw, retain_graph=True), reps=3, warm=1), 13)
+        del yw
         warp_t["pack_image"] = (timed(lambda: ssm_b200.pack_image(xw, out=pk)), 7)
         for k, (ms, per_px) in warp_t.items():
             nb = per_px * 4 * NPX * B

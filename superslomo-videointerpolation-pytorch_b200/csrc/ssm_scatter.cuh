@@ -47,7 +47,10 @@ __device__ __forceinline__ void fx_add(long long* dst, float contrib, float scal
 }
 
 // ---- the shared-memory window -----------------------------------------------------------------------------------
-constexpr int SW_TILE_W = 64, SW_TILE_H = 16;             // source pixels per CTA: 256 threads x 4 rows
+#ifndef SSM_SW_TILE_H
+#define SSM_SW_TILE_H 16
+#endif
+constexpr int SW_TILE_W = 64, SW_TILE_H = SSM_SW_TILE_H;  // source pixels per CTA: 256 threads x (SW_TILE_H / 4) rows
 #ifndef SSM_SW_HALO
 #define SSM_SW_HALO 8
 #endif

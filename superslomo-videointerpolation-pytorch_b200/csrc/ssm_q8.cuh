@@ -23,6 +23,13 @@
 #pragma once
 #include "ssm_frames.cuh"
 
+// Interpolation in difference form (12 packed operations fewer per timestep, errors 1.2e-6 instead of 2.6e-6): measured
+// SLOWER for the headline kernel (compute_output_image, fp32 U-Net output: 1.85 -> 1.94 ms, longer dependency chains at
+// 24 warps per SM), faster only with a bf16 U-Net output (2.14 -> 1.94 ms); off (profiles/r03s_q8_timing_*.json).
+#ifndef SSM_Q8_DIFF_FORM
+#define SSM_Q8_DIFF_FORM 0
+#endif
+
 namespace ssm {
 
 struct Norm3 { float a[3], c[3]; };       // normalised value of byte b in channel k: a[k] * b + c[k]
@@ -107,7 +114,11 @@ template <> __device__ __forceinline__ f2 storage_round2<__nv_bfloat16>(f2 v) {
 
 // the bilinear sample of one frame for the two pixels of a thread
 struct QTap2 {
+#if SSM_Q8_DIFF_FORM
+    f2 wx1, wy1;                // fractional position inside the 2 x 2 cell (east / south weights)
+#else
     f2 wnw, wne, wsw, wse;      // corner weights (ATen: area of the opposite sub-rectangle)
+#endif
     f2 wsum;                    // sum of the weights of the corners inside the frame
     unsigned idx[2];            // entry index in the launch-wide table, frame base + (y0+1)*(W+1) + (x0+1); only dereferenced when ok
     bool ok[2];                 // the sample has weight inside the frame (then the entry exists)
@@ -130,9 +141,13 @@ __device__ __forceinline__ QTap2 make_qtap2(f2 posx, f2 posy, f2 u, f2 v, const 
     // by one rounding (6e-8).
     const f2 wx1 = make_float2(__saturatef(ix.x - fx.x), __saturatef(ix.y - fx.y));
     const f2 wy1 = make_float2(__saturatef(iy.x - fy.x), __saturatef(iy.y - fy.y));
-    const f2 wx0 = sub2(bc2(1.0f), wx1), wy0 = sub2(bc2(1.0f), wy1);
     QTap2 t;
+#if SSM_Q8_DIFF_FORM
+    t.wx1 = wx1; t.wy1 = wy1;
+#else
+    const f2 wx0 = sub2(bc2(1.0f), wx1), wy0 = sub2(bc2(1.0f), wy1);
     t.wnw = mul2(wx0, wy0); t.wne = mul2(wx1, wy0); t.wsw = mul2(wx0, wy1); t.wse = mul2(wx1, wy1);
+#endif
     // total weight of the columns inside the frame: 1 in the interior, ix + 1 for ix in [-1, 0), W - ix for
     // ix in [W-1, W), 0 outside or NaN = min(sat(ix + 1), sat(W - ix)), the same roundings as wx1 / wx0 there
     const float Wf = g.xm1 + 1.0f, Hf = g.ym1 + 1.0f;
@@ -172,6 +187,18 @@ __device__ __forceinline__ void q8_sample2(const uint4& qa, const uint4& qb, con
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         // bytes 0-2 nw, 3-5 ne, 6-8 sw, 9-11 se
+#if SSM_Q8_DIFF_FORM
+        // interpolation in difference form: b_nw + wx (b_ne - b_nw) + wy ((b_sw - b_nw) + wx (b_se - b_sw - b_ne + b_nw)).
+        // The differences of the 2^23-biased bit patterns are exact and drop the bias; the four corner weights and their
+        // six packed operations per frame are never formed.
+        const f2 Bnw = make_float2(byte_bits(wa[c >> 2], c & 3), byte_bits(wb[c >> 2], c & 3));
+        const f2 Bne = make_float2(byte_bits(wa[(3 + c) >> 2], (3 + c) & 3), byte_bits(wb[(3 + c) >> 2], (3 + c) & 3));
+        const f2 Bsw = make_float2(byte_bits(wa[(6 + c) >> 2], (6 + c) & 3), byte_bits(wb[(6 + c) >> 2], (6 + c) & 3));
+        const f2 Bse = make_float2(byte_bits(wa[(9 + c) >> 2], (9 + c) & 3), byte_bits(wb[(9 + c) >> 2], (9 + c) & 3));
+        const f2 dx = sub2(Bne, Bnw), dy = sub2(Bsw, Bnw), dxy = sub2(sub2(Bse, Bsw), dx);
+        f2 s = fma2(t.wx1, dx, add2(Bnw, m23));
+        s = fma2(t.wy1, fma2(t.wx1, dxy, dy), s);
+#else
         const f2 bnw = add2(make_float2(byte_bits(wa[c >> 2], c & 3), byte_bits(wb[c >> 2], c & 3)), m23);
         const f2 bne = add2(make_float2(byte_bits(wa[(3 + c) >> 2], (3 + c) & 3), byte_bits(wb[(3 + c) >> 2], (3 + c) & 3)), m23);
         const f2 bsw = add2(make_float2(byte_bits(wa[(6 + c) >> 2], (6 + c) & 3), byte_bits(wb[(6 + c) >> 2], (6 + c) & 3)), m23);
@@ -180,6 +207,7 @@ __device__ __forceinline__ void q8_sample2(const uint4& qa, const uint4& qb, con
         s = fma2(bne, t.wne, s);
         s = fma2(bsw, t.wsw, s);
         s = fma2(bse, t.wse, s);
+#endif
         out[c] = fma2(bc2(nm.a[c]), s, mul2(bc2(nm.c[c]), t.wsum));
     }
 }

@@ -263,3 +263,37 @@ def test_q8_non_finite_flows_and_argument_errors():
         q8.fuse_from_flow(quads, flow4, out5, torch.tensor([[0.25, 0.5, 0.75]], device=DEV), norm)
     with pytest.raises(AssertionError):                   # validators.py:9-11 on a host-side t
         q8.flow_pack(img6, quads, flow4, torch.tensor([[0.5, 1.0]]), norm, n_timesteps=N)
+
+
+def test_q8_and_fp32_kernels_on_random_shapes_vs_c_oracle():
+    """Twelve seeded random problems (image sizes 2..140 that are not multiples of anything, 1..5 timesteps, flows from
+    sub-pixel to several image widths, both coordinate modes): the 8-bit-frame kernels and the fp32 kernels against the C
+    oracle on the normalised frames, 1e-5; estimated flows bit-identical."""
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        B, N = int(rng.integers(1, 3)), int(rng.integers(1, 6))
+        h, w = int(rng.integers(2, 141)), int(rng.integers(2, 141))
+        flow_px = float(rng.choice([0.3, 2.0, 9.0, 40.0, 300.0]))
+        kind = str(rng.choice(["smooth", "noise", "border"]))
+        mode_name, mode = MODES[case % 2]
+        images = _u8_images(2 * B, h, w, seed=900 + case, smooth=bool(case % 3))
+        planar, quads, norm, _ = q8.prepare(images.to(DEV), order="rgb", lut=ssm_b200.normalisation_lut(device="cpu"))
+        H, W = planar.shape[-2:]
+        img6 = planar.view(B, 6, H, W)
+        flow4 = synthetic.flows(B, H, W, 4, flow_px=flow_px, seed=901 + case, kind=kind)
+        out5 = synthetic.unet_out5(B, N, H, W, seed=902 + case)
+        t = synthetic.timesteps(B, N)
+        in16_q = q8.flow_pack(img6, quads, flow4.to(DEV), t, norm, n_timesteps=N, coord_mode=mode_name)
+        fr_q = q8.fuse_from_flow(quads, flow4.to(DEV), out5.to(DEV), t, norm, coord_mode=mode_name)
+        in16_f = ssm_b200.flow_pack(img6, flow4.to(DEV), t.to(DEV), n_timesteps=N, coord_mode=mode_name)
+        fr_f = ssm_b200.fuse_from_flow(img6, flow4.to(DEV), out5.to(DEV), t.to(DEV), coord_mode=mode_name)
+        img6_c = img6.cpu()
+        what = "case %d (B=%d N=%d %dx%d -> %dx%d, %s flow x %g, %s)" % (case, B, N, h, w, H, W, kind, flow_px, mode_name)
+        for n in range(N):
+            r16 = c_oracle.compute_inputs(img6_c, flow4, t[:, n], coord_mode=mode)
+            r3 = c_oracle.compute_output_image(img6_c, r16, out5[:, n].contiguous(), t[:, n], coord_mode=mode)
+            assert torch.equal(in16_q[:, n, 6:10].cpu(), r16[:, 6:10]) and torch.equal(in16_f[:, n, 6:10].cpu(), r16[:, 6:10]), what
+            assert_close_fp32(in16_q[:, n], r16, "q8 compute_inputs, " + what)
+            assert_close_fp32(in16_f[:, n], r16, "fp32 compute_inputs, " + what)
+            assert_close_fp32(fr_q[:, n], r3, "q8 compute_output_image, " + what)
+            assert_close_fp32(fr_f[:, n], r3, "fp32 compute_output_image, " + what)

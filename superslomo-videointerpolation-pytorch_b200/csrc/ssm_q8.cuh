@@ -35,8 +35,13 @@ namespace ssm {
 struct Norm3 { float a[3], c[3]; };       // normalised value of byte b in channel k: a[k] * b + c[k]
 
 constexpr int Q8_TILE_W = 64;              // 32 lanes x 2 pixels
-constexpr int Q8_TILE_H = 8;
-constexpr int Q8_THREADS = 256;
+// rows per CTA (threads = 32 x rows).  64 x 4 tiles with 128-thread CTAs, 6 per SM: compute_output_image 1.85 -> 1.81 ms,
+// compute_inputs 2.86 -> 2.91 ms -- a wash (profiles/r03u_q8_timing_128_thread_ctas_*.json)
+#ifndef SSM_Q8_TILE_H
+#define SSM_Q8_TILE_H 8
+#endif
+constexpr int Q8_TILE_H = SSM_Q8_TILE_H;
+constexpr int Q8_THREADS = 32 * Q8_TILE_H;
 
 
 // ---- two pixels at a time: packed fp32 arithmetic ------------------------------------------------

@@ -24,7 +24,7 @@ class SynthesisMixin:
     def compute_inputs_batched(self, img_tensor, flow_pred_tensor, t):
         """All N timesteps of every pair at once.  t: B x N -> B x N x 16 x H x W."""
         t = torch.as_tensor(t)
-        n = t.numel() // img_tensor.shape[0]
+        n = t.shape[1] if t.dim() == 2 else t.numel() // max(img_tensor.shape[0], 1)
         return F_ssm.flow_pack(img_tensor, flow_pred_tensor, t, n_timesteps=n)
 
     def extract_outputs(self, output_tensor):

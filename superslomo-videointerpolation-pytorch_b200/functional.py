@@ -128,6 +128,20 @@ def _t_vector(t, count, device):
     return t.contiguous()
 
 
+def _empty_result(shape, out, *inputs):
+    """An empty batch (B = 0 or N = 0): the reference's torch ops return an empty tensor whose gradients are empty
+    too (scripts/models/layers.py:73-120 on a 0 x C x H x W input); nothing to launch.  The result stays attached
+    to the inputs' graph."""
+    if out is not None:
+        return out
+    like = inputs[0]
+    res = torch.zeros(shape, dtype=like.dtype, device=like.device)
+    for t in inputs:
+        if isinstance(t, torch.Tensor) and t.requires_grad:
+            res = res + t.sum() * 0
+    return res
+
+
 class _NoCtx:
     """stand-in for the autograd context when a forward is called directly with out= (inference)"""
 
@@ -201,6 +215,8 @@ def warp(x, flo, coord_mode=None, packed=None):
     """Backward-warp image x (B x C x H x W) by flow flo (B x 2 x H x W; channel 0 horizontal).  packed: the RGBx
     copy of a 3-channel x (pack_image), for callers that warp the same image by several flows: one 16-byte gather
     per bilinear tap instead of three 4-byte ones; gradients still flow to x."""
+    if x.shape[0] == 0 and x.is_cuda:
+        return _empty_result(x.shape, None, x, flo)
     return _Warp.apply(x, flo, _resolve_mode(coord_mode), packed)
 
 
@@ -312,6 +328,8 @@ def flow_pack(img6, flow4, t, n_timesteps=1, coord_mode=None, packed=None, out=N
     pack_frames(img6) to share the RGBx copy between flow_pack and fuse.  out: optional caller-owned
     result buffer (inference only)."""
     B = img6.shape[0]
+    if B * int(n_timesteps) == 0 and img6.is_cuda:
+        return _empty_result((B, int(n_timesteps), 16) + tuple(img6.shape[2:]), out, img6, flow4)
     tvec = _t_vector(t, B * n_timesteps, img6.device)
     if out is not None:
         _no_grad_for_out(out, "flow_pack", img6, flow4)
@@ -427,6 +445,8 @@ def fuse(img6, in16, out5, t, coord_mode=None, packed=None, out=None):
     """Fused frames for every (pair, timestep): img6 B x 6, in16 B x N x 16, out5 B x N x 5 -> B x N x 3.
     out: optional caller-owned result buffer (inference only)."""
     B, N = in16.shape[0], in16.shape[1]
+    if B * N == 0 and img6.is_cuda:
+        return _empty_result((B, N, 3) + tuple(img6.shape[2:]), out, img6, in16, out5)
     tvec = _t_vector(t, B * N, img6.device)
     if out is not None:
         _no_grad_for_out(out, "fuse", img6, in16, out5)
@@ -525,6 +545,8 @@ def fuse_from_flow(img6, flow4, out5, t, coord_mode=None, packed=None, out=None)
     the 16-channel tensor back; gradients go to flow4 directly.  A bf16 out5 (the U-Net output under bf16
     autocast) next to fp32 frames and flows is read as it is (inference only)."""
     B, N = out5.shape[0], out5.shape[1]
+    if B * N == 0 and img6.is_cuda:
+        return _empty_result((B, N, 3) + tuple(img6.shape[2:]), out, img6, flow4, out5)
     tvec = _t_vector(t, B * N, img6.device)
     if out5.dtype == torch.bfloat16 and img6.dtype == torch.float32:
         return _fuse_from_flow_mixed(img6, flow4, out5, tvec, _resolve_mode(coord_mode), packed, out)

@@ -806,3 +806,37 @@ def test_image_gradient_when_every_pixel_lands_on_one_cell(H, W):
     again = _dev(img, True)
     ssm_b200.warp(again, f).backward(_dev(gout))
     assert torch.equal(again.grad, x.grad)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_empty_batch_matches_the_reference_ops():
+    """A 0 x C x H x W batch: the reference's torch ops return empty tensors with empty gradients (checked against the
+    reference itself on CPU in the build container and, here, against its restated ops on the device); nothing is
+    launched, shapes and gradient shapes are the reference's."""
+    H, W = 8, 12
+    x = torch.zeros((0, 3, H, W), device=DEV, requires_grad=True)
+    f = torch.zeros((0, 2, H, W), device=DEV, requires_grad=True)
+    y = ssm_b200.warp(x, f)
+    ref = torch_oracle.warp(x.detach(), f.detach())
+    assert y.shape == ref.shape == (0, 3, H, W)
+    y.sum().backward()
+    assert x.grad.shape == x.shape and f.grad.shape == f.shape
+    ops = ssm_b200.SynthesisMixin()
+    img = torch.zeros((0, 6, H, W), device=DEV, requires_grad=True)
+    flow = torch.zeros((0, 4, H, W), device=DEV, requires_grad=True)
+    t = torch.zeros((0, 1, 1, 1), device=DEV)
+    in16 = ops.compute_inputs(img, flow, t)
+    assert in16.shape == torch_oracle.compute_inputs(img.detach(), flow.detach(), t).shape == (0, 16, H, W)
+    out5 = torch.zeros((0, 5, H, W), device=DEV, requires_grad=True)
+    frame = ops.compute_output_image(img, in16, out5, t)
+    assert frame.shape == (0, 3, H, W)
+    frame.sum().backward()
+    assert flow.grad.shape == flow.shape and out5.grad.shape == out5.shape and img.grad.shape == img.shape
+    # timestep-batched forms: no pairs, or no timesteps
+    assert ops.compute_inputs_batched(img, flow, torch.zeros((0, 7), device=DEV)).shape == (0, 7, 16, H, W)
+    img1 = torch.zeros((2, 6, H, W), device=DEV)
+    flow1 = torch.zeros((2, 4, H, W), device=DEV)
+    assert ssm_b200.fuse_from_flow(img1, flow1, torch.zeros((2, 0, 5, H, W), device=DEV), torch.zeros((2, 0), device=DEV)).shape == (2, 0, 3, H, W)
+    # a caller-owned result buffer comes back as it is
+    buf = torch.empty((0, 1, 16, H, W), device=DEV)
+    assert ssm_b200.flow_pack(img.detach(), flow.detach(), t, out=buf) is buf

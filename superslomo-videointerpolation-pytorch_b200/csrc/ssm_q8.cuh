@@ -327,6 +327,14 @@ quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_
 #define SSM_Q8_FUSE_PREFETCH 1     // U-Net output of timestep n+1 loaded during the gathers of timestep n: 1.85 ms; without it
                                    // 2.10 ms at 3 CTAs/SM and 1.99 ms at 4 (profiles/r03c_q8_timing_fuse_prefetch_*.json)
 #endif
+// Experiment (off): the gathers of timestep n+1 are issued before the interpolation of timestep n (a whole loop trip in
+// flight); only the fractional weights, the in-frame weight and the logit travel with the entries.  102-127 registers
+// (2 CTAs/SM) or 80 with spills (3 CTAs/SM).  Measured SLOWER: 1.91 ms shipped -> 2.53 ms (2 CTAs/SM) / 2.27 ms (3, spilling);
+// the shipped loop at 2 CTAs/SM takes 2.63 ms -- the kernel needs its 24 warps per SM more than a longer load-to-use
+// distance (profiles/r04e_q8_timing_fuse_*.json, tools/gpu_exp15.sh).
+#ifndef SSM_Q8_FUSE_PIPE
+#define SSM_Q8_FUSE_PIPE 0
+#endif
 #ifndef SSM_Q8_FUSE_U8_MIN_BLOCKS
 #define SSM_Q8_FUSE_U8_MIN_BLOCKS 3
 #endif
@@ -404,6 +412,38 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
 //     U-Net output.  OUT_U8: the fused frame is de-normalised and written as uint8 H_out x W_out x 3 images
 //     (crop at (top, left)) with the arithmetic of frames_to_u8_kernel, instead of as fp32 planes.
 // =============================================================================================
+#if SSM_Q8_FUSE_PIPE
+struct QFrac2 { f2 wx1, wy1, wsum; unsigned idx[2]; bool ok[2]; };
+template <int MODE>
+__device__ __forceinline__ QFrac2 make_qfrac2(f2 posx, f2 posy, f2 u, f2 v, const Geom& g, unsigned xbias) {   // make_qtap2 without the corner products
+    const f2 ix = sample_coord2<MODE>(posx, u, g.xnorm, g.xinv, g.xm1);
+    const f2 iy = sample_coord2<MODE>(posy, v, g.ynorm, g.yinv, g.ym1);
+    const f2 rx = __fadd2_rd(ix, bc2(Q8_FLOOR_MAGIC)), ry = __fadd2_rd(iy, bc2(Q8_FLOOR_MAGIC));
+    const f2 fx = add2(rx, bc2(-Q8_FLOOR_MAGIC)), fy = add2(ry, bc2(-Q8_FLOOR_MAGIC));
+    QFrac2 t;
+    t.wx1 = make_float2(__saturatef(ix.x - fx.x), __saturatef(ix.y - fx.y));
+    t.wy1 = make_float2(__saturatef(iy.x - fy.x), __saturatef(iy.y - fy.y));
+    const float Wf = g.xm1 + 1.0f, Hf = g.ym1 + 1.0f;
+    const f2 sx = make_float2(fminf(__saturatef(ix.x + 1.0f), __saturatef(Wf - ix.x)), fminf(__saturatef(ix.y + 1.0f), __saturatef(Wf - ix.y)));
+    const f2 sy = make_float2(fminf(__saturatef(iy.x + 1.0f), __saturatef(Hf - iy.x)), fminf(__saturatef(iy.y + 1.0f), __saturatef(Hf - iy.y)));
+    t.wsum = mul2(sx, sy);
+    t.ok[0] = t.wsum.x > 0.0f; t.ok[1] = t.wsum.y > 0.0f;
+    const unsigned w1 = (unsigned)(g.W + 1);
+    t.idx[0] = ((unsigned)__float_as_int(ry.x) - (unsigned)(Q8_FLOOR_BITS - 1)) * w1 + ((unsigned)__float_as_int(rx.x) - xbias);
+    t.idx[1] = ((unsigned)__float_as_int(ry.y) - (unsigned)(Q8_FLOOR_BITS - 1)) * w1 + ((unsigned)__float_as_int(rx.y) - xbias);
+    return t;
+}
+__device__ __forceinline__ QTap2 corner_weights(f2 wx1, f2 wy1, f2 wsum) {
+    QTap2 t;
+    const f2 wx0 = sub2(bc2(1.0f), wx1), wy0 = sub2(bc2(1.0f), wy1);
+    t.wnw = mul2(wx0, wy0); t.wne = mul2(wx1, wy0); t.wsw = mul2(wx0, wy1); t.wse = mul2(wx1, wy1);
+    t.wsum = wsum;
+    return t;
+}
+// a timestep whose gathers are in flight
+struct FuseStage { uint4 q0a, q0b, q1a, q1b; f2 wx0, wy0, ws0, wx1, wy1, ws1, y0; float tt; };
+#endif
+
 struct U8Out {
     unsigned char* dst; long long frame_stride; int row_stride;    // frame index = b * N + n
     int top, left, H_out, W_out, bgr, saturate;
@@ -426,6 +466,55 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<co
     const TY* __restrict__ Y = out5.p + ti.b * out5.sb + p;
     T* __restrict__ O = OUT_U8 ? nullptr : out3.p + ti.b * out3.sb + p;
     const f2 posx = make_float2((float)ti.x, (float)(ti.x + 1)), posy = bc2((float)ti.y);
+#if SSM_Q8_FUSE_PIPE
+    f2 ys[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
+    // gather half of timestep m: coordinates and the four entry loads; starts the streaming loads of timestep m + 1
+    auto gather = [&](int m) {
+        FuseStage st;
+        st.tt = __ldg(tp + m);
+        const Coef k = make_coef(st.tt);
+        const f2 y1 = ys[1], y2 = ys[2], y3 = ys[3], y4 = ys[4];
+        st.y0 = ys[0];
+        if (m + 1 < N) {
+            Y += out5.sn;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ys[c] = lds2(Y + c * ysc);
+        }
+        const f2 f1x = add2x(storage_round2<T>(est2_t1(k, f01x, f10x)), y1);                  // :412
+        const f2 f1y = add2x(storage_round2<T>(est2_t1(k, f01y, f10y)), y2);
+        const f2 f0x = add2x(storage_round2<T>(est2_t0(k, f01x, f10x)), y3);                  // :413
+        const f2 f0y = add2x(storage_round2<T>(est2_t0(k, f01y, f10y)), y4);
+        const QFrac2 t0 = make_qfrac2<MODE>(posx, posy, f0x, f0y, g, xb0);                          // :416
+        st.q0a = load_entry(quads, t0.idx[0], t0.ok[0]); st.q0b = load_entry(quads, t0.idx[1], t0.ok[1]);
+        const QFrac2 t1 = make_qfrac2<MODE>(posx, posy, f1x, f1y, g, xb1);                          // :418
+        st.q1a = load_entry(quads, t1.idx[0], t1.ok[0]); st.q1b = load_entry(quads, t1.idx[1], t1.ok[1]);
+        st.wx0 = t0.wx1; st.wy0 = t0.wy1; st.ws0 = t0.wsum; st.wx1 = t1.wx1; st.wy1 = t1.wy1; st.ws1 = t1.wsum;
+        return st;
+    };
+    FuseStage cur = gather(0);
+    for (int n = 0; n < N; ++n) {
+        FuseStage nxt = cur;
+        if (n + 1 < N) nxt = gather(n + 1);
+        const float tt = cur.tt;
+        const float omt_ = __fsub_rn(1.0f, tt);
+        struct { float omt; } k = {omt_};
+        const f2 y0 = cur.y0;
+        const QTap2 t0 = corner_weights(cur.wx0, cur.wy0, cur.ws0), t1 = corner_weights(cur.wx1, cur.wy1, cur.ws1);
+        const uint4 q0a = cur.q0a, q0b = cur.q0b, q1a = cur.q1a, q1b = cur.q1b;
+        cur = nxt;
+        const f2 e = mul2(y0, bc2(-1.4426950408889634f));
+        const f2 d = add2(make_float2(ex2_approx(e.x), ex2_approx(e.y)), bc2(1.0f));
+        const f2 v1 = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+        const f2 v0 = sub2(bc2(1.0f), v1);
+        const f2 a0 = mul2(bc2(k.omt), v0), a1 = mul2(bc2(tt), v1);
+        const f2 z = add2(a0, a1);
+        const f2 rz = make_float2(rcp_approx(z.x), rcp_approx(z.y));                           // 1/Z  :425
+        f2 s0[3], s1[3], res[3];
+        q8_sample2(q0a, q0b, t0, nm, s0);
+        q8_sample2(q1a, q1b, t1, nm, s1);
+#else
     f2 ys[5];
 #if SSM_Q8_FUSE_PREFETCH
 #pragma unroll
@@ -466,6 +555,7 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<co
         f2 s0[3], s1[3], res[3];
         q8_sample2(q0a, q0b, t0, nm, s0);
         q8_sample2(q1a, q1b, t1, nm, s1);
+#endif
 #pragma unroll
         for (int c = 0; c < 3; ++c) res[c] = mul2(fma2(a1, s1[c], mul2(a0, s0[c])), rz);       // :420-427
         if (OUT_U8) {

@@ -29,6 +29,13 @@
 #ifndef SSM_Q8_DIFF_FORM
 #define SSM_Q8_DIFF_FORM 0
 #endif
+// Experiment (off): with bf16 storage, sample at x + flow instead of reproducing the reference's normalise / de-normalise
+// round trip bit for bit (40 of ~140 packed operations per timestep).  bf16 path 4.16 -> 3.92 ms (0.46 -> 0.49 of the HBM
+// peak), 3.87 ms with the difference form on top: the bf16 kernels are not bound by that arithmetic either, and the
+// coordinate modes would stop meaning anything for one dtype -- not shipped (profiles/r04f_bf16_*.json, tools/gpu_exp16.sh).
+#ifndef SSM_Q8_BF16_DIRECT_COORD
+#define SSM_Q8_BF16_DIRECT_COORD 0
+#endif
 
 namespace ssm {
 
@@ -133,10 +140,13 @@ constexpr float Q8_FLOOR_MAGIC = 12582912.0f;       // 1.5 * 2^23: ulp 1 on [2^2
 constexpr int Q8_FLOOR_BITS = 0x4B400000;
 
 // xbias = bit pattern of the floor constant - 1 - index of the frame's first entry in the launch-wide table (q8_xbias)
-template <int MODE>
+template <int MODE, bool DIRECT = false>
 __device__ __forceinline__ QTap2 make_qtap2(f2 posx, f2 posy, f2 u, f2 v, const Geom& g, unsigned xbias) {
-    const f2 ix = sample_coord2<MODE>(posx, u, g.xnorm, g.xinv, g.xm1);
-    const f2 iy = sample_coord2<MODE>(posy, v, g.ynorm, g.yinv, g.ym1);
+    // DIRECT (bf16 storage): the sampling coordinate is x + flow.  The reference's normalise / de-normalise round trip
+    // (layers.py:100-112) is the identity up to ~4 roundings (< 3e-4 px at 2048); a flow stored in bf16 is itself only
+    // known to 2^-9 relative (0.06-0.25 px at 32-128 px), so reproducing those roundings bit for bit buys nothing there.
+    const f2 ix = DIRECT ? add2(posx, u) : sample_coord2<MODE>(posx, u, g.xnorm, g.xinv, g.xm1);
+    const f2 iy = DIRECT ? add2(posy, v) : sample_coord2<MODE>(posy, v, g.ynorm, g.yinv, g.ym1);
     // floor without the conversion unit: RD(ix + 1.5 * 2^23) is floor(ix) + 1.5 * 2^23 exactly for |ix| < 2^22, its low
     // mantissa bits are the integer, and subtracting the constant gives floor(ix) as a float.
     const f2 rx = __fadd2_rd(ix, bc2(Q8_FLOOR_MAGIC)), ry = __fadd2_rd(iy, bc2(Q8_FLOOR_MAGIC));
@@ -167,6 +177,10 @@ __device__ __forceinline__ QTap2 make_qtap2(f2 posx, f2 posy, f2 u, f2 v, const 
     t.idx[1] = ((unsigned)__float_as_int(ry.y) - (unsigned)(Q8_FLOOR_BITS - 1)) * w1 + ((unsigned)__float_as_int(rx.y) - xbias);
     return t;
 }
+
+// (experiment, see SSM_Q8_BF16_DIRECT_COORD; a shipped version would have to keep the reference's expression for 1-pixel
+// axes, which maps every sample of such an axis to coordinate 0)
+template <typename T> constexpr bool Q8_DIRECT = SSM_Q8_BF16_DIRECT_COORD && sizeof(T) == 2;
 
 // kept in a register for the whole kernel (the compiler otherwise recomputes the table offset, ~8 instructions, in front
 // of every gather)
@@ -372,9 +386,9 @@ flow_pack_fwd_q8_kernel(View<const T> img6, const uint4* __restrict__ quads, Vie
         }
         const f2 e0x = storage_round2<T>(est2_t0(k, f01x, f10x)), e0y = storage_round2<T>(est2_t0(k, f01y, f10y));   // F_t0  :353
         const f2 e1x = storage_round2<T>(est2_t1(k, f01x, f10x)), e1y = storage_round2<T>(est2_t1(k, f01y, f10y));   // F_t1  :356
-        const QTap2 t1 = make_qtap2<MODE>(posx, posy, e1x, e1y, g, xb1);                             // warp(img_1, F_t1) :361
+        const QTap2 t1 = make_qtap2<MODE, Q8_DIRECT<T>>(posx, posy, e1x, e1y, g, xb1);                             // warp(img_1, F_t1) :361
         const uint4 q1a = load_entry(quads, t1.idx[0], t1.ok[0]), q1b = load_entry(quads, t1.idx[1], t1.ok[1]);
-        const QTap2 t0 = make_qtap2<MODE>(posx, posy, e0x, e0y, g, xb0);                             // warp(img_0, F_t0) :362
+        const QTap2 t0 = make_qtap2<MODE, Q8_DIRECT<T>>(posx, posy, e0x, e0y, g, xb0);                             // warp(img_0, F_t0) :362
         const uint4 q0a = load_entry(quads, t0.idx[0], t0.ok[0]), q0b = load_entry(quads, t0.idx[1], t0.ok[1]);
         f2 w1[3], w0[3];
         q8_sample2(q1a, q1b, t1, nm, w1);
@@ -540,9 +554,9 @@ fuse_fwd_q8_kernel(const uint4* __restrict__ quads, View<const T> flow4, View<co
         const f2 f1y = add2x(storage_round2<T>(est2_t1(k, f01y, f10y)), y2);
         const f2 f0x = add2x(storage_round2<T>(est2_t0(k, f01x, f10x)), y3);                  // :413
         const f2 f0y = add2x(storage_round2<T>(est2_t0(k, f01y, f10y)), y4);
-        const QTap2 t0 = make_qtap2<MODE>(posx, posy, f0x, f0y, g, xb0);                            // :416
+        const QTap2 t0 = make_qtap2<MODE, Q8_DIRECT<T>>(posx, posy, f0x, f0y, g, xb0);                            // :416
         const uint4 q0a = load_entry(quads, t0.idx[0], t0.ok[0]), q0b = load_entry(quads, t0.idx[1], t0.ok[1]);
-        const QTap2 t1 = make_qtap2<MODE>(posx, posy, f1x, f1y, g, xb1);                            // :418
+        const QTap2 t1 = make_qtap2<MODE, Q8_DIRECT<T>>(posx, posy, f1x, f1y, g, xb1);                            // :418
         const uint4 q1a = load_entry(quads, t1.idx[0], t1.ok[0]), q1b = load_entry(quads, t1.idx[1], t1.ok[1]);
         // V_t<-1 = sigmoid(out[:, 0]) (:386-388) as 1 / (1 + 2^(-x log2 e)); V_t<-0 = 1 - V_t<-1 (:390)
         const f2 e = mul2(y0, bc2(-1.4426950408889634f));

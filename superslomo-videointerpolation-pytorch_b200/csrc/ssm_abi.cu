@@ -125,11 +125,8 @@ unsigned sw_grid(int B, int H, int W) {      // one CTA per 64 x 16 tile of sour
     return (unsigned)((long long)B * ((H + SW_TILE_H - 1) / SW_TILE_H) * ((W + SW_TILE_W - 1) / SW_TILE_W));
 }
 
-unsigned finalize_grid(long long total) {
-    long long blocks = (total + 255) / 256;
-    long long cap = 148ll * 16;
-    return (unsigned)(blocks < cap ? blocks : cap);
-}
+// scatter_finalize_kernel: planes x chunks of FIN_THREADS * FIN_PER_THREAD pixels (check_common bounds H*W and the tile count)
+unsigned finalize_chunks(long long npx) { return (unsigned)((npx + FIN_THREADS * FIN_PER_THREAD - 1) / (FIN_THREADS * FIN_PER_THREAD)); }
 
 // ---------------------------------------------------------------------------------------------
 // packed != NULL: the image is the RGBx copy (B x H x W x 4, C = 3); img is then unused by the gathers
@@ -189,8 +186,8 @@ struct WarpBwd {
                 warp_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
                     cview<T>(gout), cview<T>(flow), acc, C, g, hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (scatter)");
-            const long long total = (long long)B * C * npx;
-            scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg), C, npx, total, hdr, cb);
+            if ((long long)B * C * finalize_chunks(npx) > 2147483647ll) return fail(SSM_ERR_SHAPE, "ssm_warp_bwd: B*C*H*W too large for one finalise launch");
+            scatter_finalize_kernel<T><<<(unsigned)(B * C) * finalize_chunks(npx), FIN_THREADS, 0, s>>>(acc, nullptr, mview<T>(gimg), C, npx, finalize_chunks(npx), hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (finalize)");
         }
         return SSM_OK;
@@ -270,8 +267,7 @@ struct PackBwd {
         flow_pack_scatter_kernel<T, MODE><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(
             cview<T>(g16), cview<T>(flow4), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_flow_pack_bwd (scatter)");
-        const long long total = (long long)B * 6 * npx;
-        scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, direct, mview<T>(gimg6), 6, npx, total, hdr, cb);
+        scatter_finalize_kernel<T><<<(unsigned)(B * 6) * finalize_chunks(npx), FIN_THREADS, 0, s>>>(acc, direct, mview<T>(gimg6), 6, npx, finalize_chunks(npx), hdr, cb);
         SSM_LAUNCH_CHECK("ssm_flow_pack_bwd (finalize)");
         return SSM_OK;
     }
@@ -333,8 +329,7 @@ struct FuseBwd {
         fuse_scatter_kernel<T, MODE, RECOMP><<<sw_grid(B, H, W), SW_THREADS, 0, s>>>(
             cview<T>(g3), cview<T>(flows4), cview<T>(out5), t, acc, N, g, hdr, cb);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd (scatter)");
-        const long long total = (long long)B * 6 * npx;
-        scatter_finalize_kernel<T><<<finalize_grid(total), 256, 0, s>>>(acc, nullptr, mview<T>(gimg6), 6, npx, total, hdr, cb);
+        scatter_finalize_kernel<T><<<(unsigned)(B * 6) * finalize_chunks(npx), FIN_THREADS, 0, s>>>(acc, nullptr, mview<T>(gimg6), 6, npx, finalize_chunks(npx), hdr, cb);
         SSM_LAUNCH_CHECK("ssm_fuse_bwd (finalize)");
         return SSM_OK;
     }

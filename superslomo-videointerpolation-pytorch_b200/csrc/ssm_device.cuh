@@ -232,8 +232,16 @@ struct ScatterHdr {          // lives at the start of the workspace, zeroed befo
 // Must be reached by all 32 lanes of the warp.  m >= 0, or NaN whose bits compare above every
 // finite value and poison the result.
 __device__ __forceinline__ void record_absmax(unsigned int* slot, float m) {
+#ifdef SSM_EXP_NO_ABSMAX       // timing experiment only (wrong scale): what the recording itself costs
+    if (m < -1.0f) *slot = 0u;
+    return;
+#endif
     unsigned int bits = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(m)));
-    if ((threadIdx.x & 31) == 0 && bits > __ldcg(slot)) atomicMax(slot, bits);
+    // The pre-check reads through L1 (ld.ca): a stale value is only ever too SMALL (the slot grows monotonically), which
+    // costs a redundant atomicMax, never a wrong result.  Read from L2 (ld.cg) the one address took a request from every
+    // warp of the launch -- 1 M requests on one L2 sector at 16 x 1088 x 1920, 1.5 ms of a 5.3 ms kernel
+    // (profiles/r04g_bwd_timing_*.json).
+    if ((threadIdx.x & 31) == 0 && bits > __ldca(slot)) atomicMax(slot, bits);
 }
 
 }  // namespace ssm

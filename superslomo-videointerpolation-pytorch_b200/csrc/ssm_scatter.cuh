@@ -10,19 +10,22 @@
 //      (integer atomicMax on the bit pattern: order-independent);
 //   2. scale = 2^k puts that maximum in [2^28, 2^29): a contribution rn(weight*grad) * 2^k (exact) is rounded
 //      ONCE to a 32-bit integer, 29 bits below the largest possible one;
-//   3. SEGMENTED accumulation (round 2): a CTA owns a 64 x 16 tile of source pixels and, per frame and
-//      timestep, a shared-memory window of int32 accumulators covering the tile shifted by the displacement of
-//      its centre pixel plus an 8-pixel halo.  Contributions that land in the window -- nearly all of them for
-//      a piecewise-smooth flow -- are added with shared-memory integer atomics; the few that fall outside go
-//      to the 64-bit global accumulators directly.  After the tile's pixels are done the window's non-zero
-//      cells are flushed with ONE 64-bit global atomic each (about a quarter of the contributions: a cell
-//      collects four taps on average).  int32 wrap-around is exact modulo 2^32 and every add checks its own
-//      overflow (the atomic returns the previous value), correcting the global cell by +-2^32, so the sums
-//      are exact whatever the data;
+//   3. SEGMENTED accumulation (round 2): a CTA owns a 64 x 16 tile of source pixels and, per frame, a shared-memory
+//      window of int32 accumulators covering the tile shifted by the displacement of its centre pixel plus a 12-pixel
+//      halo.  Contributions that land in the window -- nearly all of them for a piecewise-smooth flow -- are added
+//      with shared-memory integer atomics; the few that fall outside go to the 64-bit global accumulators directly.
+//      The window SURVIVES the timesteps of a frame: it is flushed (one 64-bit global atomic per non-zero cell) and
+//      re-anchored only when the centre displacement has drifted more than SW_DRIFT pixels from its origin, and at the
+//      end of the frame -- for the flows of one pair at N = 7 that is once per frame instead of seven times.  int32
+//      wrap-around is exact modulo 2^32 and every add checks its own overflow (the atomic returns the previous value),
+//      correcting the global cell by +-2^32, so the sums are exact whatever the data;
 //   4. a finalise pass converts the 64-bit sums back (and adds the direct, non-warped gradient terms).
 //
 // Measured (tools/exp_scatter.cu, profiles/r02k_exp_scatter.jsonl; 16 pairs x 2 frames x 7 timesteps at
 // 1088x1920): global 64-bit atomics alone 19.5 ms (rough flow) / 10.1 ms (smooth); windowed 8.5 / 7.6 ms.
+// The shipped kernels (tools/exp_bwd_timing.py, profiles/r04h-r04j): one flush per (frame, timestep) 10.9 / 9.7 ms,
+// windows kept across the timesteps of a frame 7.8 / 7.3 ms (halo 12; halo 8: 8.2 / 7.6; a drift limit of 12, 16, 24 px
+// or none: the same on these fields -- the limit is there for flows that sweep far over the N timesteps).
 #pragma once
 #include "ssm_kernels.cuh"
 
@@ -52,10 +55,14 @@ __device__ __forceinline__ void fx_add(long long* dst, float contrib, float scal
 #endif
 constexpr int SW_TILE_W = 64, SW_TILE_H = SSM_SW_TILE_H;  // source pixels per CTA: 256 threads x (SW_TILE_H / 4) rows
 #ifndef SSM_SW_HALO
-#define SSM_SW_HALO 8
+#define SSM_SW_HALO 12
 #endif
 constexpr int SW_HALO = SSM_SW_HALO;
-constexpr int SW_W = SW_TILE_W + 2 * SW_HALO, SW_H = SW_TILE_H + 2 * SW_HALO, SW_PLANE = SW_W * SW_H;   // 80 x 32 cells
+#ifndef SSM_SW_DRIFT
+#define SSM_SW_DRIFT SSM_SW_HALO       // re-anchor a frame's window when its centre displacement has moved further than this
+#endif
+constexpr int SW_DRIFT = SSM_SW_DRIFT;
+constexpr int SW_W = SW_TILE_W + 2 * SW_HALO, SW_H = SW_TILE_H + 2 * SW_HALO, SW_PLANE = SW_W * SW_H;   // 88 x 40 cells x 3 planes: 42 KB
 constexpr int SW_THREADS = 256;
 #ifndef SSM_SW_MIN_BLOCKS
 #define SSM_SW_MIN_BLOCKS 4        // 64 registers; the kernels are latency-bound at 2 CTAs per SM (119 registers, profiles/r02p)
@@ -198,6 +205,42 @@ __device__ __forceinline__ void sw_phase(int* win, volatile int* s_org, const Sw
     // s_org before the barrier above
 }
 
+// One timestep of a frame whose window is kept across timesteps (compute_inputs / compute_output_image backward): the
+// window is flushed and re-anchored only when the displacement of the tile's centre pixel has drifted more than SW_DRIFT
+// pixels from the window's origin (first timestep: anchored).  s_org (4 ints) is double-buffered by the timestep parity;
+// `have` / (ox, oy) are uniform over the CTA.  The caller flushes after the frame's last timestep.
+template <typename PixelFn>
+__device__ __forceinline__ void sw_timestep(int* win, volatile int* s_org, int parity, const SwTile& ti, const Geom& g, float scale,
+                                              long long* __restrict__ plane0, long long npx, bool& have, int& ox, int& oy,
+                                              PixelFn&& pixel) {
+    volatile int* so = s_org + 2 * parity;
+    if (ti.lx == SW_CENTRE_LX && ti.ly == (SW_CENTRE_ROW & 3)) {
+        const int x = min(ti.x0 + SW_CENTRE_LX, g.W - 1), y = min(ti.y0 + SW_CENTRE_ROW, g.H - 1);
+        Taps t; float gv[3];
+        pixel(x, y, t, gv);
+        so[0] = (int)t.fx - (x - ti.x0) - SW_HALO;
+        so[1] = (int)t.fy - (y - ti.y0) - SW_HALO;
+    }
+    __syncthreads();                         // candidate origin visible; the previous phase's adds are complete
+    const int cx = so[0], cy = so[1];
+    if (!have || abs(cx - ox) > SW_DRIFT || abs(cy - oy) > SW_DRIFT) {
+        if (have) {
+            sw_flush(win, ox, oy, plane0, npx, g.H, g.W);
+            __syncthreads();                 // the window is zero again before anything is added at the new origin
+        }
+        ox = cx; oy = cy; have = true;
+    }
+#pragma unroll 1
+    for (int j = 0; j < SW_TILE_H / 4; ++j) {
+        const int x = ti.x0 + ti.lx, y = ti.y0 + ti.ly + 4 * j;
+        if (x < g.W && y < g.H) {
+            Taps t; float gv[3];
+            pixel(x, y, t, gv);
+            sw_splat3(win, ox, oy, t, gv, scale, plane0, npx, g.W);
+        }
+    }
+}
+
 __device__ __forceinline__ void sw_clear(int* win) {
     int4* w4 = reinterpret_cast<int4*>(win);
     for (int i = threadIdx.x; i < 3 * SW_PLANE / 4; i += SW_THREADS) w4[i] = make_int4(0, 0, 0, 0);
@@ -271,7 +314,7 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
                          long long* __restrict__ acc, int N, Geom g,
                          const ScatterHdr* __restrict__ hdr, int count_bits) {
     __shared__ __align__(16) int win[3 * SW_PLANE];
-    __shared__ int s_org[2];
+    __shared__ int s_org[4];
     const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);
     const long long npx = (long long)g.H * g.W;
@@ -279,11 +322,13 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
     const T* F = flow4.p + ti.b * flow4.sb;
     const int fsc = (int)flow4.sc, gsc = (int)g16.sc;
     long long* a0 = acc + (long long)ti.b * 6 * npx;      // I0 planes 0-2, I1 planes 3-5
-    for (int n = 0; n < N; ++n) {
-        const Coef k = make_coef(__ldg(tv + ti.b * N + n));
-        const T* G = g16.p + ti.b * g16.sb + n * g16.sn;
-        for (int frame = 0; frame < 2; ++frame) {
-            sw_phase(win, s_org, ti, g, scale, a0 + frame * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
+    for (int frame = 0; frame < 2; ++frame) {
+        bool have = false; int ox = 0, oy = 0;
+        long long* plane0 = a0 + frame * 3 * npx;
+        for (int n = 0; n < N; ++n) {
+            const Coef k = make_coef(__ldg(tv + ti.b * N + n));
+            const T* G = g16.p + ti.b * g16.sb + n * g16.sn;
+            sw_timestep(win, s_org, n & 1, ti, g, scale, plane0, npx, have, ox, oy, [&](int x, int y, Taps& t, float (&gv)[3]) {
                 const int p = y * g.W + x;
                 const float f01x = ldg_(F + p), f01y = ldg_(F + fsc + p), f10x = ldg_(F + 2 * fsc + p), f10y = ldg_(F + 3 * fsc + p);
                 if (frame) t = make_taps<MODE>(x, y, storage_round<T>(est_t1(k, f01x, f10x)), storage_round<T>(est_t1(k, f01y, f10y)), g);
@@ -293,6 +338,8 @@ flow_pack_scatter_kernel(View<const T> g16, View<const T> flow4, const float* __
                 for (int c = 0; c < 3; ++c) gv[c] = lds_(gp + c * gsc);
             });
         }
+        __syncthreads();                     // every add of the frame's last timestep is in the window
+        if (have) sw_flush(win, ox, oy, plane0, npx, g.H, g.W);
     }
 }
 
@@ -305,21 +352,23 @@ fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
                     const float* __restrict__ tv, long long* __restrict__ acc, int N, Geom g,
                     const ScatterHdr* __restrict__ hdr, int count_bits) {
     __shared__ __align__(16) int win[3 * SW_PLANE];
-    __shared__ int s_org[2];
+    __shared__ int s_org[4];
     const SwTile ti = sw_tile(g.H, g.W);
     const float scale = scatter_scale(hdr, count_bits);
     const long long npx = (long long)g.H * g.W;
     sw_clear(win);
     long long* a0 = acc + (long long)ti.b * 6 * npx;
     const int fsc = (int)flows4.sc, ysc = (int)out5.sc, gsc = (int)g3.sc;
-    for (int n = 0; n < N; ++n) {
-        const float tt = __ldg(tv + ti.b * N + n);
-        const float omt = __fsub_rn(1.0f, tt);
-        const T* X = flows4.p + ti.b * flows4.sb + (RECOMP ? 0 : n * flows4.sn);
-        const T* Y = out5.p + ti.b * out5.sb + n * out5.sn;
-        const T* G = g3.p + ti.b * g3.sb + n * g3.sn;
-        for (int frame = 0; frame < 2; ++frame) {
-            sw_phase(win, s_org, ti, g, scale, a0 + frame * 3 * npx, npx, [&](int x, int y, Taps& t, float (&gv)[3]) {
+    for (int frame = 0; frame < 2; ++frame) {
+        bool have = false; int ox = 0, oy = 0;
+        long long* plane0 = a0 + frame * 3 * npx;
+        for (int n = 0; n < N; ++n) {
+            const float tt = __ldg(tv + ti.b * N + n);
+            const float omt = __fsub_rn(1.0f, tt);
+            const T* X = flows4.p + ti.b * flows4.sb + (RECOMP ? 0 : n * flows4.sn);
+            const T* Y = out5.p + ti.b * out5.sb + n * out5.sn;
+            const T* G = g3.p + ti.b * g3.sb + n * g3.sn;
+            sw_timestep(win, s_org, n & 1, ti, g, scale, plane0, npx, have, ox, oy, [&](int x, int y, Taps& t, float (&gv)[3]) {
                 const int p = y * g.W + x;
                 float xs[4];
                 if (RECOMP) {
@@ -329,7 +378,6 @@ fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
 #pragma unroll
                     for (int k = 0; k < 4; ++k) xs[k] = ldg_(X + k * fsc + p);
                 }
-                // xs: F_t1.x, F_t1.y, F_t0.x, F_t0.y; out5 channels 1:3 refine F_t1, 3:5 refine F_t0 (:412-413)
                 const int o = frame ? 0 : 2;
                 const float fx = __fadd_rn(xs[o], ldg_(Y + (1 + o) * ysc + p));
                 const float fy = __fadd_rn(xs[o + 1], ldg_(Y + (2 + o) * ysc + p));
@@ -342,24 +390,53 @@ fuse_scatter_kernel(View<const T> g3, View<const T> flows4, View<const T> out5,
                 for (int c = 0; c < 3; ++c) gv[c] = kv * ldg_(G + c * gsc + p);
             });
         }
+        __syncthreads();                     // every add of the frame's last timestep is in the window
+        if (have) sw_flush(win, ox, oy, plane0, npx, g.H, g.W);
+        // the next frame's first barrier orders this flush before its adds
     }
 }
 
 // ---- finalise: fixed point -> storage type, plus the direct (non-warped) gradient if any --------
+// One CTA converts 1024 consecutive pixels of one plane, four per thread (32 bytes of accumulator in, 16 bytes of fp32
+// out); plane and chunk come from ONE 32-bit division per CTA.  (The first version was a grid-stride loop with two 64-bit
+// divisions per element: 0.83 ms for the 1.6 GB of accumulators of 16 pairs, 2.9 TB/s.)
+constexpr int FIN_THREADS = 256, FIN_PER_THREAD = 4;
+__device__ __forceinline__ void store4(float* o, const float (&r)[4]) { __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3])); }
+__device__ __forceinline__ void store4(__nv_bfloat16* o, const float (&r)[4]) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+    __stcs(reinterpret_cast<uint2*>(o), make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi)));
+}
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FIN_THREADS)
 scatter_finalize_kernel(const long long* __restrict__ acc, const float* __restrict__ direct,
-                        View<T> gimg, int C, long long npx, long long total,
+                        View<T> gimg, int C, long long npx, unsigned chunks_per_plane,
                         const ScatterHdr* __restrict__ hdr, int count_bits) {
     const float scale = scatter_scale(hdr, count_bits);
     const double inv = 1.0 / (double)scale;   // NaN scale poisons the output, as intended
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long bc = i / npx, p = i - bc * npx;
-        long long b = bc / C, c = bc - b * C;
-        float v = (float)((double)__ldcs(acc + i) * inv);
-        if (direct) v += __ldcs(direct + i);
-        sts_(gimg.p + b * gimg.sb + c * gimg.sc + p, v);
+    const unsigned plane = blockIdx.x / chunks_per_plane, chunk = blockIdx.x - plane * chunks_per_plane;
+    const unsigned b = plane / (unsigned)C, c = plane - b * (unsigned)C;
+    const long long p0 = ((long long)chunk * FIN_THREADS + threadIdx.x) * FIN_PER_THREAD;
+    if (p0 >= npx) return;
+    const long long* a = acc + (long long)plane * npx + p0;
+    const float* d = direct ? direct + (long long)plane * npx + p0 : nullptr;
+    T* o = gimg.p + b * gimg.sb + c * gimg.sc + p0;
+    const bool whole = p0 + FIN_PER_THREAD <= npx && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+                       (!d || (reinterpret_cast<uintptr_t>(d) & 15) == 0) &&
+                       (reinterpret_cast<uintptr_t>(o) & (FIN_PER_THREAD * sizeof(T) - 1)) == 0;
+    if (whole) {
+        const longlong2 v0 = __ldcs(reinterpret_cast<const longlong2*>(a)), v1 = __ldcs(reinterpret_cast<const longlong2*>(a) + 1);
+        float r[4] = {(float)((double)v0.x * inv), (float)((double)v0.y * inv), (float)((double)v1.x * inv), (float)((double)v1.y * inv)};
+        if (d) {
+            const float4 dd = __ldcs(reinterpret_cast<const float4*>(d));
+            r[0] += dd.x; r[1] += dd.y; r[2] += dd.z; r[3] += dd.w;
+        }
+        store4(o, r);
+    } else {
+        for (int k = 0; k < FIN_PER_THREAD && p0 + k < npx; ++k) {
+            float v = (float)((double)__ldcs(a + k) * inv);
+            if (d) v += __ldcs(d + k);
+            sts_(o + k, v);
+        }
     }
 }
 

@@ -69,8 +69,18 @@ def main():
         gw = torch.randn_like(yw)
         r["warp_bwd_flow_and_image"] = timed(lambda: torch.autograd.grad(yw, (xw, fw), gw, retain_graph=True))
         r["warp_kernels_ms"] = kernel_split(lambda: torch.autograd.grad(yw, (xw, fw), gw, retain_graph=True))
+        del yw, gw, xw, fw
+        # compute_inputs backward: flow gradient only / with the image gradient
+        ig, fg = img6.clone().requires_grad_(True), flow4.clone().requires_grad_(True)
+        in16 = ssm_b200.flow_pack(ig, fg, t, n_timesteps=N, packed=rgbx)
+        in16_no = ssm_b200.flow_pack(img6, fg, t, n_timesteps=N, packed=rgbx)
+        g16 = torch.randn_like(in16)
+        r["flow_pack_bwd_gather_only"] = timed(lambda: torch.autograd.grad(in16_no, (fg,), g16, retain_graph=True))
+        r["flow_pack_bwd_with_image_grad"] = timed(lambda: torch.autograd.grad(in16, (ig, fg), g16, retain_graph=True))
+        r["flow_pack_kernels_ms"] = kernel_split(lambda: torch.autograd.grad(in16, (ig, fg), g16, retain_graph=True))
+        del in16, in16_no, g16, ig, fg
         res[name] = r
-        del yw, gw, xw, fw, flow4, rgbx
+        del flow4, rgbx
         torch.cuda.empty_cache()
     print(json.dumps(res))
 

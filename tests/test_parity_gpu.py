@@ -809,6 +809,44 @@ def test_image_gradient_when_every_pixel_lands_on_one_cell(H, W):
 
 
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flow_px,uniform,N", [(6.0, False, 3), (90.0, False, 3), (6.0, True, 7)])
+def test_image_gradient_windows_across_timesteps(flow_px, uniform, N):
+    """The image-gradient windows of csrc/ssm_scatter.cuh are kept across the timesteps of a frame and re-anchored only
+    when the tile's centre displacement has drifted more than 12 px.  6 px flows: one window per frame serves all N
+    timesteps; 90 px flows: the displacement moves ~22 px per timestep at N = 3, so the window is flushed and re-anchored
+    between timesteps; a UNIFORM 6 px flow with a constant upstream gradient at N = 7 piles seven timesteps of same-sign,
+    near-maximal contributions on the cells of a kept window, which wraps its int32 cells (7 x 1.5 x 2^28 > 2^31): the
+    overflow repair must keep the sums exact.  Image gradients of compute_inputs and compute_output_image against the
+    float64 sum of the C oracle's per-timestep terms; run twice for bit identity."""
+    B, H, W = 1, 96, 256
+    img6, flow4, out5, t = _inputs(B, N, H, W, seed=4242, kind="smooth", flow_px=flow_px)
+    gen = torch.Generator().manual_seed(11)
+    g16 = torch.randn(B, N, 16, H, W, generator=gen)
+    g3 = torch.randn(B, N, 3, H, W, generator=gen)
+    if uniform:
+        flow4 = torch.zeros_like(flow4)
+        flow4[:, 0], flow4[:, 2] = flow_px, -flow_px      # F_0->1 = +6 px, F_1->0 = -6 px horizontally
+        out5 = out5 * 0.0
+        g16, g3 = torch.full_like(g16, 3.0), torch.full_like(g3, 3.0)
+    grads = []
+    for _ in range(2):
+        a, b = _dev(img6, True), _dev(flow4, True)
+        ssm_b200.flow_pack(a, b, _dev(t), n_timesteps=N).backward(_dev(g16))
+        a2, b2, yo = _dev(img6, True), _dev(flow4, True), _dev(out5, True)
+        ssm_b200.fuse_from_flow(a2, b2, yo, _dev(t)).backward(_dev(g3))
+        grads.append((a.grad.clone(), a2.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+    ref1, ref2 = [], []
+    for n in range(N):
+        tn = t[:, n]
+        r16 = c_oracle.compute_inputs(img6, flow4, tn)
+        ref1.append(c_oracle.compute_inputs_backward(g16[:, n].contiguous(), img6, flow4, tn)[0])
+        ref2.append(c_oracle.compute_output_image_backward(g3[:, n].contiguous(), img6, r16, out5[:, n].contiguous(), tn)[0])
+    assert_sum_close(grads[0][0], ref1, "compute_inputs grad img (flow %g px)" % flow_px)
+    assert_sum_close(grads[0][1], ref2, "compute_output_image grad img (flow %g px)" % flow_px)
+
+
+# ---------------------------------------------------------------------------------------------
 def test_empty_batch_matches_the_reference_ops():
     """A 0 x C x H x W batch: the reference's torch ops return empty tensors with empty gradients (checked against the
     reference itself on CPU in the build container and, here, against its restated ops on the device); nothing is

@@ -65,7 +65,7 @@ constexpr int SW_DRIFT = SSM_SW_DRIFT;
 constexpr int SW_W = SW_TILE_W + 2 * SW_HALO, SW_H = SW_TILE_H + 2 * SW_HALO, SW_PLANE = SW_W * SW_H;   // 88 x 40 cells x 3 planes: 42 KB
 constexpr int SW_THREADS = 256;
 #ifndef SSM_SW_MIN_BLOCKS
-#define SSM_SW_MIN_BLOCKS 4        // 64 registers; the kernels are latency-bound at 2 CTAs per SM (119 registers, profiles/r02p)
+#define SSM_SW_MIN_BLOCKS 4        // 64 registers: 7.8 ms; 3 CTAs/SM (80 registers) 9.2 ms, 5 (48, spilling) 8.8 ms (profiles/r04o); 2: 14.5 -> 9.9 ms in r02p
 #endif
 constexpr int SW_MIN_BLOCKS = SSM_SW_MIN_BLOCKS;
 constexpr int SW_CENTRE_LX = SW_TILE_W / 2, SW_CENTRE_ROW = SW_TILE_H / 2;

@@ -404,7 +404,9 @@ def main():
             stage_quads()
             if events:
                 events[1].record()
-            in16 = q8.flow_pack(img6, quads, f, t, norm, n_timesteps=NT, out=in16_buf)
+            # img6=None: the six pass-through channels are looked up from the tables' own bytes (bit-identical to reading
+            # the planar normalised frames, which this step then never touches)
+            in16 = q8.flow_pack(None, quads, f, t, norm, n_timesteps=NT, out=in16_buf, lut=lut)
             if events:
                 events[2].record()
             frames = q8.fuse_from_flow(quads, f, out5 if y is None else y, t, norm, out=frames_buf)

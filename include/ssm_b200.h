@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 7
+#define SSM_ABI_VERSION 8
 
 /* storage dtype of image/flow/output tensors; arithmetic is always fp32 */
 #define SSM_DTYPE_F32  0
@@ -255,6 +255,10 @@ int ssm_frames_to_u8(const ssm_tensor* planar, int F, int H, int W, int top, int
  * ssm_flow_pack_fwd_q8 [flow_interpolation.py:338-372]: img6 (B x 6 x H x W fp32, the normalised frames from
  *   ssm_frames_from_u8) is only read for the six pass-through channels; out16 B x N x 16 x H x W fp32.
  * ssm_flow_pack_fwd_q8_nhwc: the same written channels-last (B x N x H x W x 16, fp32 or bf16) as ssm_flow_pack_fwd_nhwc.
+ * ssm_flow_pack_fwd_q8_lut: ssm_flow_pack_fwd_q8 without img6 -- the pass-through channels are looked up from the tables'
+ *   own bytes through lut (DEVICE float[3][256], the normalised value of byte b in channel c: the table ssm_frames_from_u8
+ *   applies, so the values are the ones img6 would hold when the frames were padded with byte 0 BEFORE normalising).
+ *   The planar frames are not read: 5 % less DRAM traffic for the same result.
  * ssm_fuse_flow_fwd_q8 [flow_interpolation.py:374-429]: as ssm_fuse_flow_fwd(_mixed); out5 in out5_dtype (fp32 or bf16).
  * ssm_fuse_flow_fwd_q8_u8: the same with ssm_frames_to_u8 fused behind it: the fused frames are cropped,
  *   de-normalised and written as B*N uint8 images H_out x W_out x 3 (frame index b*N + n)
@@ -268,6 +272,9 @@ int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_te
 int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                               void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
                               int dtype, int coord_mode, void* stream);
+int ssm_flow_pack_fwd_q8_lut(const void* quads, const float* lut, const ssm_tensor* flow4, const float* t,
+                             const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode,
+                             void* stream);
 int ssm_fuse_flow_fwd_q8(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,
                          const ssm_tensor* out3, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode,
                          void* stream);

@@ -28,7 +28,7 @@ EXPORTS = (
     "ssm_synthesize_host", "ssm_synthesize_host_scratch_bytes", "ssm_selftest_division",
     "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
     "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to",
-    "ssm_quads_bytes", "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8",
+    "ssm_quads_bytes", "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_flow_pack_fwd_q8_lut", "ssm_fuse_flow_fwd_q8",
     "ssm_fuse_flow_fwd_q8_u8", "ssm_synthesize_host_u8", "ssm_synthesize_host_u8_scratch_bytes",
 )
 
@@ -89,6 +89,7 @@ def lib():
     L.ssm_quads_from_u8.argtypes = [V, LL, I, I, I, I, I, I, I, I, I, V, V]
     L.ssm_flow_pack_fwd_q8.argtypes = [P, V, P, V, P, F3, I, I, I, I, I, I, V]
     L.ssm_flow_pack_fwd_q8_nhwc.argtypes = [P, V, P, V, V, I, F3, I, I, I, I, I, I, V]
+    L.ssm_flow_pack_fwd_q8_lut.argtypes = [V, V, P, V, P, F3, I, I, I, I, I, I, V]
     L.ssm_fuse_flow_fwd_q8.argtypes = [V, P, P, I, V, P, F3, I, I, I, I, I, I, V]
     L.ssm_fuse_flow_fwd_q8_u8.argtypes = [V, P, P, I, V, V, LL, I, I, I, I, I, F3, F3, ctypes.c_float, I, I, F3, I, I, I, I, I, I, V]
     L.ssm_synthesize_host_u8_scratch_bytes.argtypes = [I, I, I, I, I, I, I]
@@ -107,7 +108,7 @@ def lib():
               "ssm_frames_from_u8", "ssm_frames_to_u8", "ssm_synthesize_host",
               "ssm_upsample2x_nhwc", "ssm_bias_leaky_nhwc", "ssm_avgpool2_nhwc",
               "ssm_upsample2x_bwd_nhwc", "ssm_leaky_bwd_nhwc", "ssm_avgpool2_bwd_nhwc", "ssm_bias_leaky_nhwc_to",
-              "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8",
+              "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8", "ssm_flow_pack_fwd_q8_nhwc", "ssm_flow_pack_fwd_q8_lut", "ssm_fuse_flow_fwd_q8",
               "ssm_fuse_flow_fwd_q8_u8", "ssm_synthesize_host_u8"):
         getattr(L, n).restype = I
     _lib = L

@@ -914,24 +914,24 @@ int ssm_quads_from_u8(const unsigned char* src, long long src_frame_stride, int 
 extern "C++" {
 template <typename T, int MODE>
 static int flow_pack_q8_launch(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
-                               const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
+                               const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6, const float* lut,
                                int B, int N, int H, int W, cudaStream_t s) {
     const Geom g = make_geom(H, W);
     const Norm3 nm = make_norm(norm6);
     const unsigned grid = q8_grid(B, H, W);
     if (!nhwc) {
         flow_pack_fwd_q8_kernel<T, MODE, T, false><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads, cview<T>(flow4),
-                                                                          t, mview<T>(out16), N, g, nm);
+                                                                          t, mview<T>(out16), N, g, nm, lut);
     } else if (out_dtype == SSM_DTYPE_BF16) {
         View<__nv_bfloat16> o; o.p = (__nv_bfloat16*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
         flow_pack_fwd_q8_kernel<T, MODE, __nv_bfloat16, true><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads,
-                                                                                     cview<T>(flow4), t, o, N, g, nm);
+                                                                                     cview<T>(flow4), t, o, N, g, nm, lut);
     } else {
         if constexpr (sizeof(T) != 4) return fail(SSM_ERR_UNSUPPORTED, "ssm_flow_pack_fwd_q8_nhwc: bf16 inputs with fp32 output is not built");
         else {
             View<float> o; o.p = (float*)nhwc; o.sb = (long long)N * 16 * H * W; o.sn = 16ll * H * W; o.sc = 1;
             flow_pack_fwd_q8_kernel<T, MODE, float, true><<<grid, Q8_THREADS, 0, s>>>(cview<T>(img6), (const uint4*)quads, cview<T>(flow4),
-                                                                                 t, o, N, g, nm);
+                                                                                 t, o, N, g, nm, lut);
         }
     }
     SSM_LAUNCH_CHECK("ssm_flow_pack_fwd_q8");
@@ -962,13 +962,19 @@ static int fuse_q8_dispatch(const void* quads, const ssm_tensor* flow4, const ss
 }  // extern "C++"
 
 static int flow_pack_q8_impl(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
-                             const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6,
+                             const ssm_tensor* out16, void* nhwc, int out_dtype, const float* norm6, const float* lut,
                              int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
     SSM_TRY(check_q8("ssm_flow_pack_fwd_q8", B, N, H, W, coord_mode, quads, norm6));
     if (dtype != SSM_DTYPE_F32 && dtype != SSM_DTYPE_BF16) return fail(SSM_ERR_DTYPE, "unknown dtype %d", dtype);
-    SSM_TRY(check_tensor(img6, "img6", dtype, true));
+    static const ssm_tensor no_frames = {nullptr, 0, 0, 0};
+    if (lut) {                                  // pass-through channels from the tables: the planar frames are not read
+        if (((uintptr_t)lut) % 4 != 0) return fail(SSM_ERR_ALIGN, "lut is not aligned to 4 bytes");
+        img6 = &no_frames;
+    } else {
+        SSM_TRY(check_tensor(img6, "img6", dtype, true));
+        SSM_TRY(check_pairable(img6, "img6", dtype));
+    }
     SSM_TRY(check_tensor(flow4, "flow4", dtype, true));
-    SSM_TRY(check_pairable(img6, "img6", dtype));
     SSM_TRY(check_pairable(flow4, "flow4", dtype));
     if (!t) return fail(SSM_ERR_NULL, "t is NULL");
     if (nhwc) {
@@ -981,23 +987,29 @@ static int flow_pack_q8_impl(const ssm_tensor* img6, const void* quads, const ss
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == SSM_DTYPE_F32)
         return coord_mode == SSM_COORD_DIV
-            ? flow_pack_q8_launch<float, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s)
-            : flow_pack_q8_launch<float, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s);
+            ? flow_pack_q8_launch<float, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, lut, B, N, H, W, s)
+            : flow_pack_q8_launch<float, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, lut, B, N, H, W, s);
     return coord_mode == SSM_COORD_DIV
-        ? flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s)
-        : flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, B, N, H, W, s);
+        ? flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_DIV>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, lut, B, N, H, W, s)
+        : flow_pack_q8_launch<__nv_bfloat16, SSM_COORD_RCP>(img6, quads, flow4, t, out16, nhwc, out_dtype, norm6, lut, B, N, H, W, s);
 }
 
 int ssm_flow_pack_fwd_q8(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                          const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
-    return flow_pack_q8_impl(img6, quads, flow4, t, out16, nullptr, dtype, norm6, B, N, H, W, dtype, coord_mode, stream);
+    return flow_pack_q8_impl(img6, quads, flow4, t, out16, nullptr, dtype, norm6, nullptr, B, N, H, W, dtype, coord_mode, stream);
 }
 
 int ssm_flow_pack_fwd_q8_nhwc(const ssm_tensor* img6, const void* quads, const ssm_tensor* flow4, const float* t,
                               void* out16_nhwc, int out_dtype, const float* norm6, int B, int N, int H, int W,
                               int dtype, int coord_mode, void* stream) {
     if (!out16_nhwc) return fail(SSM_ERR_NULL, "out16_nhwc is NULL");
-    return flow_pack_q8_impl(img6, quads, flow4, t, nullptr, out16_nhwc, out_dtype, norm6, B, N, H, W, dtype, coord_mode, stream);
+    return flow_pack_q8_impl(img6, quads, flow4, t, nullptr, out16_nhwc, out_dtype, norm6, nullptr, B, N, H, W, dtype, coord_mode, stream);
+}
+
+int ssm_flow_pack_fwd_q8_lut(const void* quads, const float* lut, const ssm_tensor* flow4, const float* t,
+                             const ssm_tensor* out16, const float* norm6, int B, int N, int H, int W, int dtype, int coord_mode, void* stream) {
+    if (!lut) return fail(SSM_ERR_NULL, "lut is NULL");
+    return flow_pack_q8_impl(nullptr, quads, flow4, t, out16, nullptr, dtype, norm6, lut, B, N, H, W, dtype, coord_mode, stream);
 }
 
 static int fuse_q8_impl(const void* quads, const ssm_tensor* flow4, const ssm_tensor* out5, int out5_dtype, const float* t,

@@ -74,12 +74,49 @@ def _check_quads(quads, B, H, W, device):
     return ctypes.c_void_p(quads.data_ptr())
 
 
-def flow_pack(img6, quads, flow4, t, norm, n_timesteps=1, coord_mode=None, out=None, channels_last_dtype=None):
+def _flow_pack_from_tables(quads, lut, flow4, t, norm, n_timesteps, coord_mode, out):
+    """flow_pack with img6=None: the pass-through channels are looked up from the tables' own bytes (ssm_flow_pack_fwd_q8_lut)"""
+    if not flow4.is_cuda or flow4.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("q8.flow_pack: flow4 must be a CUDA tensor, fp32 or bf16 (no CPU fallback)")
+    if torch.is_grad_enabled() and flow4.requires_grad:
+        raise RuntimeError("q8.flow_pack is inference-only; use flow_pack on fp32 frames for a differentiable result")
+    if not (isinstance(lut, torch.Tensor) and lut.is_cuda and lut.device == flow4.device and lut.dtype == torch.float32
+            and tuple(lut.shape) == (3, 256) and lut.is_contiguous()):
+        raise RuntimeError("q8.flow_pack: lut must be the contiguous 3 x 256 fp32 normalisation table on %s "
+                           "(ssm_b200.normalisation_lut)" % flow4.device)
+    flow4 = _abi.dense_planes(flow4.detach())
+    B, C4, H, W = flow4.shape
+    N = int(n_timesteps)
+    if C4 != 4:
+        raise RuntimeError("compute_inputs: expected flow B x 4 x H x W, got %s" % (tuple(flow4.shape),))
+    qp = _check_quads(quads, B, H, W, flow4.device)
+    tvec = _t_vector(t, B * N, flow4.device)
+    if out is None:
+        out = torch.empty((B, N, 16, H, W), dtype=flow4.dtype, device=flow4.device)
+    elif tuple(out.shape) != (B, N, 16, H, W) or out.dtype != flow4.dtype or not out.is_contiguous():
+        raise RuntimeError("q8.flow_pack: out= must be a contiguous %s %s tensor" % (flow4.dtype, (B, N, 16, H, W)))
+    with torch.cuda.device(flow4.device):
+        rc = _abi.lib().ssm_flow_pack_fwd_q8_lut(qp, ctypes.c_void_p(lut.data_ptr()), _abi.ref(_abi.desc(flow4, False)),
+                                                 ctypes.c_void_p(tvec.data_ptr()), _abi.ref(_abi.desc(out, True)), norm,
+                                                 B, N, H, W, _abi.dtype_code(flow4), _resolve_mode(coord_mode),
+                                                 _abi.stream_ptr(flow4.device))
+    _abi.check(rc, "ssm_flow_pack_fwd_q8_lut")
+    return out
+
+
+def flow_pack(img6, quads, flow4, t, norm, n_timesteps=1, coord_mode=None, out=None, channels_last_dtype=None, lut=None):
     """compute_inputs (flow_interpolation.py:338-372) for n_timesteps times of every pair, warping through the
     entry tables: img6 B x 6 x H x W fp32 (normalised frames; read for the pass-through channels only),
     quads = tables of the same 2B frames, flow4 B x 4 x H x W -> B x N x 16 x H x W (fp32, or bf16 storage throughout).
     channels_last_dtype (torch.float32 / torch.bfloat16): write B x N x H x W x 16 in that dtype instead (returned as a
-    B x N x 16 x H x W view), the layout a channels-last stage-2 U-Net consumes."""
+    B x N x 16 x H x W view), the layout a channels-last stage-2 U-Net consumes.
+    img6=None with lut= (the 3 x 256 table of normalisation_lut that made the frames): the pass-through channels are
+    looked up from the tables' own bytes and no planar frame is read -- the same values when the frames were padded with
+    byte 0 before normalising (prepare(..., pad_values=lut[:, 0])), 5 % less DRAM traffic (planar layout only)."""
+    if img6 is None:
+        if lut is None or channels_last_dtype is not None:
+            raise RuntimeError("q8.flow_pack: img6=None needs lut= and the planar layout")
+        return _flow_pack_from_tables(quads, lut, flow4, t, norm, n_timesteps, coord_mode, out)
     if not (img6.is_cuda and flow4.is_cuda) or img6.dtype not in (torch.float32, torch.bfloat16) or flow4.dtype != img6.dtype:
         raise RuntimeError("q8.flow_pack: img6 and flow4 must be CUDA tensors of one storage dtype, fp32 or bf16 (no CPU fallback)")
     if torch.is_grad_enabled() and (img6.requires_grad or flow4.requires_grad):

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_error_string():
-    assert ssm_b200.abi_version() == 7
+    assert ssm_b200.abi_version() == 8
     assert isinstance(_abi.lib().ssm_last_error(), bytes)
 
 

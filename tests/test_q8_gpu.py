@@ -43,6 +43,10 @@ def test_reference_fixture(name):
     assert_close_fp32(in16, d["in16"], "compute_inputs from uint8 frames")
     frames = q8.fuse_from_flow(quads, flow4, out5, t, norm)
     assert_close_fp32(frames, d["frames"], "compute_output_image from uint8 frames")
+    # the table-only form (no planar frames read): the reference's own pass-through channels, bit for bit
+    lut = ssm_b200.normalisation_lut(device="cpu").to(DEV)
+    in16_t = q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, lut=lut)
+    assert torch.equal(in16_t, in16), "compute_inputs with the pass-through channels from the tables differs"
 
 
 def _u8_images(F, h, w, seed, smooth):
@@ -83,6 +87,34 @@ def test_q8_vs_c_oracle(mode_name, mode, B, N, h, w, kind, smooth, flow_px):
         r3 = c_oracle.compute_output_image(img6_c, r16, out5[:, n].contiguous(), t[:, n], coord_mode=mode)
         worst3 = max(worst3, assert_close_fp32(frames[:, n], r3, "q8 fuse n=%d" % n))
     print("q8 vs C oracle %s %dx%d: warped %.2e fused %.2e" % (mode_name, H, W, worst16, worst3))
+
+
+@pytest.mark.parametrize("coord_mode", ["cpu", "cuda"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_q8_flow_pack_from_tables_is_bit_identical(dtype, coord_mode):
+    """ssm_flow_pack_fwd_q8_lut: the pass-through channels looked up from the tables' own bytes instead of read from the
+    planar frames -- every one of the 16 channels must be the same bits (random bytes, a ragged source padded to a
+    multiple of 32, so the padding columns and rows are covered), in both storage types."""
+    B, N, h, w = 2, 3, 45, 78
+    images = _u8_images(2 * B, h, w, seed=77, smooth=False).to(DEV)
+    lut = ssm_b200.normalisation_lut(device=DEV)
+    planar, quads, norm, _ = q8.prepare(images, order="rgb", lut=lut)
+    H, W = planar.shape[-2:]
+    img6 = planar.view(B, 6, H, W).to(dtype)
+    flow4 = synthetic.flows(B, H, W, 4, flow_px=9.0, seed=78, device=DEV).to(dtype)
+    t = synthetic.timesteps(B, N, device=DEV)
+    a = q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N, coord_mode=coord_mode)
+    b = q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, coord_mode=coord_mode, lut=lut)
+    assert a.dtype == b.dtype == dtype and torch.equal(a, b)
+    buf = torch.empty_like(a)
+    assert q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, coord_mode=coord_mode, lut=lut, out=buf) is buf
+    assert torch.equal(buf, a)
+    with pytest.raises(RuntimeError, match="lut"):
+        q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N)
+    with pytest.raises(RuntimeError, match="lut"):
+        q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, lut=lut[:, :128].contiguous())
+    with pytest.raises(RuntimeError, match="planar"):
+        q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, lut=lut, channels_last_dtype=torch.bfloat16)
 
 
 def test_q8_layouts_and_bf16_unet_output():

@@ -56,6 +56,7 @@ def main():
                 "quads_from_u8": timed(lambda: q8.quads_from_u8(images, order="rgb")),
                 "frames_from_u8_planar": timed(lambda: ssm_b200.frames_from_u8(images, order="rgb", lut=lut, pad_values=pads)),
                 "q8_flow_pack": timed(lambda: q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=N, out=in16)),
+                "q8_flow_pack_from_tables": timed(lambda: q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=N, out=in16, lut=lut)),
                 "q8_fuse": timed(lambda: q8.fuse_from_flow(quads, flow4, out5, t, norm, out=out3)),
                 "q8_fuse_bf16_out5": timed(lambda: q8.fuse_from_flow(quads, flow4, y16, t, norm, out=out3)),
                 "q8_fuse_to_u8": timed(lambda: q8.fuse_from_flow_to_u8(quads, flow4, out5, t, norm, out=out_u8)),

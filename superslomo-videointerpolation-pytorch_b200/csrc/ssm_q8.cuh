@@ -14,8 +14,9 @@
 // so it commutes with the interpolation:  sum_k w_k (a b_k + c) = a sum_k w_k b_k + c sum_{k in frame} w_k
 // -- within 1e-6 of interpolating the normalised fp32 values as the reference does (zeros padding: taps
 // outside the frame drop out of both sums).  The pass-through channels of compute_inputs (I0, I1 at the pixel,
-// flow_interpolation.py:364-367) are read from the planar normalised frames (bit-exact with the reference's
-// normalisation, ssm_frames_from_u8).
+// flow_interpolation.py:364-367) are bit-exact with the reference's normalisation either way they are obtained: read
+// from the planar normalised frames (ssm_frames_from_u8), or looked up from the tables' own bytes through the 3 x 256
+// table that kernel applies (lut != NULL: the planar frames are then not read at all).
 //
 // One thread owns TWO horizontally adjacent pixels: every streaming access is 8 bytes per lane (a warp moves
 // 256 contiguous bytes per plane row: 6.96 TB/s instead of 5.70 TB/s for the 16-plane store pattern of

@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 PATH_ENTRY_POINTS = ["ssm_pack_frames", "ssm_flow_pack_fwd", "ssm_flow_pack_bwd", "ssm_fuse_loss_fwd", "ssm_fuse_loss_bwd",
                      "ssm_fuse_flow_fwd", "ssm_fuse_flow_bwd", "ssm_fuse_fwd", "ssm_fuse_bwd", "ssm_warp_fwd", "ssm_warp_bwd",
                      "ssm_flow_pack_fwd_nhwc", "ssm_fuse_flow_fwd_mixed", "ssm_quads_from_u8", "ssm_flow_pack_fwd_q8",
-                     "ssm_flow_pack_fwd_q8_nhwc", "ssm_fuse_flow_fwd_q8", "ssm_fuse_flow_fwd_q8_u8", "ssm_frames_from_u8",
+                     "ssm_flow_pack_fwd_q8_nhwc", "ssm_flow_pack_fwd_q8_lut", "ssm_fuse_flow_fwd_q8", "ssm_fuse_flow_fwd_q8_u8", "ssm_frames_from_u8",
                      "ssm_frames_to_u8"]
 
 
@@ -259,8 +259,7 @@ def c5_4k_sharded(world, rank, dev, steps=5, warmup=3, H_in=2160, W_in=3840, n_t
         e[1].record()
         with torch.no_grad():
             planar, quads, norm, _ = q8.prepare(images, order="rgb", lut=lut, pad_values=pads)
-            img6 = planar.view(1, 6, H, W)
-            q8.flow_pack(img6, quads, flow4, t, norm, n_timesteps=n, out=in16)
+            q8.flow_pack(None, quads, flow4, t, norm, n_timesteps=n, out=in16, lut=lut)     # pass-through channels from the tables
             q8.fuse_from_flow(quads, flow4, out5, t, norm, out=frames)
         e[2].record()
         ev.append(e)

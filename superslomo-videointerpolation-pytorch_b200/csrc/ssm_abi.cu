@@ -161,6 +161,8 @@ struct WarpBwd {
         const long long npx = (long long)H * W;
         long long* acc = want_img ? (long long*)((char*)ws + HDR_BYTES) : nullptr;
         if (want_img) {
+            if ((long long)B * C * finalize_chunks(npx) > 2147483647ll)      // before anything is launched
+                return fail(SSM_ERR_SHAPE, "ssm_warp_bwd: B*C*H*W too large for one finalise launch");
             cudaError_t e = cudaMemsetAsync(ws, 0, HDR_BYTES + sizeof(long long) * B * C * npx, s);
             if (e != cudaSuccess) return cuda_fail(e, "ssm_warp_bwd memset");
         }
@@ -186,7 +188,6 @@ struct WarpBwd {
                 warp_scatter_kernel<T, MODE><<<tile_grid(B, H, W), TILE_THREADS, 0, s>>>(
                     cview<T>(gout), cview<T>(flow), acc, C, g, hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (scatter)");
-            if ((long long)B * C * finalize_chunks(npx) > 2147483647ll) return fail(SSM_ERR_SHAPE, "ssm_warp_bwd: B*C*H*W too large for one finalise launch");
             scatter_finalize_kernel<T><<<(unsigned)(B * C) * finalize_chunks(npx), FIN_THREADS, 0, s>>>(acc, nullptr, mview<T>(gimg), C, npx, finalize_chunks(npx), hdr, cb);
             SSM_LAUNCH_CHECK("ssm_warp_bwd (finalize)");
         }

@@ -269,7 +269,7 @@ __device__ __forceinline__ void sts2(__nv_bfloat16* p, float a, float b) {
 // read as aligned 32-bit words cut up with funnel shifts (10 loads per thread instead of 30: 0.41 ms), one entry per
 // thread with fully coalesced 16-byte stores (0.43 ms; 0.41 with a 2-D grid and no 64-bit divisions), streaming stores
 // (no change), both texel rows staged in shared memory with coalesced word loads and one entry per lane (0.43 ms with one
-// tile per CTA, 0.53 ms with persistent CTAs; profiles/r04b, r04c).
+// tile per CTA, 0.53 ms with persistent CTAs; profiles/r04b, r04c); 32-bit instead of 64-bit index divisions (no change, r04w).
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 quads_from_u8_kernel(const unsigned char* __restrict__ src, long long src_frame_stride, int src_row_stride, int bgr,
